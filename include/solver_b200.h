@@ -1,0 +1,136 @@
+/* solver_b200.h -- C ABI of the B200-native sparse direct solver backend for russell_sparse.
+ *
+ * Drop-in seam: these five entry points have exactly the shape of the reference's cuDSS shim
+ *   russell_sparse/src/solver_cudss.rs:25-52        (the Rust `extern "C"` block that binds them)
+ *   russell_sparse/c_code/interface_cudss.cu:62-566 (solver_cudss_{new,drop,initialize,factorize,solve})
+ * so a `SolverB200` Rust wrapper cloned from `SolverCUDSS` (see bindings/rust/solver_b200.rs and
+ * INTEGRATION.md) binds them without any change to LinSolTrait callers (russell_ode Radau5/BwEuler,
+ * russell_pde, russell_nonlin).  Status codes follow russell_sparse/c_code/constants.h:5-36.
+ *
+ * Matrix layout (same as the reference's CSR contract, russell_sparse/src/csr_matrix.rs:359-480):
+ *   CSR, 0-based int32 indices, duplicates already summed, nnz = row_pointers[ndim]; `values` may be longer
+ *   than nnz (only the first nnz entries are read).  With general_symmetric=1 only the LOWER triangle is given.
+ * Host arrays are borrowed for the duration of a call; nothing is retained.  All calls are synchronous.
+ * One handle is used by one thread at a time; distinct handles may be driven concurrently from different
+ * threads (russell_ode/src/radau5.rs:270-296) and a handle may migrate between threads between calls.
+ */
+#ifndef SOLVER_B200_H
+#define SOLVER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ------------------------------------------------------------------------------------ */
+#define B200_SUCCESSFUL_EXIT 0                   /* constants.h:5  SUCCESSFUL_EXIT */
+#define B200_ERROR_SINGULAR 1                    /* parity with UMFPACK status 1 "Matrix is singular" (solver_umfpack.rs:492) */
+#define B200_ERROR_NULL_POINTER 100000           /* constants.h:6  */
+#define B200_ERROR_MALLOC 200000                 /* constants.h:7  */
+#define B200_ERROR_VERSION 300000                /* constants.h:8  */
+#define B200_ERROR_NOT_AVAILABLE 400000          /* constants.h:9  (no CUDA device / kernels not loadable) */
+#define B200_ERROR_NEED_INITIALIZATION 500000    /* constants.h:10 */
+#define B200_ERROR_NEED_FACTORIZATION 600000     /* constants.h:11 */
+#define B200_ERROR_ALREADY_INITIALIZED 700000    /* constants.h:12 */
+#define B200_ERROR_CUDA_MALLOC 100               /* constants.h:22 */
+#define B200_ERROR_CUDA_MEMCPY 200               /* constants.h:23 */
+#define B200_ERROR_CUDA_SYNCHRONIZE 300          /* constants.h:24 */
+#define B200_ERROR_ANALYSIS 700                  /* phase offset like ERROR_CUDSS_SYM_FACTORIZATION; +1 structurally singular, +2 invalid input */
+#define B200_ERROR_NUM_FACTORIZATION 800         /* phase offset like ERROR_CUDSS_NUM_FACTORIZATION; +1 kernel launch failure, +2 non-finite values */
+#define B200_ERROR_SOLVE 900                     /* phase offset like ERROR_CUDSS_SOLVE; +1 kernel launch failure, +7 refinement failed */
+
+/* ---- option values (same integers the Rust maps for cuDSS send, solver_cudss.rs:393-466) ------------------- */
+#define B200_ORDERING_DEFAULT 0  /* nested dissection */
+#define B200_ORDERING_AMD 3      /* minimum degree family (small problems: exact minimum degree) */
+#define B200_ORDERING_ND 4
+#define B200_ORDERING_NONE 5     /* natural order */
+#define B200_MATCHING_NONE 0
+#define B200_MATCHING_MAX_DIAG_PRODUCT 5
+#define B200_MATCHING_AUTO 6
+
+struct InterfaceB200; /* opaque: stream, device buffers, symbolic plan, numeric factors */
+
+/* replaces solver_cudss_new (interface_cudss.cu:62-123): NULL on failure (no device, out of memory) */
+struct InterfaceB200 *solver_b200_new(void);
+
+/* replaces solver_cudss_drop (interface_cudss.cu:126-171): NULL-safe, releases everything */
+void solver_b200_drop(struct InterfaceB200 *solver);
+
+/* replaces solver_cudss_initialize (interface_cudss.cu:190-396): once per structure.
+ * Runs the host analysis (matching/scaling, ordering, elimination tree, supernodes, front plan) and
+ * uploads the plan.  pivot_epsilon<=0, refinement_nstep<0 and hybrid_memory_factor<=0 select defaults
+ * (hybrid memory is accepted and ignored: 180 GB of HBM3e hold the factors). */
+int32_t solver_b200_initialize(struct InterfaceB200 *solver,
+                               int32_t ordering, int32_t matching, int32_t pivoting,
+                               double pivot_epsilon, int32_t refinement_nstep, double hybrid_memory_factor,
+                               int32_t verbose, int32_t general_symmetric, int32_t positive_definite,
+                               int32_t ndim, const int32_t *row_pointers, const int32_t *col_indices,
+                               const double *values);
+
+/* replaces solver_cudss_factorize (interface_cudss.cu:406-501): numeric LU of new values, same pattern */
+int32_t solver_b200_factorize(struct InterfaceB200 *solver, int32_t *effective_matching,
+                              int32_t *effective_pivoting, int32_t verbose, const double *values);
+
+/* replaces solver_cudss_solve (interface_cudss.cu:510-566): x <- A^{-1} rhs with iterative refinement */
+int32_t solver_b200_solve(struct InterfaceB200 *solver, double *x, const double *rhs, int32_t verbose);
+
+/* ---- extensions (not part of the reference's five; used by bench.py, tests and the stats block) -------------- */
+
+/* device-resident variants: pointers are DEVICE pointers on the handle's device; no host<->device copies */
+int32_t solver_b200_factorize_device(struct InterfaceB200 *solver, const double *d_values);
+int32_t solver_b200_solve_device(struct InterfaceB200 *solver, double *d_x, const double *d_rhs);
+
+/* residual r = rhs - A x with the CSR SpMV kernel; returns ||r||_2 / ||rhs||_2 through *rel_residual
+ * (russell's VerifyLinSys / the north-star accuracy metric).  Host pointers. */
+int32_t solver_b200_residual(struct InterfaceB200 *solver, const double *x, const double *rhs, double *rel_residual);
+
+/* y <- A x on the device (host pointers; SpMV kernel parity tests) */
+int32_t solver_b200_spmv(struct InterfaceB200 *solver, double *y, const double *x);
+
+/* determinant as mantissa * 10^exponent (StatsLinSol / solver_umfpack.rs:141-152 convention) */
+int32_t solver_b200_determinant(struct InterfaceB200 *solver, double *coefficient, double *exponent);
+
+/* stats: fills out[0..n_out-1]; see B200_STAT_* */
+#define B200_STAT_NNODES 0
+#define B200_STAT_NLEVELS 1
+#define B200_STAT_NNZ_L 2
+#define B200_STAT_NNZ_U 3
+#define B200_STAT_FLOPS 4
+#define B200_STAT_FAC_BYTES 5
+#define B200_STAT_CB_BYTES 6
+#define B200_STAT_MAX_FRONT 7
+#define B200_STAT_T_ORDER_S 8
+#define B200_STAT_T_SYMBOLIC_S 9
+#define B200_STAT_N_PERTURBED 10
+#define B200_STAT_LAST_REL_RESIDUAL 11
+#define B200_STAT_LAST_REFINE_STEPS 12
+#define B200_STAT_MS_FACTORIZE_DEVICE 13   /* CUDA-event time of the last numeric factorization (kernels only) */
+#define B200_STAT_MS_SOLVE_DEVICE 14       /* CUDA-event time of the last solve incl. refinement (kernels only) */
+#define B200_STAT_MS_SPTRSV_DEVICE 15      /* CUDA-event time of the last forward+backward sweep */
+#define B200_STAT_MS_SPMV_DEVICE 16        /* CUDA-event time of the last residual SpMV */
+#define B200_STAT_LAUNCHES_FACTORIZE 17    /* kernels launched per factorization */
+#define B200_STAT_LAUNCHES_SOLVE 18        /* kernels launched by the last solve */
+#define B200_STAT_SPTRSV_BYTES 19          /* algorithmic bytes of one forward+backward sweep */
+#define B200_STAT_SPMV_BYTES 20            /* algorithmic bytes of one SpMV */
+#define B200_STAT_MATCHED 21
+#define B200_STAT_T_MATCH_S 22
+#define B200_STAT_COUNT 23
+int32_t solver_b200_get_stats(struct InterfaceB200 *solver, double *out, int32_t n_out);
+
+/* tuning knobs, must be called before initialize: key in {"panel_width","nd_leaf","use_graph","ir_tol",
+ * "schur_variant","device"} */
+int32_t solver_b200_set_option(struct InterfaceB200 *solver, const char *key, double value);
+
+/* debug/parity: copies factor panels (fac), pivot-block inverses (dinv) and local pivots to host buffers
+ * sized by get_stats (FAC_BYTES/8 ...); any pointer may be NULL */
+int32_t solver_b200_debug_copy_factors(struct InterfaceB200 *solver, double *fac, int64_t fac_len,
+                                       double *dinv, int64_t dinv_len, int32_t *lperm, int64_t n);
+
+/* library identification string (static storage) */
+const char *solver_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOLVER_B200_H */

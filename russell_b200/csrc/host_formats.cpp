@@ -1,0 +1,201 @@
+// host_formats.cpp -- host-side data formats either side of the solver (C ABI, no CUDA needed).
+//
+// These are what the reference's Rust wrapper does before crossing the FFI:
+//   b200_coo_to_csr / b200_coo_to_csc  <- CsrMatrix::update_from_coo (russell_sparse/src/csr_matrix.rs:359-480)
+//                                         CscMatrix::update_from_coo (russell_sparse/src/csc_matrix.rs:365-505)
+//       contract: duplicates (i,j) are SUMMED in their order of appearance, rows are sorted by column,
+//       final nnz = pointers[n] may be smaller than the triplet count.
+//   b200_mm_read_*                     <- read_matrix_market (russell_sparse/src/read_matrix_market.rs:346-475)
+//       coordinate real general/symmetric, 1-based -> 0-based, MMsym handling of symmetric files.
+// The implementation is a stable two-key counting/merge sort, not the reference's workspace scheme.
+#include <algorithm>
+#include <cctype>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+extern "C" {
+
+// Converts triplets (with duplicates) to compressed rows.  ptr has nmajor+1 entries; idx/val have nnz slots,
+// of which the first ptr[nmajor] are valid on return.  Returns 0, or a negative error:
+//   -1 index out of range, -2 nnz < 1
+int32_t b200_coo_to_csr(int32_t nrow, int32_t ncol, int32_t nnz, const int32_t* ai, const int32_t* aj, const double* ax,
+                        int32_t* ptr, int32_t* idx, double* val) {
+    if (nnz < 1) return -2;
+    std::vector<int32_t> start(nrow + 1, 0);
+    for (int32_t k = 0; k < nnz; k++) {
+        if (ai[k] < 0 || ai[k] >= nrow || aj[k] < 0 || aj[k] >= ncol) return -1;
+        start[ai[k] + 1]++;
+    }
+    for (int32_t i = 0; i < nrow; i++) start[i + 1] += start[i];
+    // stable bucket by row: order[] lists triplet ids row by row, in order of appearance
+    std::vector<int32_t> order(nnz), fill(start.begin(), start.end() - 1);
+    for (int32_t k = 0; k < nnz; k++) order[fill[ai[k]]++] = k;
+    int32_t out = 0;
+    ptr[0] = 0;
+    for (int32_t i = 0; i < nrow; i++) {
+        int32_t* b = order.data() + start[i];
+        int32_t* e = order.data() + start[i + 1];
+        std::stable_sort(b, e, [&](int32_t x, int32_t y) { return aj[x] < aj[y]; });
+        for (int32_t* q = b; q != e;) {
+            const int32_t j = aj[*q];
+            double s = ax[*q];
+            for (++q; q != e && aj[*q] == j; ++q) s += ax[*q]; // duplicates: summed in order of appearance
+            idx[out] = j;
+            val[out] = s;
+            out++;
+        }
+        ptr[i + 1] = out;
+    }
+    return 0;
+}
+
+int32_t b200_coo_to_csc(int32_t nrow, int32_t ncol, int32_t nnz, const int32_t* ai, const int32_t* aj, const double* ax,
+                        int32_t* ptr, int32_t* idx, double* val) {
+    // columns of A are the rows of A^T; the duplicate-summation order (order of appearance) is unchanged
+    return b200_coo_to_csr(ncol, nrow, nnz, aj, ai, ax, ptr, idx, val);
+}
+
+// ---- Matrix Market ----------------------------------------------------------------------------------
+// error codes (the Python/Rust side maps them to the reference's messages):
+enum {
+    MM_OK = 0,
+    MM_CANNOT_OPEN = 1,
+    MM_EMPTY = 2,
+    MM_HDR_START = 3,      // "the header (first line) must start with %%MatrixMarket"
+    MM_HDR_NO_KEYWORD = 4, // "cannot find the keyword %%MatrixMarket on the first line"
+    MM_HDR_OPT1 = 5,       // first option must be "matrix"
+    MM_HDR_OPT1_MISSING = 6,
+    MM_HDR_OPT2 = 7, // second option must be "coordinate"
+    MM_HDR_OPT2_MISSING = 8,
+    MM_HDR_OPT3 = 9, // third option must be "real" or "complex"
+    MM_HDR_OPT3_MISSING = 10,
+    MM_HDR_OPT4 = 11, // fourth option must be general/symmetric/Hermitian
+    MM_HDR_OPT4_MISSING = 12,
+    MM_HDR_HERMITIAN_REAL = 13,
+    MM_DIM_ROWS = 14, // cannot parse number of rows
+    MM_DIM_NO_COLS = 15,
+    MM_DIM_COLS = 16,
+    MM_DIM_NO_NNZ = 17,
+    MM_DIM_NNZ = 18,
+    MM_DIM_INVALID = 19, // found invalid (zero or negative) dimensions
+    MM_VAL_TOO_MANY = 20,
+    MM_VAL_I = 21,
+    MM_VAL_NO_J = 22,
+    MM_VAL_J = 23,
+    MM_VAL_NO_A = 24,
+    MM_VAL_A = 25,
+    MM_VAL_INDEX = 26,     // found an invalid index
+    MM_VAL_MISSING = 27,   // not all values have been found
+    MM_SYM_RECT = 28,      // symmetric matrices must be square
+    MM_COMPLEX = 29,       // complex files are handled by the complex twin (not in this backend yet)
+    MM_NO_DIMS = 30,
+};
+
+static bool parse_i64(const std::string& s, long long& out) {
+    if (s.empty()) return false;
+    char* end = nullptr;
+    out = strtoll(s.c_str(), &end, 10);
+    return end && *end == '\0';
+}
+static bool parse_f64(const std::string& s, double& out) {
+    if (s.empty()) return false;
+    char* end = nullptr;
+    out = strtod(s.c_str(), &end);
+    return end && *end == '\0';
+}
+static std::vector<std::string> split_ws(const std::string& line) {
+    std::vector<std::string> t;
+    std::istringstream is(line);
+    std::string w;
+    while (is >> w) t.push_back(w);
+    return t;
+}
+
+static int parse_header(const std::string& line, bool& is_complex, bool& is_sym) {
+    std::vector<std::string> t = split_ws(line);
+    if (t.empty()) return MM_HDR_NO_KEYWORD;
+    if (t[0] != "%%MatrixMarket") return MM_HDR_START;
+    if (t.size() < 2) return MM_HDR_OPT1_MISSING;
+    if (t[1] != "matrix") return MM_HDR_OPT1;
+    if (t.size() < 3) return MM_HDR_OPT2_MISSING;
+    if (t[2] != "coordinate") return MM_HDR_OPT2;
+    if (t.size() < 4) return MM_HDR_OPT3_MISSING;
+    if (t[3] == "real") is_complex = false;
+    else if (t[3] == "complex") is_complex = true;
+    else return MM_HDR_OPT3;
+    if (t.size() < 5) return MM_HDR_OPT4_MISSING;
+    if (t[4] == "general") is_sym = false;
+    else if (t[4] == "symmetric") is_sym = true;
+    else if (t[4] == "Hermitian") {
+        if (!is_complex) return MM_HDR_HERMITIAN_REAL;
+        is_sym = false;
+    } else return MM_HDR_OPT4;
+    return MM_OK;
+}
+
+// Reads a coordinate/real file.  handling: 0 LeaveAsLower, 1 SwapToUpper, 2 MakeItFull (enums.rs:45-67).
+// Pass ai=aj=NULL to query: info[0..4] = nrow, ncol, nnz_file, symmetric(0/1), max_entries (capacity to allocate).
+// With arrays: fills triplets, info[5] = number of triplets written.
+int32_t b200_mm_read(const char* path, int32_t handling, int64_t* info, int32_t* ai, int32_t* aj, double* ax, int64_t cap) {
+    std::ifstream in(path);
+    if (!in.good()) return MM_CANNOT_OPEN;
+    std::string line;
+    if (!std::getline(in, line)) return MM_EMPTY;
+    bool is_complex = false, is_sym = false;
+    int rc = parse_header(line, is_complex, is_sym);
+    if (rc != MM_OK) return rc;
+    long long m = 0, n = 0, nnz = 0;
+    bool have_dims = false;
+    while (std::getline(in, line)) {
+        std::vector<std::string> t = split_ws(line);
+        if (t.empty() || t[0][0] == '%') continue;
+        if (!parse_i64(t[0], m)) return MM_DIM_ROWS;
+        if (t.size() < 2) return MM_DIM_NO_COLS;
+        if (!parse_i64(t[1], n)) return MM_DIM_COLS;
+        if (t.size() < 3) return MM_DIM_NO_NNZ;
+        if (!parse_i64(t[2], nnz)) return MM_DIM_NNZ;
+        if (m < 1 || n < 1 || nnz < 1) return MM_DIM_INVALID;
+        have_dims = true;
+        break;
+    }
+    if (!have_dims) return MM_NO_DIMS;
+    if (is_sym && m != n) return MM_SYM_RECT;
+    if (is_complex) return MM_COMPLEX;
+    long long maxent = (is_sym && handling == 2) ? 2 * nnz : nnz;
+    info[0] = m, info[1] = n, info[2] = nnz, info[3] = is_sym ? 1 : 0, info[4] = maxent;
+    if (!ai || !aj || !ax) return MM_OK;
+    long long pos = 0, w = 0;
+    while (std::getline(in, line)) {
+        std::vector<std::string> t = split_ws(line);
+        if (t.empty() || t[0][0] == '%') continue;
+        if (pos == nnz) return MM_VAL_TOO_MANY;
+        long long i, j;
+        double a;
+        if (!parse_i64(t[0], i)) return MM_VAL_I;
+        if (t.size() < 2) return MM_VAL_NO_J;
+        if (!parse_i64(t[1], j)) return MM_VAL_J;
+        if (t.size() < 3) return MM_VAL_NO_A;
+        if (!parse_f64(t[2], a)) return MM_VAL_A;
+        i -= 1, j -= 1;
+        if (i < 0 || i >= m || j < 0 || j >= n) return MM_VAL_INDEX;
+        pos++;
+        if (w + 2 > cap && w + 1 > cap) return MM_VAL_TOO_MANY;
+        if (is_sym && handling == 1) {
+            ai[w] = (int32_t)j, aj[w] = (int32_t)i, ax[w] = a, w++;
+        } else {
+            ai[w] = (int32_t)i, aj[w] = (int32_t)j, ax[w] = a, w++;
+            if (is_sym && handling == 2 && i != j) ai[w] = (int32_t)j, aj[w] = (int32_t)i, ax[w] = a, w++;
+        }
+    }
+    if (pos != nnz) return MM_VAL_MISSING;
+    info[5] = w;
+    return MM_OK;
+}
+
+} // extern "C"

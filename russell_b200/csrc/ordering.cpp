@@ -1,0 +1,328 @@
+// ordering.cpp -- fill-reducing orderings written from scratch (no METIS/AMD library is linked).
+//
+// Role in the reference: UMFPACK picks AMD/COLAMD inside umfpack_di_symbolic
+// (russell_sparse/c_code/interface_umfpack.c:104-109); cuDSS defaults to METIS nested dissection
+// (russell_sparse/src/solver_cudss.rs:401-404).  We use automatic nested dissection (BFS level-structure
+// separators from a pseudo-peripheral vertex, trimmed and greedily refined) down to small subdomains that
+// are ordered by exact minimum degree.  Nested dissection gives the wide, balanced assembly tree the GPU wants.
+#include "plan.hpp"
+
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+namespace b200 {
+
+namespace {
+
+struct NdCtx {
+    const Graph& g;
+    int leaf;
+    std::vector<int> label; // partition id of every vertex
+    std::vector<int> lvl;   // BFS level scratch, -1 = not visited
+    std::vector<int> loc;   // local index scratch
+    int next_id = 1;
+    int* out = nullptr;     // perm (new -> old)
+    explicit NdCtx(const Graph& gg, int lf) : g(gg), leaf(lf), label(gg.n, 0), lvl(gg.n, -1), loc(gg.n, -1) {}
+};
+
+// BFS restricted to label == id.  `order` receives the visit order, `lptr` the level offsets.
+void bfs_levels(NdCtx& c, int id, int start, std::vector<int>& order, std::vector<int>& lptr) {
+    order.clear();
+    lptr.clear();
+    order.push_back(start);
+    c.lvl[start] = 0;
+    lptr.push_back(0);
+    size_t head = 0;
+    int cur = 0;
+    while (head < order.size()) {
+        int v = order[head];
+        if (c.lvl[v] != cur) {
+            cur = c.lvl[v];
+            lptr.push_back((int)head);
+        }
+        head++;
+        for (int e = c.g.ptr[v]; e < c.g.ptr[v + 1]; e++) {
+            int w = c.g.adj[e];
+            if (c.label[w] == id && c.lvl[w] < 0) {
+                c.lvl[w] = cur + 1;
+                order.push_back(w);
+            }
+        }
+    }
+    lptr.push_back((int)order.size());
+}
+
+inline void clear_levels(NdCtx& c, const std::vector<int>& order) {
+    for (int v : order) c.lvl[v] = -1;
+}
+
+// exact minimum degree on the subgraph induced by `verts` (all carrying label `id`), bitset adjacency
+void local_min_degree(NdCtx& c, const std::vector<int>& verts, int id, int* out) {
+    const int m = (int)verts.size();
+    if (m == 0) return;
+    if (m == 1) {
+        out[0] = verts[0];
+        return;
+    }
+    if (m > 4096) { // too large for the dense bitset: cheap static heuristic (increasing degree)
+        std::vector<int> idx(verts);
+        std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) {
+            return (c.g.ptr[a + 1] - c.g.ptr[a]) < (c.g.ptr[b + 1] - c.g.ptr[b]);
+        });
+        std::copy(idx.begin(), idx.end(), out);
+        return;
+    }
+    const int W = (m + 63) / 64;
+    std::vector<uint64_t> bits((size_t)m * W, 0);
+    for (int i = 0; i < m; i++) c.loc[verts[i]] = i;
+    for (int i = 0; i < m; i++) {
+        int v = verts[i];
+        uint64_t* row = &bits[(size_t)i * W];
+        for (int e = c.g.ptr[v]; e < c.g.ptr[v + 1]; e++) {
+            int w = c.g.adj[e];
+            if (c.label[w] == id) {
+                int j = c.loc[w];
+                if (j >= 0 && j != i) row[j >> 6] |= (1ull << (j & 63));
+            }
+        }
+    }
+    for (int i = 0; i < m; i++) c.loc[verts[i]] = -1;
+    std::vector<int> deg(m);
+    std::vector<char> alive(m, 1);
+    for (int i = 0; i < m; i++) {
+        int d = 0;
+        for (int w = 0; w < W; w++) d += __builtin_popcountll(bits[(size_t)i * W + w]);
+        deg[i] = d;
+    }
+    std::vector<int> nb;
+    for (int step = 0; step < m; step++) {
+        int best = -1, bd = 1 << 30;
+        for (int i = 0; i < m; i++)
+            if (alive[i] && deg[i] < bd) {
+                bd = deg[i];
+                best = i;
+            }
+        out[step] = verts[best];
+        alive[best] = 0;
+        uint64_t* rb = &bits[(size_t)best * W];
+        nb.clear();
+        for (int w = 0; w < W; w++) {
+            uint64_t x = rb[w];
+            while (x) {
+                int b = __builtin_ctzll(x);
+                x &= x - 1;
+                nb.push_back(w * 64 + b);
+            }
+        }
+        for (int j : nb) {
+            uint64_t* rj = &bits[(size_t)j * W];
+            int d = 0;
+            for (int w = 0; w < W; w++) {
+                rj[w] |= rb[w];
+            }
+            rj[j >> 6] &= ~(1ull << (j & 63));
+            rj[best >> 6] &= ~(1ull << (best & 63));
+            for (int w = 0; w < W; w++) d += __builtin_popcountll(rj[w]);
+            deg[j] = d;
+        }
+    }
+}
+
+void nd_component(NdCtx& c, std::vector<int>& verts, int id, int* out, std::vector<int>& order, std::vector<int>& lptr);
+
+// `verts` all carry label `id`; writes verts.size() entries at out
+void nd_rec(NdCtx& c, std::vector<int>& verts, int id, int* out) {
+    const int m = (int)verts.size();
+    if (m == 0) return;
+    if (m <= c.leaf) {
+        local_min_degree(c, verts, id, out);
+        return;
+    }
+    // split into connected components (iteratively, so that a diagonal matrix does not recurse n deep)
+    std::vector<int> order, lptr;
+    bfs_levels(c, id, verts[0], order, lptr);
+    if ((int)order.size() == m) {
+        nd_component(c, verts, id, out, order, lptr);
+        return;
+    }
+    clear_levels(c, order);
+    // several components: give each its own label and order them one after another
+    int pos = 0;
+    std::vector<int> comp;
+    std::vector<int> small; // vertices of tiny components are ordered together (they do not interact)
+    for (int s : verts) {
+        if (c.label[s] != id) continue;
+        bfs_levels(c, id, s, order, lptr);
+        clear_levels(c, order);
+        int cid = c.next_id++;
+        for (int v : order) c.label[v] = cid;
+        if ((int)order.size() <= c.leaf) {
+            comp = order;
+            local_min_degree(c, comp, cid, out + pos);
+        } else {
+            comp = order;
+            nd_rec(c, comp, cid, out + pos);
+        }
+        pos += (int)order.size();
+    }
+}
+
+// connected subgraph; `order`/`lptr` hold a BFS from verts[0] (levels still set in c.lvl)
+void nd_component(NdCtx& c, std::vector<int>& verts, int id, int* out, std::vector<int>& order, std::vector<int>& lptr) {
+    const int m = (int)verts.size();
+    // pseudo-peripheral start: walk to the far end a few times
+    int nl = (int)lptr.size() - 1;
+    for (int it = 0; it < 4; it++) {
+        int best = -1, bd = 1 << 30;
+        for (int k = lptr[nl - 1]; k < lptr[nl]; k++) {
+            int v = order[k];
+            int d = c.g.ptr[v + 1] - c.g.ptr[v];
+            if (d < bd) {
+                bd = d;
+                best = v;
+            }
+        }
+        clear_levels(c, order);
+        std::vector<int> order2, lptr2;
+        bfs_levels(c, id, best, order2, lptr2);
+        int nl2 = (int)lptr2.size() - 1;
+        bool better = nl2 > nl;
+        order.swap(order2);
+        lptr.swap(lptr2);
+        nl = nl2;
+        if (!better) break;
+    }
+    if (nl < 3) { // a clique-like blob: nothing to dissect
+        clear_levels(c, order);
+        local_min_degree(c, verts, id, out);
+        return;
+    }
+    // choose the separator level: smallest level whose two sides both keep >= 1/4 of the vertices
+    int ls = -1;
+    {
+        long bestsz = -1;
+        long bestbal = 0;
+        for (int l = 1; l <= nl - 2; l++) {
+            long before = lptr[l], sep = lptr[l + 1] - lptr[l], after = m - lptr[l + 1];
+            if (std::min(before, after) * 4 < m - sep) continue;
+            long bal = std::labs(before - after);
+            if (ls < 0 || sep < bestsz || (sep == bestsz && bal < bestbal)) {
+                ls = l;
+                bestsz = sep;
+                bestbal = bal;
+            }
+        }
+        if (ls < 0) { // no balanced level: take the one closest to the median
+            long bestd = -1;
+            for (int l = 1; l <= nl - 2; l++) {
+                long before = lptr[l], after = m - lptr[l + 1];
+                long d = std::labs(before - after);
+                if (ls < 0 || d < bestd) {
+                    ls = l;
+                    bestd = d;
+                }
+            }
+        }
+    }
+    const int idA = c.next_id++, idB = c.next_id++;
+    long na = 0, nb = 0;
+    for (int k = 0; k < lptr[ls]; k++) c.label[order[k]] = idA, na++;
+    for (int k = lptr[ls + 1]; k < m; k++) c.label[order[k]] = idB, nb++;
+    std::vector<int> sep(order.begin() + lptr[ls], order.begin() + lptr[ls + 1]);
+    clear_levels(c, order);
+    order.clear();
+    order.shrink_to_fit();
+
+    // refinement: trim vertices that touch only one side, then zero-gain balancing moves
+    for (int pass = 0; pass < 3; pass++) {
+        bool changed = false;
+        for (int v : sep) {
+            if (c.label[v] != id) continue;
+            int ca = 0, cb = 0;
+            for (int e = c.g.ptr[v]; e < c.g.ptr[v + 1]; e++) {
+                int w = c.g.adj[e];
+                if (c.label[w] == idA) ca++;
+                else if (c.label[w] == idB) cb++;
+            }
+            if (cb == 0 && (ca > 0 || na <= nb)) {
+                c.label[v] = idA, na++, changed = true;
+            } else if (ca == 0) {
+                c.label[v] = idB, nb++, changed = true;
+            } else if (pass > 0 && cb == 1 && na + 1 < nb) {
+                // move v to A and pull its single B neighbour into the separator: |S| unchanged, better balance
+                for (int e = c.g.ptr[v]; e < c.g.ptr[v + 1]; e++) {
+                    int w = c.g.adj[e];
+                    if (c.label[w] == idB) {
+                        c.label[w] = id;
+                        sep.push_back(w);
+                        nb--;
+                        break;
+                    }
+                }
+                c.label[v] = idA, na++, changed = true;
+            } else if (pass > 0 && ca == 1 && nb + 1 < na) {
+                for (int e = c.g.ptr[v]; e < c.g.ptr[v + 1]; e++) {
+                    int w = c.g.adj[e];
+                    if (c.label[w] == idA) {
+                        c.label[w] = id;
+                        sep.push_back(w);
+                        na--;
+                        break;
+                    }
+                }
+                c.label[v] = idB, nb++, changed = true;
+            }
+        }
+        if (!changed) break;
+    }
+    std::vector<int> A, B, S;
+    A.reserve(na);
+    B.reserve(nb);
+    for (int v : verts) {
+        int l = c.label[v];
+        if (l == idA) A.push_back(v);
+        else if (l == idB) B.push_back(v);
+        else S.push_back(v);
+    }
+    verts.clear();
+    verts.shrink_to_fit();
+    const int sa = (int)A.size(), sb = (int)B.size();
+    // the separator is eliminated last
+    std::copy(S.begin(), S.end(), out + sa + sb);
+    {
+        int sid = c.next_id++;
+        for (int v : S) c.label[v] = sid; // take separator vertices out of play for the sub-problems
+    }
+    S.clear();
+    S.shrink_to_fit();
+    nd_rec(c, A, idA, out);
+    nd_rec(c, B, idB, out + sa);
+}
+
+} // namespace
+
+void order_nested_dissection(const Graph& g, int leaf_size, std::vector<int>& perm) {
+    perm.assign(g.n, 0);
+    if (g.n == 0) return;
+    NdCtx c(g, std::max(leaf_size, 4));
+    c.out = perm.data();
+    std::vector<int> verts(g.n);
+    std::iota(verts.begin(), verts.end(), 0);
+    nd_rec(c, verts, 0, perm.data());
+}
+
+void order_minimum_degree(const Graph& g, std::vector<int>& perm) {
+    perm.assign(g.n, 0);
+    if (g.n == 0) return;
+    if (g.n > 4096) { // the bitset minimum degree is meant for small graphs: fall back to dissection with small leaves
+        order_nested_dissection(g, 32, perm);
+        return;
+    }
+    NdCtx c(g, g.n);
+    std::vector<int> verts(g.n);
+    std::iota(verts.begin(), verts.end(), 0);
+    local_min_degree(c, verts, 0, perm.data());
+}
+
+} // namespace b200

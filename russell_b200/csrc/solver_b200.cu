@@ -1,0 +1,749 @@
+// solver_b200.cu -- host driver + C ABI (include/solver_b200.h) of the B200-native sparse direct solver.
+//
+// Mirrors the reference's cuDSS shim function by function (russell_sparse/c_code/interface_cudss.cu):
+//   solver_b200_new        <- solver_cudss_new        (:62-123)   stream + handle
+//   solver_b200_drop       <- solver_cudss_drop       (:126-171)  frees everything, NULL-safe
+//   solver_b200_initialize <- solver_cudss_initialize (:190-396)  H2D of the structure + ANALYSIS phase
+//   solver_b200_factorize  <- solver_cudss_factorize  (:406-501)  H2D of values + FACTORIZATION phase
+//   solver_b200_solve      <- solver_cudss_solve      (:510-566)  H2D rhs, SOLVE phase (+ refinement), D2H x
+// but the phases are our own kernels (kernels.cuh) instead of cudssExecute().
+//
+// There is deliberately NO CPU fallback: without a CUDA device solver_b200_new() returns NULL and every
+// entry point reports B200_ERROR_NOT_AVAILABLE.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/solver_b200.h"
+#include "kernels.cuh"
+#include "plan.hpp"
+
+using namespace b200;
+
+#define CUDA_TRY(expr, code)                                                                        \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            if (s && s->verbose) fprintf(stderr, "solver_b200: %s failed: %s\n", #expr, cudaGetErrorString(_e)); \
+            return (code);                                                                          \
+        }                                                                                           \
+    } while (0)
+
+struct LevelLists {
+    // offsets (nlevels+1) into the concatenated device item arrays
+    std::vector<int> asm_ptr, panel_ptr, schur_ptr, node_ptr;
+};
+
+struct InterfaceB200 {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool initialized = false, factorized = false;
+    int verbose = 0;
+
+    // options
+    int opt_panel_width = 64, opt_nd_leaf = 96;
+    int use_graph = 1;
+    int schur_variant = 1; // 0 = FMA, 1 = DMMA
+    int nrefine = 2;
+    double ir_tol = 1e-11;
+    double pivot_eps = 1e-13;
+    int force_no_matching = 0;
+
+    Plan plan;
+    LevelLists lv;
+    int n = 0, nnz_in = 0, fnnz = 0;
+    bool sym_lower = false;
+    int effective_matching = 0, effective_pivoting = 5;
+
+    // device: plan
+    NodeDev* d_nodes = nullptr;
+    int *d_rows = nullptr, *d_rel = nullptr, *d_child_idx = nullptr, *d_level_nodes = nullptr;
+    AsmItem* d_asm = nullptr;
+    PanelItem* d_panel = nullptr;
+    SchurItem* d_schur = nullptr;
+    int* d_a_src = nullptr;
+    long long* d_a_dst = nullptr;
+    double* d_a_scl = nullptr;
+    int *d_rowperm = nullptr, *d_colperm = nullptr;
+    double *d_rscale = nullptr, *d_cscale = nullptr;
+    int *d_full_ptr = nullptr, *d_full_col = nullptr, *d_full_src = nullptr, *d_rowblk = nullptr;
+    int n_rowblk = 0;
+    // device: numeric
+    double *d_vals = nullptr, *d_fullvals = nullptr;
+    const double* spmv_vals = nullptr; // mirrored values (symmetric input) or d_vals (general input)
+    double *d_fac = nullptr, *d_cb = nullptr, *d_dinv = nullptr, *d_upiv = nullptr;
+    int* d_lperm = nullptr;
+    int* d_counters = nullptr; // 4 ints
+    unsigned long long* d_amax = nullptr;
+    // device: vectors
+    double *d_b = nullptr, *d_x = nullptr, *d_r = nullptr, *d_y = nullptr, *d_xp = nullptr, *d_wv = nullptr;
+    double *d_partial = nullptr, *d_norms = nullptr;
+    double* h_norms = nullptr; // pinned, 2 doubles + counters
+    int* h_counters = nullptr; // pinned
+
+    cudaGraphExec_t g_fact = nullptr, g_sweep = nullptr;
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+
+    // stats
+    int n_perturbed = 0;
+    double last_rel_residual = -1.0;
+    int last_refine_steps = 0;
+    float ms_factorize = 0, ms_solve = 0, ms_sptrsv = 0, ms_spmv = 0;
+    int launches_factorize = 0, launches_solve = 0;
+    double sptrsv_bytes = 0, spmv_bytes = 0;
+};
+
+namespace {
+
+template <typename T>
+cudaError_t upload(T** dptr, const std::vector<T>& h) {
+    *dptr = nullptr;
+    size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+    cudaError_t e = cudaMalloc((void**)dptr, bytes);
+    if (e != cudaSuccess) return e;
+    if (!h.empty()) e = cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return e;
+}
+
+template <typename T>
+void dfree(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+void release_device(InterfaceB200* s) {
+    if (s->g_fact) cudaGraphExecDestroy(s->g_fact), s->g_fact = nullptr;
+    if (s->g_sweep) cudaGraphExecDestroy(s->g_sweep), s->g_sweep = nullptr;
+    dfree(s->d_nodes), dfree(s->d_rows), dfree(s->d_rel), dfree(s->d_child_idx), dfree(s->d_level_nodes);
+    dfree(s->d_asm), dfree(s->d_panel), dfree(s->d_schur);
+    dfree(s->d_a_src), dfree(s->d_a_dst), dfree(s->d_a_scl);
+    dfree(s->d_rowperm), dfree(s->d_colperm), dfree(s->d_rscale), dfree(s->d_cscale);
+    dfree(s->d_full_ptr), dfree(s->d_full_col), dfree(s->d_full_src), dfree(s->d_rowblk);
+    dfree(s->d_vals), dfree(s->d_fullvals);
+    dfree(s->d_fac), dfree(s->d_cb), dfree(s->d_dinv), dfree(s->d_upiv), dfree(s->d_lperm);
+    dfree(s->d_counters), dfree(s->d_amax);
+    dfree(s->d_b), dfree(s->d_x), dfree(s->d_r), dfree(s->d_y), dfree(s->d_xp), dfree(s->d_wv);
+    dfree(s->d_partial), dfree(s->d_norms);
+    if (s->h_norms) cudaFreeHost(s->h_norms), s->h_norms = nullptr;
+    if (s->h_counters) cudaFreeHost(s->h_counters), s->h_counters = nullptr;
+}
+
+int grid_for(long long work, int block = 256, int cap = 148 * 16) {
+    long long g = (work + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > cap) g = cap;
+    return (int)g;
+}
+
+// ---- work-item lists --------------------------------------------------------------------------------
+void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::vector<PanelItem>& panel_items,
+                      std::vector<SchurItem>& schur_items) {
+    const Plan& P = s->plan;
+    LevelLists& lv = s->lv;
+    lv.asm_ptr.assign(P.nlevels + 1, 0);
+    lv.panel_ptr.assign(P.nlevels + 1, 0);
+    lv.schur_ptr.assign(P.nlevels + 1, 0);
+    lv.node_ptr = P.level_ptr;
+    for (int l = 0; l < P.nlevels; l++) {
+        for (int e = P.level_ptr[l]; e < P.level_ptr[l + 1]; e++) {
+            const int v = P.level_nodes[e];
+            const int p = P.p[v], u = P.u[v], f = p + u;
+            const int nch = P.child_ptr[v + 1] - P.child_ptr[v];
+            if (nch > 0) {
+                double total = 0;
+                for (int c = P.child_ptr[v]; c < P.child_ptr[v + 1]; c++) {
+                    double uc = P.u[P.child_idx[c]];
+                    total += uc * uc;
+                }
+                int ntiles = (int)std::ceil(total / 32768.0);
+                ntiles = std::max(1, std::min(ntiles, std::max(1, f / 4)));
+                int tw = (f + ntiles - 1) / ntiles;
+                for (int t0 = 0; t0 < f; t0 += tw) asm_items.push_back({v, t0, std::min(f, t0 + tw), 0});
+            }
+            if (u > 0) {
+                for (int r0 = 0; r0 < u; r0 += B200_TR) panel_items.push_back({v, r0, std::min(B200_TR, u - r0), 0});
+                for (int r0 = 0; r0 < u; r0 += B200_TR) panel_items.push_back({v, r0, std::min(B200_TR, u - r0), 1});
+                int nt = (u + B200_TS - 1) / B200_TS;
+                for (int tj = 0; tj < nt; tj++)
+                    for (int ti = 0; ti < nt; ti++) schur_items.push_back({v, ti, tj, 0});
+            }
+        }
+        lv.asm_ptr[l + 1] = (int)asm_items.size();
+        lv.panel_ptr[l + 1] = (int)panel_items.size();
+        lv.schur_ptr[l + 1] = (int)schur_items.size();
+    }
+}
+
+size_t smem_diag(int W) { return (size_t)2 * W * W * sizeof(double) + W * sizeof(int); }
+size_t smem_panel(int W) { return (size_t)(W * W + B200_TR * W) * sizeof(double) + W * sizeof(int); }
+size_t smem_schur_fma(int W) { return (size_t)2 * W * B200_TS * sizeof(double); }
+size_t smem_schur_dmma() { return (size_t)2 * B200_MAXP * (B200_TS + 1) * sizeof(double); }
+
+// enqueue the per-level numeric kernels (assembly -> pivot block -> panels -> Schur complement)
+int enqueue_levels(InterfaceB200* s, int* launches) {
+    const Plan& P = s->plan;
+    const LevelLists& lv = s->lv;
+    const int W = s->opt_panel_width;
+    int cnt = 0;
+    for (int l = 0; l < P.nlevels; l++) {
+        int na = lv.asm_ptr[l + 1] - lv.asm_ptr[l];
+        if (na > 0) {
+            k_assemble<<<na, 256, 0, s->stream>>>(s->d_asm + lv.asm_ptr[l], s->d_nodes, s->d_child_idx, s->d_rel, s->d_fac, s->d_cb);
+            cnt++;
+        }
+        int nn = lv.node_ptr[l + 1] - lv.node_ptr[l];
+        k_diag<<<nn, 256, smem_diag(W), s->stream>>>(s->d_level_nodes + lv.node_ptr[l], s->d_nodes, s->d_fac, s->d_dinv,
+                                                       s->d_lperm, s->d_upiv, s->d_amax, s->pivot_eps, s->d_counters);
+        cnt++;
+        int np = lv.panel_ptr[l + 1] - lv.panel_ptr[l];
+        if (np > 0) {
+            k_panel<<<np, 256, smem_panel(W), s->stream>>>(s->d_panel + lv.panel_ptr[l], s->d_nodes, s->d_fac, s->d_dinv, s->d_lperm);
+            cnt++;
+        }
+        int nsch = lv.schur_ptr[l + 1] - lv.schur_ptr[l];
+        if (nsch > 0) {
+            if (s->schur_variant == 1)
+                k_schur_dmma<<<nsch, 256, smem_schur_dmma(), s->stream>>>(s->d_schur + lv.schur_ptr[l], s->d_nodes, s->d_fac, s->d_cb);
+            else
+                k_schur_fma<<<nsch, 256, smem_schur_fma(W), s->stream>>>(s->d_schur + lv.schur_ptr[l], s->d_nodes, s->d_fac, s->d_cb);
+            cnt++;
+        }
+    }
+    if (launches) *launches = cnt;
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int enqueue_sweep_levels(InterfaceB200* s, int* launches) {
+    const Plan& P = s->plan;
+    const LevelLists& lv = s->lv;
+    int cnt = 0;
+    for (int l = 0; l < P.nlevels; l++) {
+        int nn = lv.node_ptr[l + 1] - lv.node_ptr[l];
+        k_fwd<<<nn, 256, 0, s->stream>>>(s->d_level_nodes + lv.node_ptr[l], s->d_nodes, s->d_child_idx, s->d_rel, s->d_fac,
+                                          s->d_dinv, s->d_lperm, s->d_y, s->d_wv);
+        cnt++;
+    }
+    for (int l = P.nlevels - 1; l >= 0; l--) {
+        int nn = lv.node_ptr[l + 1] - lv.node_ptr[l];
+        k_bwd<<<nn, 256, 0, s->stream>>>(s->d_level_nodes + lv.node_ptr[l], s->d_nodes, s->d_rows, s->d_fac, s->d_dinv, s->d_y, s->d_xp);
+        cnt++;
+    }
+    if (launches) *launches = cnt;
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+// runs `enqueue` either directly or through a captured graph (captured on first use)
+template <typename F>
+int run_maybe_graph(InterfaceB200* s, cudaGraphExec_t* exec, F enqueue, int* launches) {
+    if (!s->use_graph) return enqueue(s, launches);
+    if (*exec == nullptr) {
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            return enqueue(s, launches);
+        }
+        int rc = enqueue(s, launches);
+        cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
+        if (rc != 0 || e != cudaSuccess || graph == nullptr) {
+            cudaGetLastError();
+            if (graph) cudaGraphDestroy(graph);
+            s->use_graph = 0;
+            if (s->verbose) fprintf(stderr, "solver_b200: graph capture failed, falling back to direct launches\n");
+            return enqueue(s, launches);
+        }
+        e = cudaGraphInstantiate(exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            *exec = nullptr;
+            s->use_graph = 0;
+            return enqueue(s, launches);
+        }
+    }
+    return cudaGraphLaunch(*exec, s->stream) == cudaSuccess ? 0 : 1;
+}
+
+int sweep(InterfaceB200* s, const double* d_rhs, double* d_out, int accumulate, bool time_it) {
+    const int n = s->n;
+    k_permute_in<<<grid_for(n), 256, 0, s->stream>>>(n, s->d_rowperm, s->d_rscale, d_rhs, s->d_y);
+    if (time_it) cudaEventRecord(s->ev[4], s->stream);
+    int launches = 0;
+    int rc = run_maybe_graph(s, &s->g_sweep, enqueue_sweep_levels, &launches);
+    if (time_it) cudaEventRecord(s->ev[5], s->stream);
+    k_permute_out<<<grid_for(n), 256, 0, s->stream>>>(n, s->d_colperm, s->d_cscale, s->d_xp, d_out, accumulate);
+    s->launches_solve += 2 + 2 * s->plan.nlevels;
+    return rc;
+}
+
+int residual(InterfaceB200* s, const double* d_xv, const double* d_rhs, double* d_rout, bool time_it) {
+    if (time_it) cudaEventRecord(s->ev[6], s->stream);
+    k_spmv_stream<<<s->n_rowblk, 256, 0, s->stream>>>(s->d_rowblk, s->d_full_ptr, s->d_full_col, s->spmv_vals, d_xv, d_rhs,
+                                                       d_rout, s->d_partial, 1);
+    if (time_it) cudaEventRecord(s->ev[7], s->stream);
+    k_reduce_partials<<<1, 256, 0, s->stream>>>(s->n_rowblk, s->d_partial, s->d_norms);
+    s->launches_solve += 2;
+    if (cudaMemcpyAsync(s->h_norms, s->d_norms, 2 * sizeof(double), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess) return 1;
+    if (cudaStreamSynchronize(s->stream) != cudaSuccess) return 1;
+    return 0;
+}
+
+} // namespace
+
+// =========================================================================================================
+extern "C" {
+
+const char* solver_b200_version(void) { return "solver_b200 0.1 (sm_100a, multifrontal LU f64)"; }
+
+struct InterfaceB200* solver_b200_new(void) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        cudaGetLastError();
+        return nullptr; // no CPU fallback, by design
+    }
+    InterfaceB200* s = new (std::nothrow) InterfaceB200();
+    if (!s) return nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    s->device = dev;
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete s;
+        return nullptr;
+    }
+    for (int i = 0; i < 8; i++)
+        if (cudaEventCreate(&s->ev[i]) != cudaSuccess) {
+            solver_b200_drop(s);
+            return nullptr;
+        }
+    const char* e;
+    if ((e = getenv("B200_NO_GRAPH")) && atoi(e)) s->use_graph = 0;
+    if ((e = getenv("B200_SCHUR_VARIANT"))) s->schur_variant = atoi(e);
+    if ((e = getenv("B200_PANEL_WIDTH"))) s->opt_panel_width = atoi(e);
+    if ((e = getenv("B200_ND_LEAF"))) s->opt_nd_leaf = atoi(e);
+    return s;
+}
+
+void solver_b200_drop(struct InterfaceB200* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    release_device(s);
+    for (int i = 0; i < 8; i++)
+        if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+int32_t solver_b200_set_option(struct InterfaceB200* s, const char* key, double value) {
+    if (!s || !key) return B200_ERROR_NULL_POINTER;
+    std::string k(key);
+    if (k == "ir_tol") { s->ir_tol = value; return 0; }
+    if (k == "refinement_nstep") { s->nrefine = (int)value; return 0; }
+    if (s->initialized) return B200_ERROR_ALREADY_INITIALIZED;
+    if (k == "panel_width") s->opt_panel_width = std::max(4, std::min((int)value, B200_MAXP));
+    else if (k == "nd_leaf") s->opt_nd_leaf = std::max(4, (int)value);
+    else if (k == "use_graph") s->use_graph = value != 0.0;
+    else if (k == "schur_variant") s->schur_variant = (int)value;
+    else if (k == "force_no_matching") s->force_no_matching = value != 0.0;
+    else if (k == "device") s->device = (int)value;
+    else return B200_ERROR_NOT_AVAILABLE;
+    return 0;
+}
+
+int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_t matching, int32_t pivoting,
+                               double pivot_epsilon, int32_t refinement_nstep, double hybrid_memory_factor,
+                               int32_t verbose, int32_t general_symmetric, int32_t positive_definite, int32_t ndim,
+                               const int32_t* row_pointers, const int32_t* col_indices, const double* values) {
+    (void)pivoting;
+    (void)hybrid_memory_factor;
+    if (!s || !row_pointers || !col_indices || !values) return B200_ERROR_NULL_POINTER;
+    if (s->initialized) return B200_ERROR_ALREADY_INITIALIZED;
+    s->verbose = verbose;
+    CUDA_TRY(cudaSetDevice(s->device), B200_ERROR_NOT_AVAILABLE);
+    if (pivot_epsilon > 0.0) s->pivot_eps = pivot_epsilon;
+    if (refinement_nstep >= 0) s->nrefine = refinement_nstep;
+    s->opt_panel_width = std::max(4, std::min(s->opt_panel_width, B200_MAXP));
+
+    AnalyzeOptions opt;
+    opt.panel_width = s->opt_panel_width;
+    opt.nd_leaf = s->opt_nd_leaf;
+    opt.verbose = verbose;
+    if (ordering == B200_ORDERING_NONE) opt.ordering = ORDERING_NATURAL;
+    else if (ordering == B200_ORDERING_AMD) opt.ordering = ORDERING_MINDEG;
+    else opt.ordering = ORDERING_ND;
+    // Matching::None is upgraded to "auto": unlike cuDSS (solver_cudss.rs:664-671) we must not lose accuracy on
+    // zero diagonals; a symmetric positive-definite promise skips it.
+    if (positive_definite || s->force_no_matching) opt.matching = 0;
+    else if (matching == B200_MATCHING_NONE || matching == B200_MATCHING_AUTO) opt.matching = 2;
+    else opt.matching = 1;
+
+    int rc = analyze(ndim, row_pointers, col_indices, values, general_symmetric != 0 || positive_definite != 0, opt, s->plan);
+    if (rc == -1) return B200_ERROR_SINGULAR;
+    if (rc != 0) return B200_ERROR_ANALYSIS + 2;
+    Plan& P = s->plan;
+    s->n = P.n;
+    s->nnz_in = P.nnz_in;
+    s->sym_lower = P.sym_lower;
+    s->fnnz = (int)P.full_col.size();
+    s->effective_matching = P.matched || !P.rscale.empty() ? B200_MATCHING_MAX_DIAG_PRODUCT : B200_MATCHING_NONE;
+
+    // node descriptors
+    std::vector<NodeDev> nodes(P.nnodes);
+    for (int v = 0; v < P.nnodes; v++) {
+        NodeDev& d = nodes[v];
+        d.p = P.p[v], d.u = P.u[v], d.c0 = P.c0[v];
+        d.nchild = P.child_ptr[v + 1] - P.child_ptr[v];
+        d.child_ptr = P.child_ptr[v];
+        d.Loff = P.Loff[v], d.Uoff = P.Uoff[v], d.Coff = P.Coff[v], d.Doff = P.Doff[v], d.rows_ptr = P.rows_ptr[v];
+        d.pad = 0;
+    }
+    std::vector<AsmItem> asm_items;
+    std::vector<PanelItem> panel_items;
+    std::vector<SchurItem> schur_items;
+    build_work_lists(s, asm_items, panel_items, schur_items);
+
+    // SpMV row blocks (rows never split; at most B200_SPMV_NNZ nonzeros and 1024 rows per block)
+    std::vector<int> rowblk;
+    {
+        rowblk.push_back(0);
+        int r = 0;
+        const std::vector<int>& ptr = P.full_ptr;
+        while (r < P.n) {
+            int r1 = r + 1;
+            while (r1 < P.n && r1 - r < 1024 && ptr[r1 + 1] - ptr[r] <= B200_SPMV_NNZ) r1++;
+            rowblk.push_back(r1);
+            r = r1;
+        }
+    }
+    s->n_rowblk = (int)rowblk.size() - 1;
+
+#define UP(dst, vec) CUDA_TRY(upload(&s->dst, vec), B200_ERROR_CUDA_MALLOC)
+    UP(d_nodes, nodes);
+    UP(d_rows, P.rows);
+    UP(d_rel, P.rel);
+    UP(d_child_idx, P.child_idx);
+    UP(d_level_nodes, P.level_nodes);
+    UP(d_asm, asm_items);
+    UP(d_panel, panel_items);
+    UP(d_schur, schur_items);
+    UP(d_a_src, P.a_src);
+    {
+        std::vector<long long> dst(P.a_dst.begin(), P.a_dst.end());
+        UP(d_a_dst, dst);
+    }
+    if (!P.a_scl.empty()) UP(d_a_scl, P.a_scl);
+    UP(d_rowperm, P.rowperm);
+    UP(d_colperm, P.colperm);
+    if (!P.rscale.empty()) {
+        UP(d_rscale, P.rscale);
+        UP(d_cscale, P.cscale);
+    }
+    UP(d_full_ptr, P.full_ptr);
+    UP(d_full_col, P.full_col);
+    if (!P.full_src.empty()) UP(d_full_src, P.full_src);
+    UP(d_rowblk, rowblk);
+#undef UP
+#define DM(ptr, count, type) CUDA_TRY(cudaMalloc((void**)&s->ptr, std::max<size_t>((size_t)(count), 1) * sizeof(type)), B200_ERROR_CUDA_MALLOC)
+    DM(d_vals, P.nnz_in, double);
+    if (P.sym_lower) DM(d_fullvals, s->fnnz, double);
+    DM(d_fac, P.fac_size, double);
+    DM(d_cb, P.cb_size, double);
+    DM(d_dinv, P.dinv_size, double);
+    DM(d_upiv, P.n, double);
+    DM(d_lperm, P.n, int);
+    DM(d_counters, 4, int);
+    DM(d_amax, 1, unsigned long long);
+    DM(d_b, P.n, double);
+    DM(d_x, P.n, double);
+    DM(d_r, P.n, double);
+    DM(d_y, P.n, double);
+    DM(d_xp, P.n, double);
+    DM(d_wv, P.rows_ptr[P.nnodes] + 1, double);
+    DM(d_partial, 2 * (size_t)s->n_rowblk, double);
+    DM(d_norms, 2, double);
+#undef DM
+    CUDA_TRY(cudaMallocHost((void**)&s->h_norms, 2 * sizeof(double)), B200_ERROR_MALLOC);
+    CUDA_TRY(cudaMallocHost((void**)&s->h_counters, 4 * sizeof(int) + sizeof(unsigned long long)), B200_ERROR_MALLOC);
+
+    // kernels that need more than 48 KB of dynamic shared memory
+    const int W = s->opt_panel_width;
+    CUDA_TRY(cudaFuncSetAttribute(k_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_diag(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
+    CUDA_TRY(cudaFuncSetAttribute(k_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_panel(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
+    CUDA_TRY(cudaFuncSetAttribute(k_schur_fma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_schur_fma(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
+    CUDA_TRY(cudaFuncSetAttribute(k_schur_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_schur_dmma()), B200_ERROR_NOT_AVAILABLE);
+    (void)W;
+
+    // algorithmic bytes: SpTRSV streams every stored factor entry once (+ the pivot-block inverses)
+    // and touches the vectors; SpMV = 12 B per nonzero + row pointers + x and y
+    s->sptrsv_bytes = 8.0 * ((double)P.nnz_L + (double)P.nnz_U) + 16.0 * P.n;
+    s->spmv_bytes = 12.0 * s->fnnz + 4.0 * (P.n + 1) + 16.0 * P.n;
+
+    // host-side plan arrays that are no longer needed
+    std::vector<int>().swap(P.a_src);
+    std::vector<int64_t>().swap(P.a_dst);
+    std::vector<double>().swap(P.a_scl);
+    std::vector<int>().swap(P.full_col);
+    std::vector<int>().swap(P.full_src);
+    std::vector<int>().swap(P.rel);
+
+    CUDA_TRY(cudaStreamSynchronize(s->stream), B200_ERROR_CUDA_SYNCHRONIZE);
+    if (verbose) {
+        size_t fr = 0, tot = 0;
+        cudaMemGetInfo(&fr, &tot);
+        printf("solver_b200_initialize: analysis done: %d fronts, %d levels, nnz(L+U)=%lld, %.3e flops, device memory used %.2f GB\n",
+               P.nnodes, P.nlevels, (long long)(P.nnz_L + P.nnz_U), P.flops, (tot - fr) / 1e9);
+    }
+    s->initialized = true;
+    return B200_SUCCESSFUL_EXIT;
+}
+
+int32_t solver_b200_factorize_device(struct InterfaceB200* s, const double* d_values) {
+    if (!s) return B200_ERROR_NULL_POINTER;
+    if (!s->initialized) return B200_ERROR_NEED_INITIALIZATION;
+    if (!d_values) return B200_ERROR_NULL_POINTER;
+    CUDA_TRY(cudaSetDevice(s->device), B200_ERROR_NOT_AVAILABLE);
+    const Plan& P = s->plan;
+    s->factorized = false;
+    if (d_values != s->d_vals)
+        CUDA_TRY(cudaMemcpyAsync(s->d_vals, d_values, (size_t)s->nnz_in * sizeof(double), cudaMemcpyDeviceToDevice, s->stream), B200_ERROR_CUDA_MEMCPY);
+    cudaEventRecord(s->ev[0], s->stream);
+    CUDA_TRY(cudaMemsetAsync(s->d_fac, 0, (size_t)P.fac_size * sizeof(double), s->stream), B200_ERROR_NUM_FACTORIZATION + 1);
+    CUDA_TRY(cudaMemsetAsync(s->d_cb, 0, std::max<size_t>((size_t)P.cb_size, 1) * sizeof(double), s->stream), B200_ERROR_NUM_FACTORIZATION + 1);
+    CUDA_TRY(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(int), s->stream), B200_ERROR_NUM_FACTORIZATION + 1);
+    CUDA_TRY(cudaMemsetAsync(s->d_amax, 0, sizeof(unsigned long long), s->stream), B200_ERROR_NUM_FACTORIZATION + 1);
+    k_scatter_values<<<grid_for(s->fnnz), 256, 0, s->stream>>>(s->fnnz, s->d_a_src, s->d_a_dst, s->d_a_scl, s->d_vals, s->d_fac, s->d_amax);
+    int extra = 1;
+    if (s->sym_lower) {
+        k_gather<<<grid_for(s->fnnz), 256, 0, s->stream>>>(s->fnnz, s->d_full_src, s->d_vals, s->d_fullvals);
+        extra++;
+    }
+    int launches = 0;
+    int rc = run_maybe_graph(s, &s->g_fact, enqueue_levels, &launches);
+    if (launches > 0) s->launches_factorize = launches + extra;
+    cudaEventRecord(s->ev[1], s->stream);
+    if (rc != 0) return B200_ERROR_NUM_FACTORIZATION + 1;
+    CUDA_TRY(cudaMemcpyAsync(s->h_counters, s->d_counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream), B200_ERROR_CUDA_MEMCPY);
+    CUDA_TRY(cudaMemcpyAsync(s->h_counters + 4, s->d_amax, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream), B200_ERROR_CUDA_MEMCPY);
+    cudaError_t e = cudaStreamSynchronize(s->stream);
+    if (e != cudaSuccess) {
+        if (s->verbose) fprintf(stderr, "solver_b200_factorize: %s\n", cudaGetErrorString(e));
+        return B200_ERROR_CUDA_SYNCHRONIZE;
+    }
+    cudaEventElapsedTime(&s->ms_factorize, s->ev[0], s->ev[1]);
+    unsigned long long bits;
+    memcpy(&bits, s->h_counters + 4, sizeof(bits));
+    double amax;
+    memcpy(&amax, &bits, sizeof(double));
+    if (!(amax <= 1.79e308)) return B200_ERROR_NUM_FACTORIZATION + 2; // NaN / Inf in the input values
+    s->n_perturbed = s->h_counters[0];
+    if (s->h_counters[2] != 0) return B200_ERROR_SINGULAR;
+    s->spmv_vals = s->sym_lower ? s->d_fullvals : s->d_vals;
+    s->factorized = true;
+    return B200_SUCCESSFUL_EXIT;
+}
+
+int32_t solver_b200_factorize(struct InterfaceB200* s, int32_t* effective_matching, int32_t* effective_pivoting,
+                              int32_t verbose, const double* values) {
+    if (!s) return B200_ERROR_NULL_POINTER;
+    if (!s->initialized) return B200_ERROR_NEED_INITIALIZATION;
+    if (!values) return B200_ERROR_NULL_POINTER;
+    s->verbose = verbose;
+    CUDA_TRY(cudaSetDevice(s->device), B200_ERROR_NOT_AVAILABLE);
+    CUDA_TRY(cudaMemcpyAsync(s->d_vals, values, (size_t)s->nnz_in * sizeof(double), cudaMemcpyHostToDevice, s->stream), B200_ERROR_CUDA_MEMCPY);
+    int32_t rc = solver_b200_factorize_device(s, s->d_vals);
+    if (effective_matching) *effective_matching = s->effective_matching;
+    if (effective_pivoting) *effective_pivoting = s->effective_pivoting;
+    if (rc == 0 && verbose) {
+        if (s->n_perturbed > 0)
+            printf("solver_b200_factorize: WARNING: %d pivot(s) perturbed (matrix may be (nearly) singular)\n", s->n_perturbed);
+        printf("solver_b200_factorize: numeric factorization completed in %.3f ms (device)\n", s->ms_factorize);
+    }
+    return rc;
+}
+
+int32_t solver_b200_solve_device(struct InterfaceB200* s, double* d_xout, const double* d_rhs) {
+    if (!s) return B200_ERROR_NULL_POINTER;
+    if (!s->factorized) return B200_ERROR_NEED_FACTORIZATION;
+    if (!d_xout || !d_rhs) return B200_ERROR_NULL_POINTER;
+    CUDA_TRY(cudaSetDevice(s->device), B200_ERROR_NOT_AVAILABLE);
+    s->launches_solve = 0;
+    cudaEventRecord(s->ev[2], s->stream);
+    int rc = sweep(s, d_rhs, d_xout, 0, true);
+    double prev = -1.0;
+    int steps = 0;
+    for (int it = 0; rc == 0; it++) {
+        if (residual(s, d_xout, d_rhs, s->d_r, it == 0) != 0) {
+            rc = 1;
+            break;
+        }
+        double rr = s->h_norms[0], bb = s->h_norms[1];
+        double rel = bb > 0.0 ? std::sqrt(rr / bb) : std::sqrt(rr);
+        s->last_rel_residual = rel;
+        if (!(rel == rel)) break;                       // NaN: nothing to refine
+        if (rel <= s->ir_tol || it >= s->nrefine) break; // converged or out of steps
+        if (prev >= 0.0 && rel > 0.5 * prev) break;      // stagnation
+        prev = rel;
+        rc = sweep(s, s->d_r, d_xout, 1, false);
+        steps++;
+    }
+    cudaEventRecord(s->ev[3], s->stream);
+    s->last_refine_steps = steps;
+    cudaError_t e = cudaStreamSynchronize(s->stream);
+    if (rc != 0 || e != cudaSuccess) {
+        if (s->verbose) fprintf(stderr, "solver_b200_solve: %s\n", cudaGetErrorString(e));
+        return B200_ERROR_SOLVE + 1;
+    }
+    cudaEventElapsedTime(&s->ms_solve, s->ev[2], s->ev[3]);
+    cudaEventElapsedTime(&s->ms_sptrsv, s->ev[4], s->ev[5]);
+    cudaEventElapsedTime(&s->ms_spmv, s->ev[6], s->ev[7]);
+    return B200_SUCCESSFUL_EXIT;
+}
+
+int32_t solver_b200_solve(struct InterfaceB200* s, double* x, const double* rhs, int32_t verbose) {
+    if (!s) return B200_ERROR_NULL_POINTER;
+    if (!s->factorized) return B200_ERROR_NEED_FACTORIZATION;
+    if (!x || !rhs) return B200_ERROR_NULL_POINTER;
+    s->verbose = verbose;
+    CUDA_TRY(cudaSetDevice(s->device), B200_ERROR_NOT_AVAILABLE);
+    CUDA_TRY(cudaMemcpyAsync(s->d_b, rhs, (size_t)s->n * sizeof(double), cudaMemcpyHostToDevice, s->stream), B200_ERROR_CUDA_MEMCPY);
+    int32_t rc = solver_b200_solve_device(s, s->d_x, s->d_b);
+    if (rc != 0) return rc;
+    CUDA_TRY(cudaMemcpyAsync(x, s->d_x, (size_t)s->n * sizeof(double), cudaMemcpyDeviceToHost, s->stream), B200_ERROR_CUDA_MEMCPY);
+    CUDA_TRY(cudaStreamSynchronize(s->stream), B200_ERROR_CUDA_SYNCHRONIZE);
+    if (verbose)
+        printf("solver_b200_solve: solution completed: %d refinement step(s), ||b-Ax||/||b|| = %.3e, %.3f ms (device)\n",
+               s->last_refine_steps, s->last_rel_residual, s->ms_solve);
+    return B200_SUCCESSFUL_EXIT;
+}
+
+int32_t solver_b200_residual(struct InterfaceB200* s, const double* x, const double* rhs, double* rel_residual) {
+    if (!s || !x || !rhs || !rel_residual) return B200_ERROR_NULL_POINTER;
+    if (!s->factorized) return B200_ERROR_NEED_FACTORIZATION;
+    CUDA_TRY(cudaSetDevice(s->device), B200_ERROR_NOT_AVAILABLE);
+    CUDA_TRY(cudaMemcpyAsync(s->d_b, rhs, (size_t)s->n * sizeof(double), cudaMemcpyHostToDevice, s->stream), B200_ERROR_CUDA_MEMCPY);
+    CUDA_TRY(cudaMemcpyAsync(s->d_x, x, (size_t)s->n * sizeof(double), cudaMemcpyHostToDevice, s->stream), B200_ERROR_CUDA_MEMCPY);
+    int rc = residual(s, s->d_x, s->d_b, s->d_r, true);
+    if (rc != 0) return B200_ERROR_SOLVE + 1;
+    double rr = s->h_norms[0], bb = s->h_norms[1];
+    *rel_residual = bb > 0.0 ? std::sqrt(rr / bb) : std::sqrt(rr);
+    cudaEventElapsedTime(&s->ms_spmv, s->ev[6], s->ev[7]);
+    return B200_SUCCESSFUL_EXIT;
+}
+
+int32_t solver_b200_spmv(struct InterfaceB200* s, double* y, const double* x) {
+    if (!s || !x || !y) return B200_ERROR_NULL_POINTER;
+    if (!s->factorized) return B200_ERROR_NEED_FACTORIZATION;
+    CUDA_TRY(cudaSetDevice(s->device), B200_ERROR_NOT_AVAILABLE);
+    CUDA_TRY(cudaMemcpyAsync(s->d_x, x, (size_t)s->n * sizeof(double), cudaMemcpyHostToDevice, s->stream), B200_ERROR_CUDA_MEMCPY);
+    cudaEventRecord(s->ev[6], s->stream);
+    k_spmv_stream<<<s->n_rowblk, 256, 0, s->stream>>>(s->d_rowblk, s->d_full_ptr, s->d_full_col, s->spmv_vals, s->d_x, nullptr, s->d_r, s->d_partial, 0);
+    cudaEventRecord(s->ev[7], s->stream);
+    CUDA_TRY(cudaMemcpyAsync(y, s->d_r, (size_t)s->n * sizeof(double), cudaMemcpyDeviceToHost, s->stream), B200_ERROR_CUDA_MEMCPY);
+    CUDA_TRY(cudaStreamSynchronize(s->stream), B200_ERROR_CUDA_SYNCHRONIZE);
+    cudaEventElapsedTime(&s->ms_spmv, s->ev[6], s->ev[7]);
+    return B200_SUCCESSFUL_EXIT;
+}
+
+int32_t solver_b200_determinant(struct InterfaceB200* s, double* coefficient, double* exponent) {
+    if (!s || !coefficient || !exponent) return B200_ERROR_NULL_POINTER;
+    if (!s->factorized) return B200_ERROR_NEED_FACTORIZATION;
+    CUDA_TRY(cudaSetDevice(s->device), B200_ERROR_NOT_AVAILABLE);
+    const Plan& P = s->plan;
+    const int n = s->n;
+    std::vector<double> up(n);
+    std::vector<int> lp(n);
+    CUDA_TRY(cudaMemcpy(up.data(), s->d_upiv, n * sizeof(double), cudaMemcpyDeviceToHost), B200_ERROR_CUDA_MEMCPY);
+    CUDA_TRY(cudaMemcpy(lp.data(), s->d_lperm, n * sizeof(int), cudaMemcpyDeviceToHost), B200_ERROR_CUDA_MEMCPY);
+    // det(A) = det(Dr)^-1 det(Dc)^-1 sign(rowperm) sign(colperm) sign(local pivots) prod(U_kk)
+    double mant = 1.0, ex = 0.0;
+    auto mul = [&](double v) {
+        if (v == 0.0) { mant = 0.0; return; }
+        mant *= v;
+        double a = std::fabs(mant);
+        if (a != 0.0 && (a >= 1e150 || a < 1e-150)) {
+            double e10 = std::floor(std::log10(a));
+            mant /= std::pow(10.0, e10);
+            ex += e10;
+        }
+    };
+    for (int k = 0; k < n; k++) mul(up[k]);
+    if (!P.rscale.empty())
+        for (int i = 0; i < n; i++) mul(1.0 / (P.rscale[i] * P.cscale[i]));
+    auto perm_sign = [&](const std::vector<int>& pm) {
+        std::vector<char> seen(pm.size(), 0);
+        int sign = 1;
+        for (size_t i = 0; i < pm.size(); i++) {
+            if (seen[i]) continue;
+            size_t j = i;
+            int len = 0;
+            while (!seen[j]) seen[j] = 1, j = pm[j], len++;
+            if ((len & 1) == 0) sign = -sign;
+        }
+        return sign;
+    };
+    int sign = perm_sign(P.rowperm) * perm_sign(P.colperm);
+    for (int v = 0; v < P.nnodes; v++) { // local pivot permutations (per front)
+        std::vector<int> loc(lp.begin() + P.c0[v], lp.begin() + P.c0[v] + P.p[v]);
+        sign *= perm_sign(loc);
+    }
+    mant *= sign;
+    double a = std::fabs(mant);
+    if (a != 0.0) {
+        double e10 = std::floor(std::log10(a));
+        mant /= std::pow(10.0, e10);
+        ex += e10;
+    }
+    *coefficient = mant;
+    *exponent = ex;
+    return B200_SUCCESSFUL_EXIT;
+}
+
+int32_t solver_b200_get_stats(struct InterfaceB200* s, double* out, int32_t n_out) {
+    if (!s || !out) return B200_ERROR_NULL_POINTER;
+    if (!s->initialized) return B200_ERROR_NEED_INITIALIZATION;
+    const Plan& P = s->plan;
+    double v[B200_STAT_COUNT];
+    v[B200_STAT_NNODES] = P.nnodes;
+    v[B200_STAT_NLEVELS] = P.nlevels;
+    v[B200_STAT_NNZ_L] = (double)P.nnz_L;
+    v[B200_STAT_NNZ_U] = (double)P.nnz_U;
+    v[B200_STAT_FLOPS] = P.flops;
+    v[B200_STAT_FAC_BYTES] = 8.0 * P.fac_size;
+    v[B200_STAT_CB_BYTES] = 8.0 * P.cb_size;
+    v[B200_STAT_MAX_FRONT] = P.max_front;
+    v[B200_STAT_T_ORDER_S] = P.t_order;
+    v[B200_STAT_T_SYMBOLIC_S] = P.t_symbolic;
+    v[B200_STAT_N_PERTURBED] = s->n_perturbed;
+    v[B200_STAT_LAST_REL_RESIDUAL] = s->last_rel_residual;
+    v[B200_STAT_LAST_REFINE_STEPS] = s->last_refine_steps;
+    v[B200_STAT_MS_FACTORIZE_DEVICE] = s->ms_factorize;
+    v[B200_STAT_MS_SOLVE_DEVICE] = s->ms_solve;
+    v[B200_STAT_MS_SPTRSV_DEVICE] = s->ms_sptrsv;
+    v[B200_STAT_MS_SPMV_DEVICE] = s->ms_spmv;
+    v[B200_STAT_LAUNCHES_FACTORIZE] = s->launches_factorize;
+    v[B200_STAT_LAUNCHES_SOLVE] = s->launches_solve;
+    v[B200_STAT_SPTRSV_BYTES] = s->sptrsv_bytes;
+    v[B200_STAT_SPMV_BYTES] = s->spmv_bytes;
+    v[B200_STAT_MATCHED] = P.matched ? 1.0 : 0.0;
+    v[B200_STAT_T_MATCH_S] = P.t_match;
+    for (int i = 0; i < n_out && i < B200_STAT_COUNT; i++) out[i] = v[i];
+    return B200_SUCCESSFUL_EXIT;
+}
+
+int32_t solver_b200_debug_copy_factors(struct InterfaceB200* s, double* fac, int64_t fac_len, double* dinv,
+                                       int64_t dinv_len, int32_t* lperm, int64_t n) {
+    if (!s) return B200_ERROR_NULL_POINTER;
+    if (!s->factorized) return B200_ERROR_NEED_FACTORIZATION;
+    CUDA_TRY(cudaSetDevice(s->device), B200_ERROR_NOT_AVAILABLE);
+    if (fac) CUDA_TRY(cudaMemcpy(fac, s->d_fac, std::min<int64_t>(fac_len, s->plan.fac_size) * sizeof(double), cudaMemcpyDeviceToHost), B200_ERROR_CUDA_MEMCPY);
+    if (dinv) CUDA_TRY(cudaMemcpy(dinv, s->d_dinv, std::min<int64_t>(dinv_len, s->plan.dinv_size) * sizeof(double), cudaMemcpyDeviceToHost), B200_ERROR_CUDA_MEMCPY);
+    if (lperm) CUDA_TRY(cudaMemcpy(lperm, s->d_lperm, std::min<int64_t>(n, s->n) * sizeof(int), cudaMemcpyDeviceToHost), B200_ERROR_CUDA_MEMCPY);
+    return B200_SUCCESSFUL_EXIT;
+}
+
+} // extern "C"

@@ -1,0 +1,564 @@
+// symbolic.cpp -- elimination tree, column counts, relaxed supernodes, front plan (host, once per structure).
+//
+// Reference role: umfpack_di_symbolic (russell_sparse/c_code/interface_umfpack.c:109) /
+// CUDSS_PHASE_ANALYSIS (russell_sparse/c_code/interface_cudss.cu:361).  The algorithms are the textbook
+// ones (Liu's elimination tree with path compression, Gilbert-Ng-Peyton column counts, supernode
+// amalgamation with an explicit-zero budget); the code is written from scratch for the flat, GPU-facing
+// Plan layout in plan.hpp.
+#include "plan.hpp"
+
+#include <algorithm>
+#include <cassert>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <numeric>
+
+namespace b200 {
+
+namespace {
+double now_s() {
+    using namespace std::chrono;
+    return duration<double>(steady_clock::now().time_since_epoch()).count();
+}
+inline int64_t round_up4(int64_t x) { return (x + 3) & ~int64_t(3); }
+} // namespace
+
+// Liu's algorithm on a symmetric graph (uses the neighbours i < k of every vertex k)
+void etree_symmetric(const Graph& g, std::vector<int>& parent) {
+    const int n = g.n;
+    parent.assign(n, -1);
+    std::vector<int> anc(n, -1);
+    for (int k = 0; k < n; k++) {
+        for (int e = g.ptr[k]; e < g.ptr[k + 1]; e++) {
+            int i = g.adj[e];
+            while (i != -1 && i < k) {
+                int nxt = anc[i];
+                anc[i] = k;
+                if (nxt == -1) parent[i] = k;
+                i = nxt;
+            }
+        }
+    }
+}
+
+// post[k] = vertex visited k-th; children are visited in increasing `weight` (heaviest child last)
+void postorder_tree(const std::vector<int>& parent, const std::vector<int>& weight, std::vector<int>& post) {
+    const int n = (int)parent.size();
+    std::vector<int> cptr(n + 2, 0), cidx(n);
+    // bucket children under their parent; virtual root = n
+    for (int v = 0; v < n; v++) cptr[(parent[v] < 0 ? n : parent[v]) + 1]++;
+    for (int v = 0; v <= n; v++) cptr[v + 1] += cptr[v];
+    {
+        std::vector<int> fill(cptr.begin(), cptr.end() - 1);
+        for (int v = 0; v < n; v++) cidx[fill[parent[v] < 0 ? n : parent[v]]++] = v;
+    }
+    if (!weight.empty()) {
+        for (int v = 0; v <= n; v++) {
+            int a = cptr[v], b = cptr[v + 1];
+            if (b - a > 1)
+                std::stable_sort(cidx.begin() + a, cidx.begin() + b, [&](int x, int y) { return weight[x] < weight[y]; });
+        }
+    }
+    post.clear();
+    post.reserve(n);
+    // iterative DFS
+    std::vector<int> stack, it(n + 1);
+    for (int v = 0; v <= n; v++) it[v] = cptr[v];
+    stack.push_back(n);
+    while (!stack.empty()) {
+        int v = stack.back();
+        if (it[v] < cptr[v + 1]) {
+            stack.push_back(cidx[it[v]++]);
+        } else {
+            stack.pop_back();
+            if (v != n) post.push_back(v);
+        }
+    }
+}
+
+// Gilbert-Ng-Peyton column counts of the Cholesky factor of a symmetric pattern (diagonal included)
+static void column_counts_post(const Graph& g, const std::vector<int>& parent, const std::vector<int>& post,
+                               std::vector<int>& cc) {
+    const int n = g.n;
+    std::vector<int> first(n, -1), maxfirst(n, -1), prevleaf(n, -1), anc(n);
+    cc.assign(n, 0);
+    for (int k = 0; k < n; k++) {
+        int j = post[k];
+        cc[j] = (first[j] == -1) ? 1 : 0;
+        for (; j != -1 && first[j] == -1; j = parent[j]) first[j] = k;
+    }
+    std::iota(anc.begin(), anc.end(), 0);
+    for (int k = 0; k < n; k++) {
+        int j = post[k];
+        if (parent[j] != -1) cc[parent[j]]--;
+        for (int e = g.ptr[j]; e < g.ptr[j + 1]; e++) {
+            int i = g.adj[e];
+            if (i <= j || first[j] <= maxfirst[i]) continue;
+            maxfirst[i] = first[j];
+            int jprev = prevleaf[i];
+            prevleaf[i] = j;
+            if (jprev == -1) {
+                cc[j]++;
+            } else {
+                int q = jprev;
+                while (q != anc[q]) q = anc[q];
+                for (int s = jprev; s != q;) {
+                    int sp = anc[s];
+                    anc[s] = q;
+                    s = sp;
+                }
+                cc[j]++;
+                cc[q]--;
+            }
+        }
+        if (parent[j] != -1) anc[j] = parent[j];
+    }
+    for (int j = 0; j < n; j++)
+        if (parent[j] != -1) cc[parent[j]] += cc[j];
+}
+
+void column_counts(const Graph& g, const std::vector<int>& parent, std::vector<int>& cc) {
+    std::vector<int> post, none;
+    postorder_tree(parent, none, post);
+    column_counts_post(g, parent, post, cc);
+}
+
+// relabels a symmetric graph: vertex old -> inv[old]
+static void relabel_graph(const Graph& g, const std::vector<int>& perm /*new->old*/, Graph& out) {
+    const int n = g.n;
+    std::vector<int> inv(n);
+    for (int k = 0; k < n; k++) inv[perm[k]] = k;
+    out.n = n;
+    out.ptr.assign(n + 1, 0);
+    for (int k = 0; k < n; k++) out.ptr[k + 1] = out.ptr[k] + (g.ptr[perm[k] + 1] - g.ptr[perm[k]]);
+    out.adj.resize(g.adj.size());
+    for (int k = 0; k < n; k++) {
+        int o = perm[k], d = out.ptr[k];
+        for (int e = g.ptr[o]; e < g.ptr[o + 1]; e++) out.adj[d++] = inv[g.adj[e]];
+        std::sort(out.adj.begin() + out.ptr[k], out.adj.begin() + out.ptr[k + 1]);
+    }
+}
+
+int analyze(int n, const int* rowptr, const int* colidx, const double* vals, bool sym_lower,
+            const AnalyzeOptions& opt, Plan& P) {
+    P = Plan();
+    P.opt = opt;
+    P.n = n;
+    P.sym_lower = sym_lower;
+    if (n < 1 || rowptr == nullptr || colidx == nullptr) return -2;
+    const int nnz = rowptr[n];
+    P.nnz_in = nnz;
+    if (rowptr[0] != 0 || nnz < 1) return -2;
+    for (int i = 0; i < n; i++) {
+        if (rowptr[i + 1] < rowptr[i]) return -2;
+        for (int k = rowptr[i]; k < rowptr[i + 1]; k++) {
+            int j = colidx[k];
+            if (j < 0 || j >= n) return -2;
+            if (sym_lower && j > i) return -2;
+        }
+    }
+    const int W = std::max(4, std::min(opt.panel_width, 128));
+
+    // ---- full (mirrored) CSR of the original matrix -------------------------------------------------
+    std::vector<int>&fptr = P.full_ptr, &fcol = P.full_col, &fsrc = P.full_src;
+    if (sym_lower) {
+        fptr.assign(n + 1, 0);
+        for (int i = 0; i < n; i++)
+            for (int k = rowptr[i]; k < rowptr[i + 1]; k++) {
+                fptr[i + 1]++;
+                if (colidx[k] != i) fptr[colidx[k] + 1]++;
+            }
+        for (int i = 0; i < n; i++) fptr[i + 1] += fptr[i];
+        fcol.resize(fptr[n]);
+        fsrc.resize(fptr[n]);
+        std::vector<int> fill(fptr.begin(), fptr.end() - 1);
+        // rows are visited in increasing order, so each row's columns come out sorted:
+        // mirrored entries (j,i) with i>j land after row j's own lower entries (cols <= j)
+        for (int i = 0; i < n; i++)
+            for (int k = rowptr[i]; k < rowptr[i + 1]; k++) {
+                int j = colidx[k];
+                fcol[fill[i]] = j, fsrc[fill[i]] = k, fill[i]++;
+            }
+        // second sweep for the mirrored part keeps ascending column order per row
+        for (int i = 0; i < n; i++)
+            for (int k = rowptr[i]; k < rowptr[i + 1]; k++) {
+                int j = colidx[k];
+                if (j != i) fcol[fill[j]] = i, fsrc[fill[j]] = k, fill[j]++;
+            }
+        for (int i = 0; i < n; i++) { // lower entries of a row might be unsorted in the input: sort pairs
+            int a = fptr[i], b = fptr[i + 1];
+            bool sorted = true;
+            for (int k = a + 1; k < b; k++)
+                if (fcol[k] < fcol[k - 1]) sorted = false;
+            if (!sorted) {
+                std::vector<std::pair<int, int>> tmp(b - a);
+                for (int k = a; k < b; k++) tmp[k - a] = {fcol[k], fsrc[k]};
+                std::sort(tmp.begin(), tmp.end());
+                for (int k = a; k < b; k++) fcol[k] = tmp[k - a].first, fsrc[k] = tmp[k - a].second;
+            }
+        }
+    } else {
+        fptr.assign(rowptr, rowptr + n + 1);
+        fcol.assign(colidx, colidx + nnz);
+        fsrc.clear(); // identity
+    }
+    const int fnnz = fptr[n];
+    auto src_of = [&](int k) { return fsrc.empty() ? k : fsrc[k]; };
+
+    // ---- matching / scaling ----------------------------------------------------------------------------
+    double t0 = now_s();
+    std::vector<int> rowmatch; // rowmatch[j] = row matched to column j
+    bool want_match = (opt.matching == 1);
+    if (opt.matching == 2 && vals != nullptr) {
+        // auto: only when some diagonal entry is structurally or numerically zero
+        for (int i = 0; i < n && !want_match; i++) {
+            bool ok = false;
+            for (int k = fptr[i]; k < fptr[i + 1]; k++)
+                if (fcol[k] == i && vals[src_of(k)] != 0.0) ok = true;
+            if (!ok) want_match = true;
+        }
+    }
+    if (want_match && vals != nullptr) {
+        std::vector<double> fv(fnnz);
+        for (int k = 0; k < fnnz; k++) fv[k] = vals[src_of(k)];
+        int matched = max_product_matching(n, fptr.data(), fcol.data(), fv.data(), rowmatch, P.rscale, P.cscale);
+        if (matched < n) return -1; // structurally singular
+        P.matched = false;
+        for (int j = 0; j < n; j++)
+            if (rowmatch[j] != j) P.matched = true;
+    } else {
+        rowmatch.resize(n);
+        std::iota(rowmatch.begin(), rowmatch.end(), 0);
+    }
+    std::vector<int> colmatch(n); // colmatch[i] = column matched to row i
+    for (int j = 0; j < n; j++) colmatch[rowmatch[j]] = j;
+    P.t_match = now_s() - t0;
+
+    // ---- graph of A' + A'^T (A' = row-permuted A, vertex = column index) --------------------------------
+    t0 = now_s();
+    Graph g0;
+    g0.n = n;
+    {
+        std::vector<int> deg(n + 1, 0);
+        for (int i = 0; i < n; i++) {
+            int ip = colmatch[i];
+            for (int k = fptr[i]; k < fptr[i + 1]; k++) {
+                int j = fcol[k];
+                if (j != ip) deg[ip + 1]++, deg[j + 1]++;
+            }
+        }
+        for (int i = 0; i < n; i++) deg[i + 1] += deg[i];
+        std::vector<int> adj(deg[n]);
+        std::vector<int> fill(deg.begin(), deg.end() - 1);
+        for (int i = 0; i < n; i++) {
+            int ip = colmatch[i];
+            for (int k = fptr[i]; k < fptr[i + 1]; k++) {
+                int j = fcol[k];
+                if (j != ip) adj[fill[ip]++] = j, adj[fill[j]++] = ip;
+            }
+        }
+        g0.ptr.assign(n + 1, 0);
+        g0.adj.reserve(adj.size());
+        for (int v = 0; v < n; v++) {
+            std::sort(adj.begin() + deg[v], adj.begin() + deg[v + 1]);
+            int prev = -1;
+            for (int e = deg[v]; e < deg[v + 1]; e++)
+                if (adj[e] != prev) g0.adj.push_back(prev = adj[e]);
+            g0.ptr[v + 1] = (int)g0.adj.size();
+        }
+    }
+
+    // ---- fill-reducing ordering ----------------------------------------------------------------------
+    std::vector<int> q; // new -> old
+    if (opt.ordering == ORDERING_NATURAL) {
+        q.resize(n);
+        std::iota(q.begin(), q.end(), 0);
+    } else if (opt.ordering == ORDERING_MINDEG) {
+        order_minimum_degree(g0, q);
+    } else {
+        order_nested_dissection(g0, opt.nd_leaf, q);
+    }
+    P.t_order = now_s() - t0;
+
+    // ---- elimination tree, postorder (heaviest child last), final labelling -----------------------------
+    t0 = now_s();
+    Graph g;
+    std::vector<int> parent, cc;
+    {
+        Graph g1;
+        relabel_graph(g0, q, g1);
+        std::vector<int> par1, cc1, post1, none;
+        etree_symmetric(g1, par1);
+        postorder_tree(par1, none, post1);
+        column_counts_post(g1, par1, post1, cc1);
+        std::vector<int> post;
+        postorder_tree(par1, cc1, post);
+        std::vector<int> q2(n);
+        for (int k = 0; k < n; k++) q2[k] = q[post[k]];
+        q.swap(q2);
+        relabel_graph(g0, q, g);
+        etree_symmetric(g, parent);
+        std::vector<int> ident(n);
+        std::iota(ident.begin(), ident.end(), 0);
+        column_counts_post(g, parent, ident, cc);
+    }
+    g0 = Graph();
+    std::vector<int> invq(n);
+    for (int k = 0; k < n; k++) invq[q[k]] = k;
+    P.colperm = q;
+    P.rowperm.resize(n);
+    for (int k = 0; k < n; k++) P.rowperm[k] = rowmatch[q[k]];
+
+    // ---- fundamental supernodes, then relaxed amalgamation -------------------------------------------
+    struct Grp {
+        int first, ncols;
+        int64_t f;     // front order (pivots + update rows) predicted from the column counts
+        int64_t zeros; // explicit zeros accumulated in the L panel
+    };
+    std::vector<Grp> grp;
+    for (int j = 0; j < n; j++) {
+        bool join = j > 0 && parent[j - 1] == j && cc[j] == cc[j - 1] - 1;
+        if (join) grp.back().ncols++;
+        else grp.push_back({j, 1, cc[j], 0});
+    }
+    P.nsuper_fundamental = (int)grp.size();
+    {
+        std::vector<Grp> out;
+        out.reserve(grp.size());
+        for (const Grp& gnew : grp) {
+            out.push_back(gnew);
+            while (out.size() >= 2) {
+                Grp& par = out[out.size() - 1];
+                Grp& ch = out[out.size() - 2];
+                int lastc = ch.first + ch.ncols - 1;
+                if (parent[lastc] != par.first) break; // not the contiguous last child
+                int64_t a = ch.ncols, b = par.ncols, nm = a + b;
+                int64_t fm = a + par.f;
+                int64_t newz = a * (fm - ch.f);
+                int64_t z = ch.zeros + par.zeros + newz;
+                int64_t lnz = nm * fm - nm * (nm - 1) / 2;
+                double ratio = lnz > 0 ? (double)z / (double)lnz : 0.0;
+                bool merge;
+                if (nm <= opt.relax_small) merge = true;
+                else if (nm <= 32) merge = ratio <= opt.relax_z1;
+                else if (nm <= W) merge = ratio <= opt.relax_z2;
+                else merge = ratio <= opt.relax_z3;
+                if (!merge) break;
+                Grp m{ch.first, (int)nm, fm, z};
+                out.pop_back();
+                out.back() = m;
+            }
+        }
+        grp.swap(out);
+    }
+    const int ns = (int)grp.size();
+    P.nsuper_relaxed = ns;
+    std::vector<int> col2sn(n);
+    for (int s = 0; s < ns; s++)
+        for (int j = grp[s].first; j < grp[s].first + grp[s].ncols; j++) col2sn[j] = s;
+    std::vector<int> sparent(ns, -1);
+    for (int s = 0; s < ns; s++) {
+        int lastc = grp[s].first + grp[s].ncols - 1;
+        sparent[s] = parent[lastc] < 0 ? -1 : col2sn[parent[lastc]];
+    }
+
+    // ---- row structure of every supernode (rows beyond its last column, ascending) ----------------------
+    std::vector<std::vector<int>> srows(ns);
+    {
+        std::vector<int> mark(n, -1);
+        std::vector<int> scptr(ns + 1, 0), scidx(ns);
+        for (int s = 0; s < ns; s++)
+            if (sparent[s] >= 0) scptr[sparent[s] + 1]++;
+        for (int s = 0; s < ns; s++) scptr[s + 1] += scptr[s];
+        {
+            std::vector<int> fill(scptr.begin(), scptr.end() - 1);
+            for (int s = 0; s < ns; s++)
+                if (sparent[s] >= 0) scidx[fill[sparent[s]]++] = s;
+        }
+        for (int s = 0; s < ns; s++) {
+            const int first = grp[s].first, last = first + grp[s].ncols - 1;
+            std::vector<int>& r = srows[s];
+            for (int j = first; j <= last; j++)
+                for (int e = g.ptr[j]; e < g.ptr[j + 1]; e++) {
+                    int i = g.adj[e];
+                    if (i > last && mark[i] != s) mark[i] = s, r.push_back(i);
+                }
+            for (int e = scptr[s]; e < scptr[s + 1]; e++) {
+                int c = scidx[e];
+                for (int i : srows[c])
+                    if (i > last && mark[i] != s) mark[i] = s, r.push_back(i);
+            }
+            std::sort(r.begin(), r.end());
+            if ((int64_t)r.size() + grp[s].ncols != grp[s].f) {
+                if (opt.verbose)
+                    fprintf(stderr, "b200 analyze: supernode %d predicted front %lld, found %lld\n", s,
+                            (long long)grp[s].f, (long long)(r.size() + grp[s].ncols));
+                grp[s].f = (int64_t)r.size() + grp[s].ncols; // the enumerated structure is authoritative
+            }
+        }
+    }
+    g = Graph();
+
+    // ---- split wide supernodes into panels: the front tree ------------------------------------------------
+    std::vector<int> sn_firstnode(ns), sn_npieces(ns);
+    int nnodes = 0;
+    for (int s = 0; s < ns; s++) {
+        int K = (grp[s].ncols + W - 1) / W;
+        sn_firstnode[s] = nnodes;
+        sn_npieces[s] = K;
+        nnodes += K;
+    }
+    P.nnodes = nnodes;
+    P.c0.resize(nnodes), P.p.resize(nnodes), P.u.resize(nnodes), P.parent.assign(nnodes, -1), P.level.assign(nnodes, 0);
+    P.Loff.resize(nnodes), P.Uoff.resize(nnodes), P.Coff.resize(nnodes), P.Doff.resize(nnodes);
+    P.rows_ptr.assign(nnodes + 1, 0);
+    std::vector<int> col2node(n);
+    for (int s = 0; s < ns; s++) {
+        const int K = sn_npieces[s], nc = grp[s].ncols;
+        int off = 0;
+        for (int k = 0; k < K; k++) {
+            int w = nc / K + (k < nc % K ? 1 : 0);
+            int v = sn_firstnode[s] + k;
+            P.c0[v] = grp[s].first + off;
+            P.p[v] = w;
+            P.u[v] = (nc - off - w) + (int)srows[s].size();
+            P.parent[v] = (k + 1 < K) ? v + 1 : (sparent[s] >= 0 ? sn_firstnode[sparent[s]] : -1);
+            for (int j = 0; j < w; j++) col2node[P.c0[v] + j] = v;
+            off += w;
+            P.rows_ptr[v + 1] = P.rows_ptr[v] + P.u[v];
+        }
+    }
+    P.rows.resize(P.rows_ptr[nnodes]);
+    P.rel.assign(P.rows_ptr[nnodes], -1);
+    for (int s = 0; s < ns; s++) {
+        const int K = sn_npieces[s];
+        const int lastcol = grp[s].first + grp[s].ncols - 1;
+        for (int k = 0; k < K; k++) {
+            int v = sn_firstnode[s] + k;
+            int* r = &P.rows[P.rows_ptr[v]];
+            int t = 0;
+            for (int j = P.c0[v] + P.p[v]; j <= lastcol; j++) r[t++] = j; // remaining columns of the supernode
+            for (int i : srows[s]) r[t++] = i;
+            assert(t == P.u[v]);
+        }
+    }
+    // relative indices into the parent front
+    for (int s = 0; s < ns; s++) {
+        const int K = sn_npieces[s];
+        for (int k = 0; k < K; k++) {
+            int v = sn_firstnode[s] + k;
+            int* rel = &P.rel[P.rows_ptr[v]];
+            if (k + 1 < K) {
+                for (int i = 0; i < P.u[v]; i++) rel[i] = i; // the next panel's front is exactly this update set
+            } else if (sparent[s] >= 0) {
+                int t = sparent[s];
+                const int tfirst = grp[t].first, tn = grp[t].ncols;
+                const std::vector<int>& tr = srows[t];
+                size_t w = 0;
+                const int* r = &P.rows[P.rows_ptr[v]];
+                for (int i = 0; i < P.u[v]; i++) {
+                    int gi = r[i];
+                    if (gi < tfirst + tn) {
+                        rel[i] = gi - tfirst;
+                    } else {
+                        while (w < tr.size() && tr[w] < gi) w++;
+                        if (w >= tr.size() || tr[w] != gi) return -2; // structure inconsistency (should not happen)
+                        rel[i] = tn + (int)w;
+                    }
+                }
+            }
+        }
+    }
+    // children lists + levels
+    P.child_ptr.assign(nnodes + 1, 0);
+    P.child_idx.resize(nnodes);
+    for (int v = 0; v < nnodes; v++)
+        if (P.parent[v] >= 0) P.child_ptr[P.parent[v] + 1]++;
+    for (int v = 0; v < nnodes; v++) P.child_ptr[v + 1] += P.child_ptr[v];
+    {
+        std::vector<int> fill(P.child_ptr.begin(), P.child_ptr.end() - 1);
+        for (int v = 0; v < nnodes; v++)
+            if (P.parent[v] >= 0) P.child_idx[fill[P.parent[v]]++] = v;
+    }
+    P.child_idx.resize(P.child_ptr[nnodes]);
+    int nlev = 0;
+    for (int v = 0; v < nnodes; v++) { // children precede parents
+        if (P.parent[v] >= 0) P.level[P.parent[v]] = std::max(P.level[P.parent[v]], P.level[v] + 1);
+        nlev = std::max(nlev, P.level[v] + 1);
+    }
+    P.nlevels = nlev;
+    P.level_ptr.assign(nlev + 1, 0);
+    for (int v = 0; v < nnodes; v++) P.level_ptr[P.level[v] + 1]++;
+    for (int l = 0; l < nlev; l++) P.level_ptr[l + 1] += P.level_ptr[l];
+    P.level_nodes.resize(nnodes);
+    {
+        std::vector<int> fill(P.level_ptr.begin(), P.level_ptr.end() - 1);
+        for (int v = 0; v < nnodes; v++) P.level_nodes[fill[P.level[v]]++] = v;
+    }
+    // storage offsets + stats
+    int64_t fo = 0, co = 0, dof = 0;
+    for (int v = 0; v < nnodes; v++) {
+        int64_t p = P.p[v], u = P.u[v], f = p + u;
+        P.Loff[v] = fo, fo = round_up4(fo + f * p);
+        P.Uoff[v] = fo, fo = round_up4(fo + u * p);
+        P.Coff[v] = co, co = round_up4(co + u * u);
+        P.Doff[v] = dof, dof = round_up4(dof + p * p);
+        P.nnz_L += f * p;
+        P.nnz_U += u * p;
+        P.flops += (2.0 / 3.0) * p * p * p + 2.0 * p * p * u + 2.0 * (double)p * u * u;
+        P.max_front = std::max<int>(P.max_front, (int)f);
+    }
+    P.fac_size = fo, P.cb_size = co, P.dinv_size = dof;
+
+    // ---- value scatter map ---------------------------------------------------------------------------
+    const bool scaled = !P.rscale.empty();
+    P.a_src.resize(fnnz);
+    P.a_dst.resize(fnnz);
+    if (scaled) P.a_scl.resize(fnnz);
+    for (int i = 0; i < n; i++) {
+        const int kr = invq[colmatch[i]];
+        for (int k = fptr[i]; k < fptr[i + 1]; k++) {
+            const int j = fcol[k];
+            const int kc = invq[j];
+            int64_t dst;
+            if (kc <= kr) { // lower triangle (incl. diagonal): column kc's node, L panel
+                int v = col2node[kc];
+                int64_t f = P.p[v] + P.u[v];
+                int rpos;
+                if (kr < P.c0[v] + P.p[v]) rpos = kr - P.c0[v];
+                else {
+                    const int* r = &P.rows[P.rows_ptr[v]];
+                    const int* it = std::lower_bound(r, r + P.u[v], kr);
+                    if (it == r + P.u[v] || *it != kr) return -2;
+                    rpos = P.p[v] + (int)(it - r);
+                }
+                dst = P.Loff[v] + rpos + (int64_t)(kc - P.c0[v]) * f;
+            } else { // upper triangle: row kr's node
+                int v = col2node[kr];
+                int64_t f = P.p[v] + P.u[v];
+                if (kc < P.c0[v] + P.p[v]) dst = P.Loff[v] + (kr - P.c0[v]) + (int64_t)(kc - P.c0[v]) * f;
+                else {
+                    const int* r = &P.rows[P.rows_ptr[v]];
+                    const int* it = std::lower_bound(r, r + P.u[v], kc);
+                    if (it == r + P.u[v] || *it != kc) return -2;
+                    dst = P.Uoff[v] + (int64_t)(it - r) + (int64_t)(kr - P.c0[v]) * P.u[v];
+                }
+            }
+            P.a_src[k] = src_of(k);
+            P.a_dst[k] = dst;
+            if (scaled) P.a_scl[k] = P.rscale[i] * P.cscale[j];
+        }
+    }
+    P.t_symbolic = now_s() - t0;
+    if (opt.verbose) {
+        fprintf(stderr,
+                "b200 analyze: n=%d nnz=%d nodes=%d (fund %d, relaxed %d) levels=%d nnz(L)=%lld nnz(U)=%lld "
+                "flops=%.3e maxfront=%d cb=%.1f MB  t(match,order,symb)=%.3f %.3f %.3f s\n",
+                n, fnnz, nnodes, P.nsuper_fundamental, P.nsuper_relaxed, P.nlevels, (long long)P.nnz_L,
+                (long long)P.nnz_U, P.flops, P.max_front, P.cb_size * 8e-6, P.t_match, P.t_order, P.t_symbolic);
+    }
+    return 0;
+}
+
+} // namespace b200
