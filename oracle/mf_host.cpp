@@ -293,4 +293,46 @@ int oracle_mf_analyze(int n, const int* rowptr, const int* colidx, const double*
     stats[8] = P.t_order, stats[9] = P.t_symbolic;
     return 0;
 }
+
+// ---- handle API (used by the GPU parity tests to compare factor panels array-by-array) --------------------
+void* oracle_mf_create(int n, const int* rowptr, const int* colidx, const double* vals, int sym_lower, int ordering,
+                       int matching, int panel_width, int nd_leaf, double pivot_eps, int* status) {
+    HostSolver* S = new HostSolver();
+    AnalyzeOptions opt;
+    opt.ordering = ordering;
+    opt.matching = matching;
+    if (panel_width > 0) opt.panel_width = panel_width;
+    if (nd_leaf > 0) opt.nd_leaf = nd_leaf;
+    int rc = analyze(n, rowptr, colidx, vals, sym_lower != 0, opt, S->P);
+    if (rc != 0) {
+        *status = rc;
+        delete S;
+        return nullptr;
+    }
+    host_factorize(*S, vals, pivot_eps > 0 ? pivot_eps : 1e-13);
+    *status = S->singular ? 1 : 0;
+    return S;
+}
+void oracle_mf_sizes(void* h, int64_t* out) { // fac, dinv, n, nnodes, perturbed
+    HostSolver* S = (HostSolver*)h;
+    out[0] = S->P.fac_size, out[1] = S->P.dinv_size, out[2] = S->P.n, out[3] = S->P.nnodes, out[4] = S->n_perturbed;
+}
+// lperm: composed local permutation per front (row at position k after pivoting = original local row lperm[k])
+void oracle_mf_get(void* h, double* fac, double* dinv, int* lperm) {
+    HostSolver* S = (HostSolver*)h;
+    if (fac) std::copy(S->fac.begin(), S->fac.end(), fac);
+    if (dinv) std::copy(S->dinv.begin(), S->dinv.end(), dinv);
+    if (lperm) {
+        const Plan& P = S->P;
+        for (int v = 0; v < P.nnodes; v++) {
+            const int p = P.p[v], c0 = P.c0[v];
+            for (int k = 0; k < p; k++) lperm[c0 + k] = k;
+            for (int k = 0; k < p; k++) std::swap(lperm[c0 + k], lperm[c0 + S->piv[c0 + k]]);
+        }
+    }
+}
+void oracle_mf_handle_solve(void* h, const double* vals, const double* b, double* x, int nrefine, double* resid) {
+    host_solve(*(HostSolver*)h, vals, b, x, nrefine, resid);
+}
+void oracle_mf_free(void* h) { delete (HostSolver*)h; }
 }

@@ -18,10 +18,19 @@
 
 namespace b200 {
 
-int max_product_matching(int n, const int* rowptr, const int* colidx, const double* vals,
+static int matching_impl(int n, const int* rowptr, const int* colidx, const double* vals_in, bool zeros_as_tiny,
                          std::vector<int>& rowmatch, std::vector<double>& rscale, std::vector<double>& cscale) {
     const double INF = std::numeric_limits<double>::infinity();
     const int nnz = rowptr[n];
+    // structural mode: stored entries that are exactly zero stay usable, at a prohibitive (but finite) cost
+    std::vector<double> tmp;
+    const double* vals = vals_in;
+    if (zeros_as_tiny) {
+        tmp.assign(vals_in, vals_in + nnz);
+        for (int k = 0; k < nnz; k++)
+            if (tmp[k] == 0.0) tmp[k] = 1e-150;
+        vals = tmp.data();
+    }
     // CSC copy with costs
     std::vector<int> cp(n + 1, 0), ri(nnz);
     std::vector<double> cost(nnz);
@@ -149,9 +158,26 @@ int max_product_matching(int n, const int* rowptr, const int* colidx, const doub
     if (matched < n) return matched;
     rscale.resize(n);
     cscale.resize(n);
-    for (int i = 0; i < n; i++) rscale[i] = std::exp(u[i]);
-    for (int j = 0; j < n; j++) cscale[j] = std::exp(v[j]) / colmax[j];
+    bool sane = !zeros_as_tiny;
+    for (int i = 0; i < n && sane; i++)
+        if (!(std::fabs(u[i]) < 200.0) || !(std::fabs(v[i]) < 200.0)) sane = false;
+    if (sane) {
+        for (int i = 0; i < n; i++) rscale[i] = std::exp(u[i]);
+        for (int j = 0; j < n; j++) cscale[j] = std::exp(v[j]) / colmax[j];
+    } else { // keep the permutation, drop the scaling (it would overflow / be dominated by the placeholder entries)
+        rscale.clear();
+        cscale.clear();
+    }
     return matched;
+}
+
+int max_product_matching(int n, const int* rowptr, const int* colidx, const double* vals,
+                         std::vector<int>& rowmatch, std::vector<double>& rscale, std::vector<double>& cscale) {
+    int m = matching_impl(n, rowptr, colidx, vals, false, rowmatch, rscale, cscale);
+    if (m == n) return m;
+    // no perfect matching on the numerically nonzero entries: the values seen at analysis time may contain
+    // explicit zeros that later become nonzero (Jacobian structures), so retry on the stored PATTERN
+    return matching_impl(n, rowptr, colidx, vals, true, rowmatch, rscale, cscale);
 }
 
 } // namespace b200

@@ -237,7 +237,8 @@ void nd_component(NdCtx& c, std::vector<int>& verts, int id, int* out, std::vect
     // refinement: trim vertices that touch only one side, then zero-gain balancing moves
     for (int pass = 0; pass < 3; pass++) {
         bool changed = false;
-        for (int v : sep) {
+        for (size_t si = 0; si < sep.size(); si++) { // index loop: the balancing moves below append to `sep`
+            const int v = sep[si];
             if (c.label[v] != id) continue;
             int ca = 0, cb = 0;
             for (int e = c.g.ptr[v]; e < c.g.ptr[v + 1]; e++) {
