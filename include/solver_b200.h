@@ -127,6 +127,11 @@ int32_t solver_b200_set_option(struct InterfaceB200 *solver, const char *key, do
 int32_t solver_b200_debug_copy_factors(struct InterfaceB200 *solver, double *fac, int64_t fac_len,
                                        double *dinv, int64_t dinv_len, int32_t *lperm, int64_t n);
 
+/* the CUDA stream (cudaStream_t) every kernel of this handle is launched on, and its device ordinal: lets a
+ * caller bracket calls with its own CUDA events (bench.py) or order its own work after ours */
+void *solver_b200_get_stream(struct InterfaceB200 *solver);
+int32_t solver_b200_get_device(struct InterfaceB200 *solver);
+
 /* library identification string (static storage) */
 const char *solver_b200_version(void);
 

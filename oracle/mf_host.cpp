@@ -335,4 +335,26 @@ void oracle_mf_handle_solve(void* h, const double* vals, const double* b, double
     host_solve(*(HostSolver*)h, vals, b, x, nrefine, resid);
 }
 void oracle_mf_free(void* h) { delete (HostSolver*)h; }
+
+// analysis-only handle: node shapes for studying the front tree (p, u, level, parent per node)
+void* oracle_plan_create(int n, const int* rowptr, const int* colidx, const double* vals, int sym_lower, int ordering,
+                         int matching, int panel_width, int nd_leaf, int* nnodes) {
+    Plan* P = new Plan();
+    AnalyzeOptions opt;
+    opt.ordering = ordering;
+    opt.matching = matching;
+    if (panel_width > 0) opt.panel_width = panel_width;
+    if (nd_leaf > 0) opt.nd_leaf = nd_leaf;
+    if (analyze(n, rowptr, colidx, vals, sym_lower != 0, opt, *P) != 0) {
+        delete P;
+        return nullptr;
+    }
+    *nnodes = P->nnodes;
+    return P;
+}
+void oracle_plan_nodes(void* h, int* p, int* u, int* level, int* parent) {
+    Plan* P = (Plan*)h;
+    for (int v = 0; v < P->nnodes; v++) p[v] = P->p[v], u[v] = P->u[v], level[v] = P->level[v], parent[v] = P->parent[v];
+}
+void oracle_plan_free(void* h) { delete (Plan*)h; }
 }

@@ -35,6 +35,8 @@ SIGNATURES = {
     "solver_b200_set_option": (c_i32, [p_void, ctypes.c_char_p, c_f64]),
     "solver_b200_debug_copy_factors": (c_i32, [p_void, p_f64, c_i64, p_f64, c_i64, p_i32, c_i64]),
     "solver_b200_version": (ctypes.c_char_p, []),
+    "solver_b200_get_stream": (p_void, [p_void]),
+    "solver_b200_get_device": (c_i32, [p_void]),
     # host formats (russell_b200/csrc/host_formats.cpp)
     "b200_coo_to_csr": (c_i32, [c_i32, c_i32, c_i32, p_i32, p_i32, p_f64, p_i32, p_i32, p_f64]),
     "b200_coo_to_csc": (c_i32, [c_i32, c_i32, c_i32, p_i32, p_i32, p_f64, p_i32, p_i32, p_f64]),

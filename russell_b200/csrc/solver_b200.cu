@@ -35,9 +35,23 @@ using namespace b200;
         }                                                                                           \
     } while (0)
 
+// front-size classes of the fused kernel: upper bound on f and CTA size; class NFC = "big" (multi-kernel path)
+static const int NFC = 4;
+static const int FC_MAXF[NFC] = {16, 32, 64, B200_FUSED_MAXF};
+static const int FC_THREADS[NFC] = {32, 64, 128, 256};
+// solve classes: CTA size by front order
+static const int NSC = 3;
+static const int SC_MAXF[NSC] = {48, 256, 1 << 30};
+static const int SC_THREADS[NSC] = {32, 128, 256};
+
 struct LevelLists {
-    // offsets (nlevels+1) into the concatenated device item arrays
-    std::vector<int> asm_ptr, panel_ptr, schur_ptr, node_ptr;
+    // offsets (nlevels+1) into the concatenated device item arrays (big fronts only)
+    std::vector<int> asm_ptr, panel_ptr, schur_ptr;
+    // fact_ptr[l*(NFC+1)+c .. +1]: nodes of level l and factorization class c inside d_fact_nodes (class NFC = big)
+    std::vector<int> fact_ptr;
+    // solve_ptr[l*NSC+c .. +1] inside d_solve_nodes
+    std::vector<int> solve_ptr;
+    std::vector<size_t> fused_smem; // per (level, class): dynamic shared memory of the fused launch
 };
 
 struct InterfaceB200 {
@@ -50,6 +64,7 @@ struct InterfaceB200 {
     int opt_panel_width = 64, opt_nd_leaf = 96;
     int use_graph = 1;
     int schur_variant = 1; // 0 = FMA, 1 = DMMA
+    int use_fused = 1;     // fronts with f <= B200_FUSED_MAXF go through k_front_fused
     int nrefine = 2;
     double ir_tol = 1e-11;
     double pivot_eps = 1e-13;
@@ -63,7 +78,7 @@ struct InterfaceB200 {
 
     // device: plan
     NodeDev* d_nodes = nullptr;
-    int *d_rows = nullptr, *d_rel = nullptr, *d_child_idx = nullptr, *d_level_nodes = nullptr;
+    int *d_rows = nullptr, *d_rel = nullptr, *d_child_idx = nullptr, *d_fact_nodes = nullptr, *d_solve_nodes = nullptr;
     AsmItem* d_asm = nullptr;
     PanelItem* d_panel = nullptr;
     SchurItem* d_schur = nullptr;
@@ -95,7 +110,7 @@ struct InterfaceB200 {
     double last_rel_residual = -1.0;
     int last_refine_steps = 0;
     float ms_factorize = 0, ms_solve = 0, ms_sptrsv = 0, ms_spmv = 0;
-    int launches_factorize = 0, launches_solve = 0;
+    int launches_factorize = 0, launches_solve = 0, sweep_launches = 0;
     double sptrsv_bytes = 0, spmv_bytes = 0;
 };
 
@@ -120,7 +135,7 @@ void dfree(T*& p) {
 void release_device(InterfaceB200* s) {
     if (s->g_fact) cudaGraphExecDestroy(s->g_fact), s->g_fact = nullptr;
     if (s->g_sweep) cudaGraphExecDestroy(s->g_sweep), s->g_sweep = nullptr;
-    dfree(s->d_nodes), dfree(s->d_rows), dfree(s->d_rel), dfree(s->d_child_idx), dfree(s->d_level_nodes);
+    dfree(s->d_nodes), dfree(s->d_rows), dfree(s->d_rel), dfree(s->d_child_idx), dfree(s->d_fact_nodes), dfree(s->d_solve_nodes);
     dfree(s->d_asm), dfree(s->d_panel), dfree(s->d_schur);
     dfree(s->d_a_src), dfree(s->d_a_dst), dfree(s->d_a_scl);
     dfree(s->d_rowperm), dfree(s->d_colperm), dfree(s->d_rscale), dfree(s->d_cscale);
@@ -142,18 +157,54 @@ int grid_for(long long work, int block = 256, int cap = 148 * 16) {
 }
 
 // ---- work-item lists --------------------------------------------------------------------------------
+size_t smem_fused(int f, int p) { return ((size_t)(f | 1) * f + (size_t)p * p) * sizeof(double) + (size_t)p * sizeof(int); }
+
 void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::vector<PanelItem>& panel_items,
-                      std::vector<SchurItem>& schur_items) {
+                      std::vector<SchurItem>& schur_items, std::vector<int>& fact_nodes, std::vector<int>& solve_nodes) {
     const Plan& P = s->plan;
     LevelLists& lv = s->lv;
     lv.asm_ptr.assign(P.nlevels + 1, 0);
     lv.panel_ptr.assign(P.nlevels + 1, 0);
     lv.schur_ptr.assign(P.nlevels + 1, 0);
-    lv.node_ptr = P.level_ptr;
+    lv.fact_ptr.assign((size_t)P.nlevels * (NFC + 1) + 1, 0);
+    lv.solve_ptr.assign((size_t)P.nlevels * NSC + 1, 0);
+    lv.fused_smem.assign((size_t)P.nlevels * NFC, 0);
+    auto fclass = [&](int f) {
+        if (!s->use_fused) return NFC;
+        for (int c = 0; c < NFC; c++)
+            if (f <= FC_MAXF[c]) return c;
+        return NFC;
+    };
+    auto sclass = [&](int f) {
+        for (int c = 0; c < NSC; c++)
+            if (f <= SC_MAXF[c]) return c;
+        return NSC - 1;
+    };
     for (int l = 0; l < P.nlevels; l++) {
+        for (int c = 0; c <= NFC; c++) {
+            for (int e = P.level_ptr[l]; e < P.level_ptr[l + 1]; e++) {
+                const int v = P.level_nodes[e];
+                const int f = P.p[v] + P.u[v];
+                if (fclass(f) != c) continue;
+                fact_nodes.push_back(v);
+                if (c < NFC) {
+                    size_t& sm = lv.fused_smem[(size_t)l * NFC + c];
+                    sm = std::max(sm, smem_fused(f, P.p[v]));
+                }
+            }
+            lv.fact_ptr[(size_t)l * (NFC + 1) + c + 1] = (int)fact_nodes.size();
+        }
+        for (int c = 0; c < NSC; c++) {
+            for (int e = P.level_ptr[l]; e < P.level_ptr[l + 1]; e++) {
+                const int v = P.level_nodes[e];
+                if (sclass(P.p[v] + P.u[v]) == c) solve_nodes.push_back(v);
+            }
+            lv.solve_ptr[(size_t)l * NSC + c + 1] = (int)solve_nodes.size();
+        }
         for (int e = P.level_ptr[l]; e < P.level_ptr[l + 1]; e++) {
             const int v = P.level_nodes[e];
             const int p = P.p[v], u = P.u[v], f = p + u;
+            if (fclass(f) != NFC) continue; // fused fronts need no work items
             const int nch = P.child_ptr[v + 1] - P.child_ptr[v];
             if (nch > 0) {
                 double total = 0;
@@ -161,8 +212,8 @@ void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::ve
                     double uc = P.u[P.child_idx[c]];
                     total += uc * uc;
                 }
-                int ntiles = (int)std::ceil(total / 32768.0);
-                ntiles = std::max(1, std::min(ntiles, std::max(1, f / 4)));
+                int ntiles = (int)std::ceil(total / 8192.0);
+                ntiles = std::max(1, std::min(ntiles, std::max(1, f / 2)));
                 int tw = (f + ntiles - 1) / ntiles;
                 for (int t0 = 0; t0 < f; t0 += tw) asm_items.push_back({v, t0, std::min(f, t0 + tw), 0});
             }
@@ -185,21 +236,33 @@ size_t smem_panel(int W) { return (size_t)(W * W + B200_TR * W) * sizeof(double)
 size_t smem_schur_fma(int W) { return (size_t)2 * W * B200_TS * sizeof(double); }
 size_t smem_schur_dmma() { return (size_t)2 * B200_MAXP * (B200_TS + 1) * sizeof(double); }
 
-// enqueue the per-level numeric kernels (assembly -> pivot block -> panels -> Schur complement)
+// enqueue the per-level numeric kernels: fused fronts (one launch per size class), then the big-front path
+// (assembly -> pivot block -> panels -> Schur complement)
 int enqueue_levels(InterfaceB200* s, int* launches) {
     const Plan& P = s->plan;
     const LevelLists& lv = s->lv;
     const int W = s->opt_panel_width;
     int cnt = 0;
     for (int l = 0; l < P.nlevels; l++) {
+        const int* fp = &lv.fact_ptr[(size_t)l * (NFC + 1)];
+        for (int c = 0; c < NFC; c++) {
+            int nn = fp[c + 1] - fp[c];
+            if (nn > 0) {
+                k_front_fused<<<nn, FC_THREADS[c], lv.fused_smem[(size_t)l * NFC + c], s->stream>>>(
+                    s->d_fact_nodes + fp[c], s->d_nodes, s->d_child_idx, s->d_rel, s->d_fac, s->d_cb, s->d_dinv, s->d_lperm,
+                    s->d_upiv, s->d_amax, s->pivot_eps, s->d_counters);
+                cnt++;
+            }
+        }
+        int nbig = fp[NFC + 1] - fp[NFC];
+        if (nbig == 0) continue;
         int na = lv.asm_ptr[l + 1] - lv.asm_ptr[l];
         if (na > 0) {
             k_assemble<<<na, 256, 0, s->stream>>>(s->d_asm + lv.asm_ptr[l], s->d_nodes, s->d_child_idx, s->d_rel, s->d_fac, s->d_cb);
             cnt++;
         }
-        int nn = lv.node_ptr[l + 1] - lv.node_ptr[l];
-        k_diag<<<nn, 256, smem_diag(W), s->stream>>>(s->d_level_nodes + lv.node_ptr[l], s->d_nodes, s->d_fac, s->d_dinv,
-                                                       s->d_lperm, s->d_upiv, s->d_amax, s->pivot_eps, s->d_counters);
+        k_diag<<<nbig, 256, smem_diag(W), s->stream>>>(s->d_fact_nodes + fp[NFC], s->d_nodes, s->d_fac, s->d_dinv,
+                                                         s->d_lperm, s->d_upiv, s->d_amax, s->pivot_eps, s->d_counters);
         cnt++;
         int np = lv.panel_ptr[l + 1] - lv.panel_ptr[l];
         if (np > 0) {
@@ -224,15 +287,23 @@ int enqueue_sweep_levels(InterfaceB200* s, int* launches) {
     const LevelLists& lv = s->lv;
     int cnt = 0;
     for (int l = 0; l < P.nlevels; l++) {
-        int nn = lv.node_ptr[l + 1] - lv.node_ptr[l];
-        k_fwd<<<nn, 256, 0, s->stream>>>(s->d_level_nodes + lv.node_ptr[l], s->d_nodes, s->d_child_idx, s->d_rel, s->d_fac,
-                                          s->d_dinv, s->d_lperm, s->d_y, s->d_wv);
-        cnt++;
+        for (int c = 0; c < NSC; c++) {
+            int a = lv.solve_ptr[(size_t)l * NSC + c], b = lv.solve_ptr[(size_t)l * NSC + c + 1];
+            if (b > a) {
+                k_fwd<<<b - a, SC_THREADS[c], 0, s->stream>>>(s->d_solve_nodes + a, s->d_nodes, s->d_child_idx, s->d_rel, s->d_fac,
+                                                             s->d_dinv, s->d_lperm, s->d_y, s->d_wv);
+                cnt++;
+            }
+        }
     }
     for (int l = P.nlevels - 1; l >= 0; l--) {
-        int nn = lv.node_ptr[l + 1] - lv.node_ptr[l];
-        k_bwd<<<nn, 256, 0, s->stream>>>(s->d_level_nodes + lv.node_ptr[l], s->d_nodes, s->d_rows, s->d_fac, s->d_dinv, s->d_y, s->d_xp);
-        cnt++;
+        for (int c = 0; c < NSC; c++) {
+            int a = lv.solve_ptr[(size_t)l * NSC + c], b = lv.solve_ptr[(size_t)l * NSC + c + 1];
+            if (b > a) {
+                k_bwd<<<b - a, SC_THREADS[c], 0, s->stream>>>(s->d_solve_nodes + a, s->d_nodes, s->d_rows, s->d_fac, s->d_dinv, s->d_y, s->d_xp);
+                cnt++;
+            }
+        }
     }
     if (launches) *launches = cnt;
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
@@ -277,7 +348,8 @@ int sweep(InterfaceB200* s, const double* d_rhs, double* d_out, int accumulate, 
     int rc = run_maybe_graph(s, &s->g_sweep, enqueue_sweep_levels, &launches);
     if (time_it) cudaEventRecord(s->ev[5], s->stream);
     k_permute_out<<<grid_for(n), 256, 0, s->stream>>>(n, s->d_colperm, s->d_cscale, s->d_xp, d_out, accumulate);
-    s->launches_solve += 2 + 2 * s->plan.nlevels;
+    if (launches > 0) s->sweep_launches = launches;
+    s->launches_solve += 2 + s->sweep_launches;
     return rc;
 }
 
@@ -298,6 +370,10 @@ int residual(InterfaceB200* s, const double* d_xv, const double* d_rhs, double* 
 // =========================================================================================================
 extern "C" {
 
+void* solver_b200_get_stream(struct InterfaceB200* s) { return s ? (void*)s->stream : nullptr; }
+
+int32_t solver_b200_get_device(struct InterfaceB200* s) { return s ? s->device : -1; }
+
 const char* solver_b200_version(void) { return "solver_b200 0.1 (sm_100a, multifrontal LU f64)"; }
 
 struct InterfaceB200* solver_b200_new(void) {
@@ -310,8 +386,10 @@ struct InterfaceB200* solver_b200_new(void) {
     if (!s) return nullptr;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    const char* edev = getenv("B200_DEVICE"); // one process per GPU: the launcher may pin the device explicitly
+    if (edev && atoi(edev) >= 0 && atoi(edev) < ndev) dev = atoi(edev);
     s->device = dev;
-    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete s;
         return nullptr;
     }
@@ -323,6 +401,7 @@ struct InterfaceB200* solver_b200_new(void) {
     const char* e;
     if ((e = getenv("B200_NO_GRAPH")) && atoi(e)) s->use_graph = 0;
     if ((e = getenv("B200_SCHUR_VARIANT"))) s->schur_variant = atoi(e);
+    if ((e = getenv("B200_USE_FUSED"))) s->use_fused = atoi(e);
     if ((e = getenv("B200_PANEL_WIDTH"))) s->opt_panel_width = atoi(e);
     if ((e = getenv("B200_ND_LEAF"))) s->opt_nd_leaf = atoi(e);
     return s;
@@ -349,8 +428,24 @@ int32_t solver_b200_set_option(struct InterfaceB200* s, const char* key, double 
     else if (k == "nd_leaf") s->opt_nd_leaf = std::max(4, (int)value);
     else if (k == "use_graph") s->use_graph = value != 0.0;
     else if (k == "schur_variant") s->schur_variant = (int)value;
+    else if (k == "use_fused") s->use_fused = value != 0.0;
     else if (k == "force_no_matching") s->force_no_matching = value != 0.0;
-    else if (k == "device") s->device = (int)value;
+    else if (k == "device") {
+        // re-home the handle: the stream and the timing events belong to a device
+        int ndev = 0, dev = (int)value;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || dev < 0 || dev >= ndev) return B200_ERROR_NOT_AVAILABLE;
+        if (dev != s->device) {
+            cudaSetDevice(s->device);
+            for (int i = 0; i < 8; i++)
+                if (s->ev[i]) cudaEventDestroy(s->ev[i]), s->ev[i] = nullptr;
+            if (s->stream) cudaStreamDestroy(s->stream), s->stream = nullptr;
+            s->device = dev;
+            if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess)
+                return B200_ERROR_NOT_AVAILABLE;
+            for (int i = 0; i < 8; i++)
+                if (cudaEventCreate(&s->ev[i]) != cudaSuccess) return B200_ERROR_NOT_AVAILABLE;
+        }
+    }
     else return B200_ERROR_NOT_AVAILABLE;
     return 0;
 }
@@ -405,7 +500,8 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     std::vector<AsmItem> asm_items;
     std::vector<PanelItem> panel_items;
     std::vector<SchurItem> schur_items;
-    build_work_lists(s, asm_items, panel_items, schur_items);
+    std::vector<int> fact_nodes, solve_nodes;
+    build_work_lists(s, asm_items, panel_items, schur_items, fact_nodes, solve_nodes);
 
     // SpMV row blocks (rows never split; at most B200_SPMV_NNZ nonzeros and 1024 rows per block)
     std::vector<int> rowblk;
@@ -427,7 +523,8 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     UP(d_rows, P.rows);
     UP(d_rel, P.rel);
     UP(d_child_idx, P.child_idx);
-    UP(d_level_nodes, P.level_nodes);
+    UP(d_fact_nodes, fact_nodes);
+    UP(d_solve_nodes, solve_nodes);
     UP(d_asm, asm_items);
     UP(d_panel, panel_items);
     UP(d_schur, schur_items);
@@ -473,6 +570,7 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     // kernels that need more than 48 KB of dynamic shared memory
     const int W = s->opt_panel_width;
     CUDA_TRY(cudaFuncSetAttribute(k_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_diag(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
+    CUDA_TRY(cudaFuncSetAttribute(k_front_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused(B200_FUSED_MAXF, B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_panel(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_schur_fma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_schur_fma(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_schur_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_schur_dmma()), B200_ERROR_NOT_AVAILABLE);

@@ -310,47 +310,149 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
     P.rowperm.resize(n);
     for (int k = 0; k < n; k++) P.rowperm[k] = rowmatch[q[k]];
 
-    // ---- fundamental supernodes, then relaxed amalgamation -------------------------------------------
+    // ---- fundamental supernodes, then amalgamation over the supernode tree -------------------------------
+    // Any child may be merged into its parent (not only a contiguous last child): columns of different
+    // subtrees are independent, so the merged children's columns can be moved right in front of the parent's
+    // columns without changing the fill.  The budget is counted in STORED entries p*(2f-p) of the L/U panels.
     struct Grp {
         int first, ncols;
-        int64_t f;     // front order (pivots + update rows) predicted from the column counts
-        int64_t zeros; // explicit zeros accumulated in the L panel
+        int64_t f;     // front order (pivots + update rows)
+        int64_t zeros; // explicit zeros accumulated in the stored panels
     };
     std::vector<Grp> grp;
-    for (int j = 0; j < n; j++) {
-        bool join = j > 0 && parent[j - 1] == j && cc[j] == cc[j - 1] - 1;
-        if (join) grp.back().ncols++;
-        else grp.push_back({j, 1, cc[j], 0});
-    }
-    P.nsuper_fundamental = (int)grp.size();
     {
-        std::vector<Grp> out;
-        out.reserve(grp.size());
-        for (const Grp& gnew : grp) {
-            out.push_back(gnew);
-            while (out.size() >= 2) {
-                Grp& par = out[out.size() - 1];
-                Grp& ch = out[out.size() - 2];
-                int lastc = ch.first + ch.ncols - 1;
-                if (parent[lastc] != par.first) break; // not the contiguous last child
-                int64_t a = ch.ncols, b = par.ncols, nm = a + b;
-                int64_t fm = a + par.f;
-                int64_t newz = a * (fm - ch.f);
-                int64_t z = ch.zeros + par.zeros + newz;
-                int64_t lnz = nm * fm - nm * (nm - 1) / 2;
-                double ratio = lnz > 0 ? (double)z / (double)lnz : 0.0;
+        std::vector<Grp> fund;
+        for (int j = 0; j < n; j++) {
+            bool join = j > 0 && parent[j - 1] == j && cc[j] == cc[j - 1] - 1;
+            if (join) fund.back().ncols++;
+            else fund.push_back({j, 1, cc[j], 0});
+        }
+        const int nf = (int)fund.size();
+        P.nsuper_fundamental = nf;
+        std::vector<int> c2s(n);
+        for (int s = 0; s < nf; s++)
+            for (int j = fund[s].first; j < fund[s].first + fund[s].ncols; j++) c2s[j] = s;
+        std::vector<int> fpar(nf, -1);
+        for (int s = 0; s < nf; s++) {
+            int lastc = fund[s].first + fund[s].ncols - 1;
+            fpar[s] = parent[lastc] < 0 ? -1 : c2s[parent[lastc]];
+        }
+        // children lists of the fundamental supernode tree
+        std::vector<int> cptr(nf + 1, 0), cidx(nf);
+        for (int s = 0; s < nf; s++)
+            if (fpar[s] >= 0) cptr[fpar[s] + 1]++;
+        for (int s = 0; s < nf; s++) cptr[s + 1] += cptr[s];
+        {
+            std::vector<int> fill(cptr.begin(), cptr.end() - 1);
+            for (int s = 0; s < nf; s++)
+                if (fpar[s] >= 0) cidx[fill[fpar[s]]++] = s;
+        }
+        // bottom-up greedy merging; nc/ff/zz describe the merged group rooted at s
+        std::vector<int64_t> nc(nf), ff(nf), zz(nf, 0);
+        std::vector<char> merged_into_parent(nf, 0);
+        for (int s = 0; s < nf; s++) nc[s] = fund[s].ncols, ff[s] = fund[s].f;
+        auto stor = [](int64_t c, int64_t f) { return c * (2 * f - c); };
+        std::vector<int> kids;
+        for (int s = 0; s < nf; s++) { // children have smaller indices: already final
+            kids.assign(cidx.begin() + cptr[s], cidx.begin() + cptr[s + 1]);
+            // cheapest candidates first: small children with tall fronts add the fewest zeros
+            std::sort(kids.begin(), kids.end(), [&](int a, int b) {
+                int64_t da = nc[a] * (ff[s] - ff[a] + nc[a]), db = nc[b] * (ff[s] - ff[b] + nc[b]);
+                return da != db ? da < db : a < b;
+            });
+            for (int c : kids) {
+                const int64_t nm = nc[s] + nc[c], fm = ff[s] + nc[c];
+                const int64_t delta = stor(nm, fm) - stor(nc[s], ff[s]) - stor(nc[c], ff[c]);
+                const int64_t z = zz[s] + zz[c] + delta;
+                const double ratio = (double)z / (double)stor(nm, fm);
                 bool merge;
                 if (nm <= opt.relax_small) merge = true;
                 else if (nm <= 32) merge = ratio <= opt.relax_z1;
                 else if (nm <= W) merge = ratio <= opt.relax_z2;
                 else merge = ratio <= opt.relax_z3;
-                if (!merge) break;
-                Grp m{ch.first, (int)nm, fm, z};
-                out.pop_back();
-                out.back() = m;
+                if (!merge) continue;
+                merged_into_parent[c] = 1;
+                nc[s] = nm, ff[s] = fm, zz[s] = z;
             }
         }
-        grp.swap(out);
+        // new elimination order: for every group, first the (unmerged) child groups, then the group's columns
+        // (merged children's columns before their parent's columns)
+        std::vector<int> order;
+        order.reserve(n);
+        std::vector<int> roots;
+        for (int s = 0; s < nf; s++)
+            if (fpar[s] < 0) roots.push_back(s);
+        // iterative two-phase traversal: phase 0 = emit unmerged descendants' groups, phase 1 = emit own columns
+        struct Frame {
+            int s, phase;
+        };
+        std::vector<Frame> st;
+        std::vector<int> members; // supernodes of the current group in emission order
+        // collect(s): members of the group rooted at s = collect(merged children)... + s
+        auto collect = [&](int root, std::vector<int>& out) {
+            // post-order over merged-children edges only
+            std::vector<std::pair<int, int>> stack;
+            stack.push_back({root, cptr[root]});
+            while (!stack.empty()) {
+                auto& top = stack.back();
+                int sidx = top.first;
+                bool pushed = false;
+                while (top.second < cptr[sidx + 1]) {
+                    int c = cidx[top.second++];
+                    if (merged_into_parent[c]) {
+                        stack.push_back({c, cptr[c]});
+                        pushed = true;
+                        break;
+                    }
+                }
+                if (pushed) continue;
+                out.push_back(sidx);
+                stack.pop_back();
+            }
+        };
+        for (int r : roots) st.push_back({r, 0});
+        std::reverse(st.begin(), st.end());
+        std::vector<int> tmp;
+        while (!st.empty()) {
+            Frame fr = st.back();
+            st.pop_back();
+            if (fr.phase == 1) {
+                members.clear();
+                collect(fr.s, members);
+                Grp gnew{(int)order.size(), 0, ff[fr.s], zz[fr.s]};
+                for (int m : members)
+                    for (int j = fund[m].first; j < fund[m].first + fund[m].ncols; j++) order.push_back(j);
+                gnew.ncols = (int)order.size() - gnew.first;
+                grp.push_back(gnew);
+                continue;
+            }
+            // phase 0: schedule own emission after all unmerged child groups of every member
+            st.push_back({fr.s, 1});
+            members.clear();
+            collect(fr.s, members);
+            tmp.clear();
+            for (int m : members)
+                for (int e = cptr[m]; e < cptr[m + 1]; e++)
+                    if (!merged_into_parent[cidx[e]]) tmp.push_back(cidx[e]);
+            for (auto it = tmp.rbegin(); it != tmp.rend(); ++it) st.push_back({*it, 0});
+        }
+        // relabel everything to the new order
+        bool identity = true;
+        for (int k = 0; k < n; k++)
+            if (order[k] != k) identity = false;
+        if (!identity) {
+            std::vector<int> q2(n);
+            for (int k = 0; k < n; k++) q2[k] = q[order[k]];
+            q.swap(q2);
+            Graph g2;
+            relabel_graph(g, order, g2);
+            g.ptr.swap(g2.ptr);
+            g.adj.swap(g2.adj);
+            etree_symmetric(g, parent);
+            for (int k = 0; k < n; k++) invq[q[k]] = k;
+            P.colperm = q;
+            for (int k = 0; k < n; k++) P.rowperm[k] = rowmatch[q[k]];
+        }
     }
     const int ns = (int)grp.size();
     P.nsuper_relaxed = ns;
