@@ -178,7 +178,7 @@ def main():
     import torch.distributed as dist
 
     import russell_b200 as rb
-    from russell_b200 import _lib
+    from russell_b200 import _lib, batch
     from russell_b200._lib import p_f64, p_i32, ptr
 
     if not torch.cuda.is_available():
@@ -214,7 +214,6 @@ def main():
     d_vals = h_vals.cuda()
     d_rhs = h_rhs.cuda()
     d_x = torch.zeros(n, dtype=torch.float64, device="cuda")
-    gather = [torch.zeros(n, dtype=torch.float64, device="cuda") for _ in range(world)] if world > 1 else None
     em, ep = ctypes.c_int32(0), ctypes.c_int32(0)
 
     def step_device():
@@ -223,7 +222,7 @@ def main():
         rc = lib.solver_b200_solve_device(h, d_x.data_ptr(), d_rhs.data_ptr())
         assert rc == 0, rc
         if world > 1:
-            dist.all_gather(gather, d_x)
+            batch.gather_solutions(d_x[None, :], world, world, rank)  # system r lives on rank r
 
     def step_e2e():
         rc = lib.solver_b200_factorize(h, ctypes.byref(em), ctypes.byref(ep), 0, ctypes.cast(h_vals.data_ptr(), p_f64))
@@ -231,7 +230,7 @@ def main():
         rc = lib.solver_b200_solve(h, ctypes.cast(h_x.data_ptr(), p_f64), ctypes.cast(h_rhs.data_ptr(), p_f64), 0)
         assert rc == 0, rc
         if world > 1:
-            dist.all_gather(gather, d_x.copy_(h_x, non_blocking=True))
+            batch.gather_solutions(d_x.copy_(h_x, non_blocking=True)[None, :], world, world, rank)
 
     def get_stats():
         out = np.zeros(len(rb.SolverB200.STAT_NAMES))

@@ -115,7 +115,8 @@ int32_t solver_b200_determinant(struct InterfaceB200 *solver, double *coefficien
 #define B200_STAT_SPMV_BYTES 20            /* algorithmic bytes of one SpMV */
 #define B200_STAT_MATCHED 21
 #define B200_STAT_T_MATCH_S 22
-#define B200_STAT_COUNT 23
+#define B200_STAT_LAST_BACKWARD_ERROR 23 /* max_i |r_i| / (|A||x|+|b|)_i of the last solve */
+#define B200_STAT_COUNT 24
 int32_t solver_b200_get_stats(struct InterfaceB200 *solver, double *out, int32_t n_out);
 
 /* tuning knobs, must be called before initialize: key in {"panel_width","nd_leaf","use_graph","ir_tol",

@@ -361,7 +361,7 @@ class SolverB200:
     STAT_NAMES = ["nnodes", "nlevels", "nnz_l", "nnz_u", "flops", "fac_bytes", "cb_bytes", "max_front", "t_order_s",
                   "t_symbolic_s", "n_perturbed", "last_rel_residual", "last_refine_steps", "ms_factorize_device",
                   "ms_solve_device", "ms_sptrsv_device", "ms_spmv_device", "launches_factorize", "launches_solve",
-                  "sptrsv_bytes", "spmv_bytes", "matched", "t_match_s"]
+                  "sptrsv_bytes", "spmv_bytes", "matched", "t_match_s", "last_backward_error"]
 
     def __init__(self):
         self._lib = _lib.load()

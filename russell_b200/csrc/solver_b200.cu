@@ -36,12 +36,12 @@ using namespace b200;
     } while (0)
 
 // front-size classes of the fused kernel: upper bound on f and CTA size; class NFC = "big" (multi-kernel path)
-static const int NFC = 4;
-static const int FC_MAXF[NFC] = {16, 32, 64, B200_FUSED_MAXF};
-static const int FC_THREADS[NFC] = {32, 64, 128, 256};
+static const int NFC = 6;
+static const int FC_MAXF[NFC] = {16, 32, 48, 64, 96, B200_FUSED_MAXF};
+static const int FC_THREADS[NFC] = {32, 64, 64, 128, 256, 256};
 // solve classes: CTA size by front order
 static const int NSC = 3;
-static const int SC_MAXF[NSC] = {48, 256, 1 << 30};
+static const int SC_MAXF[NSC] = {32, 256, 1 << 30};
 static const int SC_THREADS[NSC] = {32, 128, 256};
 
 struct LevelLists {
@@ -51,6 +51,7 @@ struct LevelLists {
     std::vector<int> fact_ptr;
     // solve_ptr[l*NSC+c .. +1] inside d_solve_nodes
     std::vector<int> solve_ptr;
+    std::vector<int> big_ptr; // nlevels+1: slices of the big solve class inside d_big_items
     std::vector<size_t> fused_smem; // per (level, class): dynamic shared memory of the fused launch
 };
 
@@ -82,6 +83,11 @@ struct InterfaceB200 {
     AsmItem* d_asm = nullptr;
     PanelItem* d_panel = nullptr;
     SchurItem* d_schur = nullptr;
+    SolveItem* d_big_items = nullptr;
+    int* d_big_slot = nullptr;
+    int *d_asm_ranges = nullptr, *d_big_ranges = nullptr;
+    double* d_big_scratch = nullptr;
+    int* d_big_tickets = nullptr;
     int* d_a_src = nullptr;
     long long* d_a_dst = nullptr;
     double* d_a_scl = nullptr;
@@ -97,7 +103,7 @@ struct InterfaceB200 {
     int* d_counters = nullptr; // 4 ints
     unsigned long long* d_amax = nullptr;
     // device: vectors
-    double *d_b = nullptr, *d_x = nullptr, *d_r = nullptr, *d_y = nullptr, *d_xp = nullptr, *d_wv = nullptr;
+    double *d_b = nullptr, *d_x = nullptr, *d_r = nullptr, *d_y = nullptr, *d_z = nullptr, *d_xp = nullptr, *d_wv = nullptr;
     double *d_partial = nullptr, *d_norms = nullptr;
     double* h_norms = nullptr; // pinned, 2 doubles + counters
     int* h_counters = nullptr; // pinned
@@ -107,7 +113,7 @@ struct InterfaceB200 {
 
     // stats
     int n_perturbed = 0;
-    double last_rel_residual = -1.0;
+    double last_rel_residual = -1.0, last_backward_error = -1.0;
     int last_refine_steps = 0;
     float ms_factorize = 0, ms_solve = 0, ms_sptrsv = 0, ms_spmv = 0;
     int launches_factorize = 0, launches_solve = 0, sweep_launches = 0;
@@ -137,13 +143,14 @@ void release_device(InterfaceB200* s) {
     if (s->g_sweep) cudaGraphExecDestroy(s->g_sweep), s->g_sweep = nullptr;
     dfree(s->d_nodes), dfree(s->d_rows), dfree(s->d_rel), dfree(s->d_child_idx), dfree(s->d_fact_nodes), dfree(s->d_solve_nodes);
     dfree(s->d_asm), dfree(s->d_panel), dfree(s->d_schur);
+    dfree(s->d_big_items), dfree(s->d_big_slot), dfree(s->d_asm_ranges), dfree(s->d_big_ranges), dfree(s->d_big_scratch), dfree(s->d_big_tickets);
     dfree(s->d_a_src), dfree(s->d_a_dst), dfree(s->d_a_scl);
     dfree(s->d_rowperm), dfree(s->d_colperm), dfree(s->d_rscale), dfree(s->d_cscale);
     dfree(s->d_full_ptr), dfree(s->d_full_col), dfree(s->d_full_src), dfree(s->d_rowblk);
     dfree(s->d_vals), dfree(s->d_fullvals);
     dfree(s->d_fac), dfree(s->d_cb), dfree(s->d_dinv), dfree(s->d_upiv), dfree(s->d_lperm);
     dfree(s->d_counters), dfree(s->d_amax);
-    dfree(s->d_b), dfree(s->d_x), dfree(s->d_r), dfree(s->d_y), dfree(s->d_xp), dfree(s->d_wv);
+    dfree(s->d_b), dfree(s->d_x), dfree(s->d_r), dfree(s->d_y), dfree(s->d_z), dfree(s->d_xp), dfree(s->d_wv);
     dfree(s->d_partial), dfree(s->d_norms);
     if (s->h_norms) cudaFreeHost(s->h_norms), s->h_norms = nullptr;
     if (s->h_counters) cudaFreeHost(s->h_counters), s->h_counters = nullptr;
@@ -160,7 +167,8 @@ int grid_for(long long work, int block = 256, int cap = 148 * 16) {
 size_t smem_fused(int f, int p) { return ((size_t)(f | 1) * f + (size_t)p * p) * sizeof(double) + (size_t)p * sizeof(int); }
 
 void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::vector<PanelItem>& panel_items,
-                      std::vector<SchurItem>& schur_items, std::vector<int>& fact_nodes, std::vector<int>& solve_nodes) {
+                      std::vector<SchurItem>& schur_items, std::vector<int>& fact_nodes, std::vector<int>& solve_nodes,
+                      std::vector<int>& asm_ranges) {
     const Plan& P = s->plan;
     LevelLists& lv = s->lv;
     lv.asm_ptr.assign(P.nlevels + 1, 0);
@@ -215,7 +223,16 @@ void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::ve
                 int ntiles = (int)std::ceil(total / 8192.0);
                 ntiles = std::max(1, std::min(ntiles, std::max(1, f / 2)));
                 int tw = (f + ntiles - 1) / ntiles;
-                for (int t0 = 0; t0 < f; t0 += tw) asm_items.push_back({v, t0, std::min(f, t0 + tw), 0});
+                for (int t0 = 0; t0 < f; t0 += tw) {
+                    const int t1 = std::min(f, t0 + tw);
+                    asm_items.push_back({v, t0, t1, (int)asm_ranges.size()});
+                    for (int c = P.child_ptr[v]; c < P.child_ptr[v + 1]; c++) { // child columns landing in [t0, t1)
+                        const int ch = P.child_idx[c];
+                        const int* rel = &P.rel[P.rows_ptr[ch]];
+                        asm_ranges.push_back((int)(std::lower_bound(rel, rel + P.u[ch], t0) - rel));
+                        asm_ranges.push_back((int)(std::lower_bound(rel, rel + P.u[ch], t1) - rel));
+                    }
+                }
             }
             if (u > 0) {
                 for (int r0 = 0; r0 < u; r0 += B200_TR) panel_items.push_back({v, r0, std::min(B200_TR, u - r0), 0});
@@ -231,7 +248,7 @@ void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::ve
     }
 }
 
-size_t smem_diag(int W) { return (size_t)2 * W * W * sizeof(double) + W * sizeof(int); }
+size_t smem_diag(int) { return (size_t)(B200_MAXP * (B200_MAXP + 1) + B200_MAXP * B200_MAXP) * sizeof(double) + B200_MAXP * sizeof(int); }
 size_t smem_panel(int W) { return (size_t)(W * W + B200_TR * W) * sizeof(double) + W * sizeof(int); }
 size_t smem_schur_fma(int W) { return (size_t)2 * W * B200_TS * sizeof(double); }
 size_t smem_schur_dmma() { return (size_t)2 * B200_MAXP * (B200_TS + 1) * sizeof(double); }
@@ -258,7 +275,7 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
         if (nbig == 0) continue;
         int na = lv.asm_ptr[l + 1] - lv.asm_ptr[l];
         if (na > 0) {
-            k_assemble<<<na, 256, 0, s->stream>>>(s->d_asm + lv.asm_ptr[l], s->d_nodes, s->d_child_idx, s->d_rel, s->d_fac, s->d_cb);
+            k_assemble<<<na, 256, 0, s->stream>>>(s->d_asm + lv.asm_ptr[l], s->d_nodes, s->d_child_idx, s->d_rel, s->d_asm_ranges, s->d_fac, s->d_cb);
             cnt++;
         }
         k_diag<<<nbig, 256, smem_diag(W), s->stream>>>(s->d_fact_nodes + fp[NFC], s->d_nodes, s->d_fac, s->d_dinv,
@@ -287,22 +304,34 @@ int enqueue_sweep_levels(InterfaceB200* s, int* launches) {
     const LevelLists& lv = s->lv;
     int cnt = 0;
     for (int l = 0; l < P.nlevels; l++) {
-        for (int c = 0; c < NSC; c++) {
+        for (int c = 0; c < NSC - 1; c++) {
             int a = lv.solve_ptr[(size_t)l * NSC + c], b = lv.solve_ptr[(size_t)l * NSC + c + 1];
             if (b > a) {
                 k_fwd<<<b - a, SC_THREADS[c], 0, s->stream>>>(s->d_solve_nodes + a, s->d_nodes, s->d_child_idx, s->d_rel, s->d_fac,
-                                                             s->d_dinv, s->d_lperm, s->d_y, s->d_wv);
+                                                             s->d_dinv, s->d_lperm, s->d_y, s->d_z, s->d_wv);
                 cnt++;
             }
         }
+        int nb = lv.big_ptr[l + 1] - lv.big_ptr[l];
+        if (nb > 0) {
+            k_fwd_big<<<nb, 256, 0, s->stream>>>(s->d_big_items + lv.big_ptr[l], s->d_nodes, s->d_child_idx, s->d_rel, s->d_fac, s->d_dinv,
+                                                  s->d_lperm, s->d_big_ranges, s->d_y, s->d_z, s->d_wv);
+            cnt++;
+        }
     }
     for (int l = P.nlevels - 1; l >= 0; l--) {
-        for (int c = 0; c < NSC; c++) {
+        for (int c = 0; c < NSC - 1; c++) {
             int a = lv.solve_ptr[(size_t)l * NSC + c], b = lv.solve_ptr[(size_t)l * NSC + c + 1];
             if (b > a) {
-                k_bwd<<<b - a, SC_THREADS[c], 0, s->stream>>>(s->d_solve_nodes + a, s->d_nodes, s->d_rows, s->d_fac, s->d_dinv, s->d_y, s->d_xp);
+                k_bwd<<<b - a, SC_THREADS[c], 0, s->stream>>>(s->d_solve_nodes + a, s->d_nodes, s->d_rows, s->d_fac, s->d_dinv, s->d_z, s->d_xp);
                 cnt++;
             }
+        }
+        int nb = lv.big_ptr[l + 1] - lv.big_ptr[l];
+        if (nb > 0) {
+            k_bwd_big<<<nb, 256, 0, s->stream>>>(s->d_big_items + lv.big_ptr[l], s->d_nodes, s->d_rows, s->d_fac, s->d_dinv, s->d_z, s->d_xp,
+                                                  s->d_big_scratch, s->d_big_tickets, s->d_big_slot + lv.big_ptr[l]);
+            cnt++;
         }
     }
     if (launches) *launches = cnt;
@@ -360,7 +389,7 @@ int residual(InterfaceB200* s, const double* d_xv, const double* d_rhs, double* 
     if (time_it) cudaEventRecord(s->ev[7], s->stream);
     k_reduce_partials<<<1, 256, 0, s->stream>>>(s->n_rowblk, s->d_partial, s->d_norms);
     s->launches_solve += 2;
-    if (cudaMemcpyAsync(s->h_norms, s->d_norms, 2 * sizeof(double), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess) return 1;
+    if (cudaMemcpyAsync(s->h_norms, s->d_norms, 3 * sizeof(double), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess) return 1;
     if (cudaStreamSynchronize(s->stream) != cudaSuccess) return 1;
     return 0;
 }
@@ -500,8 +529,37 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     std::vector<AsmItem> asm_items;
     std::vector<PanelItem> panel_items;
     std::vector<SchurItem> schur_items;
-    std::vector<int> fact_nodes, solve_nodes;
-    build_work_lists(s, asm_items, panel_items, schur_items, fact_nodes, solve_nodes);
+    std::vector<int> fact_nodes, solve_nodes, asm_ranges, big_ranges;
+    build_work_lists(s, asm_items, panel_items, schur_items, fact_nodes, solve_nodes, asm_ranges);
+    // big solve class: row slices of the update set; a node with no update rows still needs one (head-only) item
+    std::vector<SolveItem> big_items;
+    std::vector<int> big_slot;
+    int nslots = 0;
+    s->lv.big_ptr.assign(P.nlevels + 1, 0);
+    for (int l = 0; l < P.nlevels; l++) {
+        int a = s->lv.solve_ptr[(size_t)l * NSC + NSC - 1], b = s->lv.solve_ptr[(size_t)l * NSC + NSC];
+        for (int e = a; e < b; e++) {
+            const int v = solve_nodes[e];
+            const int u = P.u[v];
+            const int nsl = std::max(1, (u + B200_SLICE - 1) / B200_SLICE);
+            for (int sl = 0; sl < nsl; sl++) {
+                int r0 = sl * B200_SLICE;
+                const int nrows = std::max(0, std::min(B200_SLICE, u - r0));
+                big_items.push_back({v, r0, nrows, sl, (int)big_ranges.size(), 0});
+                big_slot.push_back(nslots);
+                for (int c = P.child_ptr[v]; c < P.child_ptr[v + 1]; c++) {
+                    const int ch = P.child_idx[c];
+                    const int* rel = &P.rel[P.rows_ptr[ch]];
+                    const int pv = P.p[v];
+                    big_ranges.push_back((int)(std::lower_bound(rel, rel + P.u[ch], pv) - rel));
+                    big_ranges.push_back((int)(std::lower_bound(rel, rel + P.u[ch], pv + r0) - rel));
+                    big_ranges.push_back((int)(std::lower_bound(rel, rel + P.u[ch], pv + r0 + nrows) - rel));
+                }
+            }
+            nslots += nsl;
+        }
+        s->lv.big_ptr[l + 1] = (int)big_items.size();
+    }
 
     // SpMV row blocks (rows never split; at most B200_SPMV_NNZ nonzeros and 1024 rows per block)
     std::vector<int> rowblk;
@@ -528,6 +586,10 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     UP(d_asm, asm_items);
     UP(d_panel, panel_items);
     UP(d_schur, schur_items);
+    UP(d_big_items, big_items);
+    UP(d_big_slot, big_slot);
+    UP(d_asm_ranges, asm_ranges);
+    UP(d_big_ranges, big_ranges);
     UP(d_a_src, P.a_src);
     {
         std::vector<long long> dst(P.a_dst.begin(), P.a_dst.end());
@@ -559,12 +621,16 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     DM(d_x, P.n, double);
     DM(d_r, P.n, double);
     DM(d_y, P.n, double);
+    DM(d_z, P.n, double);
     DM(d_xp, P.n, double);
     DM(d_wv, P.rows_ptr[P.nnodes] + 1, double);
-    DM(d_partial, 2 * (size_t)s->n_rowblk, double);
-    DM(d_norms, 2, double);
+    DM(d_partial, 3 * (size_t)s->n_rowblk, double);
+    DM(d_big_scratch, (size_t)std::max(nslots, 1) * B200_MAXP, double);
+    DM(d_big_tickets, std::max(nslots, 1), int);
+    CUDA_TRY(cudaMemset(s->d_big_tickets, 0, (size_t)std::max(nslots, 1) * sizeof(int)), B200_ERROR_CUDA_MALLOC);
+    DM(d_norms, 4, double);
 #undef DM
-    CUDA_TRY(cudaMallocHost((void**)&s->h_norms, 2 * sizeof(double)), B200_ERROR_MALLOC);
+    CUDA_TRY(cudaMallocHost((void**)&s->h_norms, 4 * sizeof(double)), B200_ERROR_MALLOC);
     CUDA_TRY(cudaMallocHost((void**)&s->h_counters, 4 * sizeof(int) + sizeof(unsigned long long)), B200_ERROR_MALLOC);
 
     // kernels that need more than 48 KB of dynamic shared memory
@@ -672,20 +738,25 @@ int32_t solver_b200_solve_device(struct InterfaceB200* s, double* d_xout, const 
     s->launches_solve = 0;
     cudaEventRecord(s->ev[2], s->stream);
     int rc = sweep(s, d_rhs, d_xout, 0, true);
-    double prev = -1.0;
+    double prev = -1.0, prev_omega = -1.0;
     int steps = 0;
     for (int it = 0; rc == 0; it++) {
         if (residual(s, d_xout, d_rhs, s->d_r, it == 0) != 0) {
             rc = 1;
             break;
         }
-        double rr = s->h_norms[0], bb = s->h_norms[1];
-        double rel = bb > 0.0 ? std::sqrt(rr / bb) : std::sqrt(rr);
+        const double rr = s->h_norms[0], bb = s->h_norms[1], omega = s->h_norms[2];
+        const double rel = bb > 0.0 ? std::sqrt(rr / bb) : std::sqrt(rr);
         s->last_rel_residual = rel;
-        if (!(rel == rel)) break;                       // NaN: nothing to refine
-        if (rel <= s->ir_tol || it >= s->nrefine) break; // converged or out of steps
-        if (prev >= 0.0 && rel > 0.5 * prev) break;      // stagnation
+        s->last_backward_error = omega;
+        if (!(rel == rel)) break;                        // NaN: nothing to refine
+        if (it >= s->nrefine) break;                     // out of steps
+        if (rel <= s->ir_tol) break;                     // requested residual reached
+        if (omega <= 4.0 * 2.220446049250313e-16) break; // componentwise backward error at machine precision:
+                                                         // the residual itself is rounding noise from here on
+        if (prev >= 0.0 && rel > 0.5 * prev && omega > 0.5 * prev_omega) break; // stagnation
         prev = rel;
+        prev_omega = omega;
         rc = sweep(s, s->d_r, d_xout, 1, false);
         steps++;
     }
@@ -829,6 +900,7 @@ int32_t solver_b200_get_stats(struct InterfaceB200* s, double* out, int32_t n_ou
     v[B200_STAT_SPMV_BYTES] = s->spmv_bytes;
     v[B200_STAT_MATCHED] = P.matched ? 1.0 : 0.0;
     v[B200_STAT_T_MATCH_S] = P.t_match;
+    v[B200_STAT_LAST_BACKWARD_ERROR] = s->last_backward_error;
     for (int i = 0; i < n_out && i < B200_STAT_COUNT; i++) out[i] = v[i];
     return B200_SUCCESSFUL_EXIT;
 }
