@@ -22,6 +22,7 @@
 
 #include "../../include/solver_b200.h"
 #include "kernels.cuh"
+#include "sweep_top.cuh"
 #include "plan.hpp"
 
 using namespace b200;
@@ -39,10 +40,15 @@ using namespace b200;
 static const int NFC = 6;
 static const int FC_MAXF[NFC] = {16, 32, 48, 64, 96, B200_FUSED_MAXF};
 static const int FC_THREADS[NFC] = {32, 64, 64, 128, 256, 256};
+// pivot-count classes of the batched inverse post-pass
+static const int NIC = 3;
+static const int IC_MAXP[NIC] = {16, 32, B200_MAXP};
+static const int IC_THREADS[NIC] = {32, 64, 256};
 // solve classes: CTA size by front order
 static const int NSC = 3;
 static const int SC_MAXF[NSC] = {32, 256, 1 << 30};
 static const int SC_THREADS[NSC] = {32, 128, 256};
+static const int SC_MAXP[NSC] = {32, B200_MAXP, B200_MAXP};
 
 struct LevelLists {
     // offsets (nlevels+1) into the concatenated device item arrays (big fronts only)
@@ -52,6 +58,7 @@ struct LevelLists {
     // solve_ptr[l*NSC+c .. +1] inside d_solve_nodes
     std::vector<int> solve_ptr;
     std::vector<int> big_ptr; // nlevels+1: slices of the big solve class inside d_big_items
+    std::vector<int> inv_ptr; // NIC+1: fronts by pivot-count class inside d_inv_nodes
     std::vector<size_t> fused_smem; // per (level, class): dynamic shared memory of the fused launch
 };
 
@@ -79,12 +86,18 @@ struct InterfaceB200 {
 
     // device: plan
     NodeDev* d_nodes = nullptr;
-    int *d_rows = nullptr, *d_rel = nullptr, *d_child_idx = nullptr, *d_fact_nodes = nullptr, *d_solve_nodes = nullptr;
+    int *d_rows = nullptr, *d_rel = nullptr, *d_child_idx = nullptr, *d_fact_nodes = nullptr, *d_solve_nodes = nullptr, *d_inv_nodes = nullptr;
     AsmItem* d_asm = nullptr;
     PanelItem* d_panel = nullptr;
     SchurItem* d_schur = nullptr;
     SolveItem* d_big_items = nullptr;
     int* d_big_slot = nullptr;
+    // persistent top-of-tree sweep (sweep_top.cuh)
+    int use_top = 1, ltop = 0, n_top_items = 0, top_grid = 0, n_slots = 0;
+    bool sweep_dirty = false;          // a persistent sweep aborted: counters must be re-armed
+    std::vector<int> cdone_init;       // host copy of the initial completion counters
+    SolveItem* d_top_items = nullptr;
+    int *d_top_ranges = nullptr, *d_top_slot = nullptr, *d_cdone = nullptr, *d_xdone = nullptr, *d_epoch = nullptr, *d_abort = nullptr;
     int *d_asm_ranges = nullptr, *d_big_ranges = nullptr;
     double* d_big_scratch = nullptr;
     int* d_big_tickets = nullptr;
@@ -141,9 +154,10 @@ void dfree(T*& p) {
 void release_device(InterfaceB200* s) {
     if (s->g_fact) cudaGraphExecDestroy(s->g_fact), s->g_fact = nullptr;
     if (s->g_sweep) cudaGraphExecDestroy(s->g_sweep), s->g_sweep = nullptr;
-    dfree(s->d_nodes), dfree(s->d_rows), dfree(s->d_rel), dfree(s->d_child_idx), dfree(s->d_fact_nodes), dfree(s->d_solve_nodes);
+    dfree(s->d_nodes), dfree(s->d_rows), dfree(s->d_rel), dfree(s->d_child_idx), dfree(s->d_fact_nodes), dfree(s->d_solve_nodes), dfree(s->d_inv_nodes);
     dfree(s->d_asm), dfree(s->d_panel), dfree(s->d_schur);
-    dfree(s->d_big_items), dfree(s->d_big_slot), dfree(s->d_asm_ranges), dfree(s->d_big_ranges), dfree(s->d_big_scratch), dfree(s->d_big_tickets);
+    dfree(s->d_big_items), dfree(s->d_big_slot), dfree(s->d_top_items), dfree(s->d_top_ranges), dfree(s->d_top_slot),
+    dfree(s->d_cdone), dfree(s->d_xdone), dfree(s->d_epoch), dfree(s->d_abort), dfree(s->d_asm_ranges), dfree(s->d_big_ranges), dfree(s->d_big_scratch), dfree(s->d_big_tickets);
     dfree(s->d_a_src), dfree(s->d_a_dst), dfree(s->d_a_scl);
     dfree(s->d_rowperm), dfree(s->d_colperm), dfree(s->d_rscale), dfree(s->d_cscale);
     dfree(s->d_full_ptr), dfree(s->d_full_col), dfree(s->d_full_src), dfree(s->d_rowblk);
@@ -164,7 +178,7 @@ int grid_for(long long work, int block = 256, int cap = 148 * 16) {
 }
 
 // ---- work-item lists --------------------------------------------------------------------------------
-size_t smem_fused(int f, int p) { return ((size_t)(f | 1) * f + (size_t)p * p) * sizeof(double) + (size_t)p * sizeof(int); }
+size_t smem_fused(int f, int p) { return ((size_t)(f | 1) * f) * sizeof(double) + (size_t)p * sizeof(int); }
 
 void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::vector<PanelItem>& panel_items,
                       std::vector<SchurItem>& schur_items, std::vector<int>& fact_nodes, std::vector<int>& solve_nodes,
@@ -220,8 +234,8 @@ void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::ve
                     double uc = P.u[P.child_idx[c]];
                     total += uc * uc;
                 }
-                int ntiles = (int)std::ceil(total / 8192.0);
-                ntiles = std::max(1, std::min(ntiles, std::max(1, f / 2)));
+                int ntiles = (int)std::ceil(total / 4096.0);
+                ntiles = std::max(1, std::min(ntiles, f));
                 int tw = (f + ntiles - 1) / ntiles;
                 for (int t0 = 0; t0 < f; t0 += tw) {
                     const int t1 = std::min(f, t0 + tw);
@@ -248,7 +262,8 @@ void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::ve
     }
 }
 
-size_t smem_diag(int) { return (size_t)(B200_MAXP * (B200_MAXP + 1) + B200_MAXP * B200_MAXP) * sizeof(double) + B200_MAXP * sizeof(int); }
+size_t smem_diag(int) { return (size_t)(B200_MAXP * (B200_MAXP + 1)) * sizeof(double) + B200_MAXP * sizeof(int); }
+size_t smem_invert(int pmax) { return (size_t)(pmax * (pmax | 1) + pmax * pmax) * sizeof(double); }
 size_t smem_panel(int W) { return (size_t)(W * W + B200_TR * W) * sizeof(double) + W * sizeof(int); }
 size_t smem_schur_fma(int W) { return (size_t)2 * W * B200_TS * sizeof(double); }
 size_t smem_schur_dmma() { return (size_t)2 * B200_MAXP * (B200_TS + 1) * sizeof(double); }
@@ -266,7 +281,7 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
             int nn = fp[c + 1] - fp[c];
             if (nn > 0) {
                 k_front_fused<<<nn, FC_THREADS[c], lv.fused_smem[(size_t)l * NFC + c], s->stream>>>(
-                    s->d_fact_nodes + fp[c], s->d_nodes, s->d_child_idx, s->d_rel, s->d_fac, s->d_cb, s->d_dinv, s->d_lperm,
+                    s->d_fact_nodes + fp[c], s->d_nodes, s->d_child_idx, s->d_rel, s->d_fac, s->d_cb, s->d_lperm,
                     s->d_upiv, s->d_amax, s->pivot_eps, s->d_counters);
                 cnt++;
             }
@@ -278,12 +293,12 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
             k_assemble<<<na, 256, 0, s->stream>>>(s->d_asm + lv.asm_ptr[l], s->d_nodes, s->d_child_idx, s->d_rel, s->d_asm_ranges, s->d_fac, s->d_cb);
             cnt++;
         }
-        k_diag<<<nbig, 256, smem_diag(W), s->stream>>>(s->d_fact_nodes + fp[NFC], s->d_nodes, s->d_fac, s->d_dinv,
+        k_diag<<<nbig, 512, smem_diag(W), s->stream>>>(s->d_fact_nodes + fp[NFC], s->d_nodes, s->d_fac,
                                                          s->d_lperm, s->d_upiv, s->d_amax, s->pivot_eps, s->d_counters);
         cnt++;
         int np = lv.panel_ptr[l + 1] - lv.panel_ptr[l];
         if (np > 0) {
-            k_panel<<<np, 256, smem_panel(W), s->stream>>>(s->d_panel + lv.panel_ptr[l], s->d_nodes, s->d_fac, s->d_dinv, s->d_lperm);
+            k_panel<<<np, 256, smem_panel(W), s->stream>>>(s->d_panel + lv.panel_ptr[l], s->d_nodes, s->d_fac, s->d_lperm);
             cnt++;
         }
         int nsch = lv.schur_ptr[l + 1] - lv.schur_ptr[l];
@@ -295,19 +310,41 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
             cnt++;
         }
     }
+    // pivot-block inverses of ALL fronts (solve phase only needs them): one batched launch per pivot-count class
+    for (int c = 0; c < NIC; c++) {
+        int nn = lv.inv_ptr[c + 1] - lv.inv_ptr[c];
+        if (nn > 0) {
+            k_invert<<<nn, IC_THREADS[c], smem_invert(IC_MAXP[c]), s->stream>>>(s->d_inv_nodes + lv.inv_ptr[c], s->d_nodes, s->d_fac,
+                                                                                 s->d_dinv, IC_MAXP[c]);
+            cnt++;
+        }
+    }
     if (launches) *launches = cnt;
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+__global__ void k_bump_epoch(int* epoch) { *epoch += 1; }
+void k_fwd_top_launch(InterfaceB200* s) {
+    k_fwd_top<<<s->top_grid, 256, B200_TOP_SMEM, s->stream>>>(s->d_top_items, s->n_top_items, s->d_nodes, s->d_child_idx, s->d_rel, s->d_fac,
+                                                            s->d_dinv, s->d_lperm, s->d_top_ranges, s->d_y, s->d_z, s->d_wv, s->d_cdone,
+                                                            s->d_epoch, s->d_abort);
+}
+void k_bwd_top_launch(InterfaceB200* s) {
+    k_bwd_top<<<s->top_grid, 256, B200_TOP_SMEM, s->stream>>>(s->d_top_items, s->n_top_items, s->d_nodes, s->d_rows, s->d_fac, s->d_dinv,
+                                                            s->d_z, s->d_xp, s->d_big_scratch, s->d_big_tickets, s->d_top_slot, s->d_xdone,
+                                                            s->d_epoch, s->d_abort);
 }
 
 int enqueue_sweep_levels(InterfaceB200* s, int* launches) {
     const Plan& P = s->plan;
     const LevelLists& lv = s->lv;
     int cnt = 0;
-    for (int l = 0; l < P.nlevels; l++) {
+    const int lsplit = s->n_top_items > 0 ? s->ltop : P.nlevels; // levels >= lsplit run in the persistent kernels
+    for (int l = 0; l < lsplit; l++) {
         for (int c = 0; c < NSC - 1; c++) {
             int a = lv.solve_ptr[(size_t)l * NSC + c], b = lv.solve_ptr[(size_t)l * NSC + c + 1];
             if (b > a) {
-                k_fwd<<<b - a, SC_THREADS[c], 0, s->stream>>>(s->d_solve_nodes + a, s->d_nodes, s->d_child_idx, s->d_rel, s->d_fac,
+                k_fwd<<<b - a, SC_THREADS[c], (size_t)SC_MAXP[c] * SC_MAXP[c] * sizeof(double), s->stream>>>(s->d_solve_nodes + a, s->d_nodes, s->d_child_idx, s->d_rel, s->d_fac,
                                                              s->d_dinv, s->d_lperm, s->d_y, s->d_z, s->d_wv);
                 cnt++;
             }
@@ -319,11 +356,17 @@ int enqueue_sweep_levels(InterfaceB200* s, int* launches) {
             cnt++;
         }
     }
-    for (int l = P.nlevels - 1; l >= 0; l--) {
+    if (s->n_top_items > 0) {
+        k_bump_epoch<<<1, 1, 0, s->stream>>>(s->d_epoch);
+        k_fwd_top_launch(s);
+        k_bwd_top_launch(s);
+        cnt += 3;
+    }
+    for (int l = lsplit - 1; l >= 0; l--) {
         for (int c = 0; c < NSC - 1; c++) {
             int a = lv.solve_ptr[(size_t)l * NSC + c], b = lv.solve_ptr[(size_t)l * NSC + c + 1];
             if (b > a) {
-                k_bwd<<<b - a, SC_THREADS[c], 0, s->stream>>>(s->d_solve_nodes + a, s->d_nodes, s->d_rows, s->d_fac, s->d_dinv, s->d_z, s->d_xp);
+                k_bwd<<<b - a, SC_THREADS[c], (size_t)SC_MAXP[c] * SC_MAXP[c] * sizeof(double), s->stream>>>(s->d_solve_nodes + a, s->d_nodes, s->d_rows, s->d_fac, s->d_dinv, s->d_z, s->d_xp);
                 cnt++;
             }
         }
@@ -431,6 +474,7 @@ struct InterfaceB200* solver_b200_new(void) {
     if ((e = getenv("B200_NO_GRAPH")) && atoi(e)) s->use_graph = 0;
     if ((e = getenv("B200_SCHUR_VARIANT"))) s->schur_variant = atoi(e);
     if ((e = getenv("B200_USE_FUSED"))) s->use_fused = atoi(e);
+    if ((e = getenv("B200_USE_TOP"))) s->use_top = atoi(e);
     if ((e = getenv("B200_PANEL_WIDTH"))) s->opt_panel_width = atoi(e);
     if ((e = getenv("B200_ND_LEAF"))) s->opt_nd_leaf = atoi(e);
     return s;
@@ -458,6 +502,7 @@ int32_t solver_b200_set_option(struct InterfaceB200* s, const char* key, double 
     else if (k == "use_graph") s->use_graph = value != 0.0;
     else if (k == "schur_variant") s->schur_variant = (int)value;
     else if (k == "use_fused") s->use_fused = value != 0.0;
+    else if (k == "use_top") s->use_top = value != 0.0;
     else if (k == "force_no_matching") s->force_no_matching = value != 0.0;
     else if (k == "device") {
         // re-home the handle: the stream and the timing events belong to a device
@@ -524,7 +569,7 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
         d.nchild = P.child_ptr[v + 1] - P.child_ptr[v];
         d.child_ptr = P.child_ptr[v];
         d.Loff = P.Loff[v], d.Uoff = P.Uoff[v], d.Coff = P.Coff[v], d.Doff = P.Doff[v], d.rows_ptr = P.rows_ptr[v];
-        d.pad = 0;
+        d.pad = P.parent[v]; // parent front (used by the persistent backward sweep)
     }
     std::vector<AsmItem> asm_items;
     std::vector<PanelItem> panel_items;
@@ -576,6 +621,38 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     }
     s->n_rowblk = (int)rowblk.size() - 1;
 
+    // persistent top-of-tree sweep: all levels above the last "wide" level (more than 96 fronts)
+    std::vector<SolveItem> top_items;
+    std::vector<int> top_ranges, top_slot, cdone_init(P.nnodes, 1 << 30);
+    s->ltop = P.nlevels;
+    if (s->use_top) {
+        int l = P.nlevels;
+        while (l > 0 && P.level_ptr[l] - P.level_ptr[l - 1] <= 96) l--;
+        if (P.nlevels - l >= 4) s->ltop = l; // worth it only when a real chain of levels is replaced
+    }
+    for (int l = s->ltop; l < P.nlevels; l++)
+        for (int e = P.level_ptr[l]; e < P.level_ptr[l + 1]; e++) {
+            const int v = P.level_nodes[e];
+            const int u = P.u[v], pv = P.p[v];
+            const int nsl = std::max(1, (u + B200_SLICE - 1) / B200_SLICE);
+            cdone_init[v] = 0;
+            for (int sl = 0; sl < nsl; sl++) {
+                const int r0 = sl * B200_SLICE;
+                const int nrows = std::max(0, std::min(B200_SLICE, u - r0));
+                top_items.push_back({v, r0, nrows, sl, (int)top_ranges.size(), 0});
+                top_slot.push_back(nslots);
+                for (int c = P.child_ptr[v]; c < P.child_ptr[v + 1]; c++) {
+                    const int ch = P.child_idx[c];
+                    const int* rel = &P.rel[P.rows_ptr[ch]];
+                    top_ranges.push_back((int)(std::lower_bound(rel, rel + P.u[ch], pv) - rel));
+                    top_ranges.push_back((int)(std::lower_bound(rel, rel + P.u[ch], pv + r0) - rel));
+                    top_ranges.push_back((int)(std::lower_bound(rel, rel + P.u[ch], pv + r0 + nrows) - rel));
+                }
+            }
+            nslots += nsl;
+        }
+    s->n_top_items = (int)top_items.size();
+
 #define UP(dst, vec) CUDA_TRY(upload(&s->dst, vec), B200_ERROR_CUDA_MALLOC)
     UP(d_nodes, nodes);
     UP(d_rows, P.rows);
@@ -583,6 +660,19 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     UP(d_child_idx, P.child_idx);
     UP(d_fact_nodes, fact_nodes);
     UP(d_solve_nodes, solve_nodes);
+    {
+        std::vector<int> inv_nodes;
+        s->lv.inv_ptr.assign(NIC + 1, 0);
+        for (int c = 0; c < NIC; c++) {
+            for (int v = 0; v < P.nnodes; v++) {
+                int cls = 0;
+                while (cls < NIC - 1 && P.p[v] > IC_MAXP[cls]) cls++;
+                if (cls == c) inv_nodes.push_back(v);
+            }
+            s->lv.inv_ptr[c + 1] = (int)inv_nodes.size();
+        }
+        UP(d_inv_nodes, inv_nodes);
+    }
     UP(d_asm, asm_items);
     UP(d_panel, panel_items);
     UP(d_schur, schur_items);
@@ -590,6 +680,12 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     UP(d_big_slot, big_slot);
     UP(d_asm_ranges, asm_ranges);
     UP(d_big_ranges, big_ranges);
+    UP(d_top_items, top_items);
+    UP(d_top_ranges, top_ranges);
+    UP(d_top_slot, top_slot);
+    UP(d_cdone, cdone_init);
+    s->cdone_init = cdone_init;
+    s->n_slots = nslots;
     UP(d_a_src, P.a_src);
     {
         std::vector<long long> dst(P.a_dst.begin(), P.a_dst.end());
@@ -629,18 +725,36 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     DM(d_big_tickets, std::max(nslots, 1), int);
     CUDA_TRY(cudaMemset(s->d_big_tickets, 0, (size_t)std::max(nslots, 1) * sizeof(int)), B200_ERROR_CUDA_MALLOC);
     DM(d_norms, 4, double);
+    DM(d_xdone, P.nnodes, int);
+    DM(d_epoch, 1, int);
+    DM(d_abort, 1, int);
+    CUDA_TRY(cudaMemset(s->d_xdone, 0, (size_t)std::max(P.nnodes, 1) * sizeof(int)), B200_ERROR_CUDA_MALLOC);
+    CUDA_TRY(cudaMemset(s->d_epoch, 0, sizeof(int)), B200_ERROR_CUDA_MALLOC);
+    CUDA_TRY(cudaMemset(s->d_abort, 0, sizeof(int)), B200_ERROR_CUDA_MALLOC);
 #undef DM
     CUDA_TRY(cudaMallocHost((void**)&s->h_norms, 4 * sizeof(double)), B200_ERROR_MALLOC);
-    CUDA_TRY(cudaMallocHost((void**)&s->h_counters, 4 * sizeof(int) + sizeof(unsigned long long)), B200_ERROR_MALLOC);
+    CUDA_TRY(cudaMallocHost((void**)&s->h_counters, 16 * sizeof(int)), B200_ERROR_MALLOC);
 
     // kernels that need more than 48 KB of dynamic shared memory
     const int W = s->opt_panel_width;
     CUDA_TRY(cudaFuncSetAttribute(k_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_diag(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
+    CUDA_TRY(cudaFuncSetAttribute(k_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_invert(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_front_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused(B200_FUSED_MAXF, B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_panel(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_schur_fma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_schur_fma(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_schur_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_schur_dmma()), B200_ERROR_NOT_AVAILABLE);
     (void)W;
+    if (s->n_top_items > 0) {
+        CUDA_TRY(cudaFuncSetAttribute(k_fwd_top, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_TOP_SMEM), B200_ERROR_NOT_AVAILABLE);
+        CUDA_TRY(cudaFuncSetAttribute(k_bwd_top, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_TOP_SMEM), B200_ERROR_NOT_AVAILABLE);
+        int occ_f = 0, occ_b = 0, nsm = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_fwd_top, 256, B200_TOP_SMEM), B200_ERROR_NOT_AVAILABLE);
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_bwd_top, 256, B200_TOP_SMEM), B200_ERROR_NOT_AVAILABLE);
+        CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device), B200_ERROR_NOT_AVAILABLE);
+        int occ = std::min(occ_f, occ_b);
+        if (occ < 1) s->n_top_items = 0; // cannot guarantee co-residency: fall back to per-level launches
+        s->top_grid = std::max(1, std::min(s->n_top_items, occ * nsm));
+    }
 
     // algorithmic bytes: SpTRSV streams every stored factor entry once (+ the pivot-block inverses)
     // and touches the vectors; SpMV = 12 B per nonzero + row pointers + x and y
@@ -673,6 +787,15 @@ int32_t solver_b200_factorize_device(struct InterfaceB200* s, const double* d_va
     CUDA_TRY(cudaSetDevice(s->device), B200_ERROR_NOT_AVAILABLE);
     const Plan& P = s->plan;
     s->factorized = false;
+    if (s->sweep_dirty) { // re-arm the dependency counters of the persistent sweep after an aborted solve
+        CUDA_TRY(cudaMemcpyAsync(s->d_cdone, s->cdone_init.data(), s->cdone_init.size() * sizeof(int), cudaMemcpyHostToDevice, s->stream), B200_ERROR_CUDA_MEMCPY);
+        CUDA_TRY(cudaMemsetAsync(s->d_xdone, 0, (size_t)std::max(P.nnodes, 1) * sizeof(int), s->stream), B200_ERROR_CUDA_MEMCPY);
+        CUDA_TRY(cudaMemsetAsync(s->d_epoch, 0, sizeof(int), s->stream), B200_ERROR_CUDA_MEMCPY);
+        CUDA_TRY(cudaMemsetAsync(s->d_abort, 0, sizeof(int), s->stream), B200_ERROR_CUDA_MEMCPY);
+        CUDA_TRY(cudaMemsetAsync(s->d_big_tickets, 0, (size_t)std::max(s->n_slots, 1) * sizeof(int), s->stream), B200_ERROR_CUDA_MEMCPY);
+        CUDA_TRY(cudaStreamSynchronize(s->stream), B200_ERROR_CUDA_SYNCHRONIZE);
+        s->sweep_dirty = false;
+    }
     if (d_values != s->d_vals)
         CUDA_TRY(cudaMemcpyAsync(s->d_vals, d_values, (size_t)s->nnz_in * sizeof(double), cudaMemcpyDeviceToDevice, s->stream), B200_ERROR_CUDA_MEMCPY);
     cudaEventRecord(s->ev[0], s->stream);
@@ -762,9 +885,16 @@ int32_t solver_b200_solve_device(struct InterfaceB200* s, double* d_xout, const 
     }
     cudaEventRecord(s->ev[3], s->stream);
     s->last_refine_steps = steps;
+    if (s->n_top_items > 0) cudaMemcpyAsync(s->h_counters + 8, s->d_abort, sizeof(int), cudaMemcpyDeviceToHost, s->stream);
     cudaError_t e = cudaStreamSynchronize(s->stream);
     if (rc != 0 || e != cudaSuccess) {
         if (s->verbose) fprintf(stderr, "solver_b200_solve: %s\n", cudaGetErrorString(e));
+        return B200_ERROR_SOLVE + 1;
+    }
+    if (s->n_top_items > 0 && s->h_counters[8] != 0) { // a dependency wait timed out: reset the sweep state and report
+        s->sweep_dirty = true;
+        s->factorized = false;
+        if (s->verbose) fprintf(stderr, "solver_b200_solve: persistent sweep aborted (dependency wait timed out)\n");
         return B200_ERROR_SOLVE + 1;
     }
     cudaEventElapsedTime(&s->ms_solve, s->ev[2], s->ev[3]);

@@ -1,0 +1,217 @@
+// sweep_top.cuh -- persistent, dependency-driven triangular-solve kernels for the TOP of the front tree.
+//
+// The upper levels of the assembly tree hold few, large fronts (the chain-split separators): per-level kernel
+// launches leave the GPU idle between ~60 dependent launches.  Here ONE co-resident grid walks all (front, row
+// slice) items of those levels in level order; instead of kernel boundaries, a slice waits on per-front completion
+// counters in global memory (release: __threadfence + atomicAdd, acquire: volatile load + __threadfence), and the
+// front's panel slice and pivot-block inverse are staged into shared memory with cp.async BEFORE the wait, so the
+// HBM stream runs ahead of the dependency wave.
+//
+// Progress guarantee: items are sorted so that every dependency has a smaller index; CTA b processes items
+// b, b+G, b+2G, ... in increasing order and all G CTAs are co-resident (G <= occupancy * #SMs), hence the
+// unfinished item with the smallest index can always run.  Spins are bounded: on timeout an abort flag makes every
+// CTA leave, and the host reports B200_ERROR_SOLVE+1 instead of hanging the device.
+//
+// Role in the reference: the inside of umfpack_di_solve / cudssExecute(SOLVE)
+// (russell_sparse/c_code/interface_umfpack.c:229, interface_cudss.cu:530).
+#pragma once
+#include "kernels.cuh"
+
+namespace b200 {
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n" ::);
+    asm volatile("cp.async.wait_group 0;\n" ::);
+}
+
+// bounded acquire-spin: returns false (and raises *abort_flag) on timeout or when another CTA aborted
+__device__ __forceinline__ bool wait_counter_ge(const int* counter, int target, int* abort_flag) {
+    const volatile int* vc = counter;
+    const volatile int* va = abort_flag;
+    for (int it = 0; it < (1 << 22); it++) {
+        if (*vc >= target) {
+            __threadfence();
+            return true;
+        }
+        if ((it & 255) == 255 && *va) return false;
+        __nanosleep(32);
+    }
+    atomicExch(abort_flag, 1);
+    return false;
+}
+
+// dynamic shared memory: D (MAXP*MAXP) | panel slice (SLICE*MAXP) doubles
+#define B200_TOP_SMEM ((size_t)(B200_MAXP * B200_MAXP + B200_SLICE * B200_MAXP) * sizeof(double))
+
+__device__ __forceinline__ int slices_of(int u) { return u > 0 ? (u + B200_SLICE - 1) / B200_SLICE : 1; }
+
+__global__ void __launch_bounds__(256) k_fwd_top(const SolveItem* __restrict__ items, int nitems, const NodeDev* __restrict__ nodes,
+                                                 const int* __restrict__ child_idx, const int* __restrict__ rel_all,
+                                                 const double* __restrict__ fac, const double* __restrict__ dinv,
+                                                 const int* __restrict__ lperm, const int* __restrict__ ranges,
+                                                 const double* __restrict__ y, double* __restrict__ zv, double* __restrict__ wv,
+                                                 int* __restrict__ cdone, const int* __restrict__ epoch_ptr, int* __restrict__ abort_flag) {
+    const int epoch = *epoch_ptr;
+    extern __shared__ double smt[];
+    double* Ds = smt;
+    double* Ps = smt + B200_MAXP * B200_MAXP; // Ps[k * SLICE + r]
+    __shared__ double t1[B200_MAXP], z[B200_MAXP], wloc[B200_SLICE], wpart[B200_SLICE];
+    __shared__ int s_ok;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int itx = blockIdx.x; itx < nitems; itx += gridDim.x) {
+        const SolveItem it = items[itx];
+        const NodeDev nd = nodes[it.node];
+        const int p = nd.p, u = nd.u;
+        const long long f = (long long)p + u;
+        // ---- stage the pivot-block inverse and this slice of L21 (independent of the dependency wait)
+        {
+            const double* D = dinv + nd.Doff;
+            for (int e = tid; e < p * p; e += nt) cp_async8(Ds + e, D + e);
+            const int r = tid & (B200_SLICE - 1), g = tid >> 7;
+            if (r < it.nrows) {
+                const double* src = fac + nd.Loff + p + it.r0 + r;
+                for (int k = g; k < p; k += 2) cp_async8(Ps + k * B200_SLICE + r, src + (long long)k * f);
+            }
+        }
+        if (tid < p) t1[tid] = y[nd.c0 + tid];
+        if (tid < B200_SLICE) wloc[tid] = 0.0;
+        // ---- wait for the children (fronts below the top region are complete before this kernel starts:
+        //      their counters are pre-set to a huge value)
+        if (tid == 0) {
+            int ok = 1;
+            for (int e = 0; e < nd.nchild && ok; e++) {
+                const int c = child_idx[nd.child_ptr + e];
+                ok = wait_counter_ge(&cdone[c], epoch * slices_of(nodes[c].u), abort_flag) ? 1 : 0;
+            }
+            s_ok = ok;
+        }
+        __syncthreads();
+        if (!s_ok) return;
+        const int lo = p + it.r0;
+        for (int e = 0; e < nd.nchild; e++) {
+            const int c = child_idx[nd.child_ptr + e];
+            const NodeDev cd = nodes[c];
+            const int* rel = rel_all + cd.rows_ptr;
+            const double* wc = wv + cd.rows_ptr;
+            const int nhead = ranges[it.rng + 3 * e], a = ranges[it.rng + 3 * e + 1], b = ranges[it.rng + 3 * e + 2];
+            for (int i = tid; i < nhead; i += nt) t1[rel[i]] += __ldcg(wc + i); // written by other SMs: read through L2
+            for (int i = a + tid; i < b; i += nt) wloc[rel[i] - lo] += __ldcg(wc + i);
+            __syncthreads();
+        }
+        double tp = 0.0;
+        if (tid < p) tp = t1[lperm[nd.c0 + tid]];
+        cp_async_wait_all();
+        __syncthreads();
+        if (tid < p) t1[tid] = tp;
+        __syncthreads();
+        if (tid < p) {
+            double s = t1[tid];
+            for (int m = 0; m < tid; m++) s += Ds[tid + m * p] * t1[m];
+            z[tid] = s;
+            if (it.slice == 0) zv[nd.c0 + tid] = s;
+        }
+        __syncthreads();
+        {
+            const int r = tid & (B200_SLICE - 1), h = tid >> 7;
+            const int kh = (p + 1) >> 1;
+            const int kbeg = h * kh, kend = min(p, kbeg + kh);
+            double s = 0.0;
+            if (r < it.nrows)
+                for (int k = kbeg; k < kend; k++) s += Ps[k * B200_SLICE + r] * z[k];
+            if (h == 1) wpart[r] = s;
+            __syncthreads();
+            if (h == 0 && r < it.nrows) wv[nd.rows_ptr + it.r0 + r] = wloc[r] - (s + wpart[r]);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(&cdone[it.node], 1);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_bwd_top(const SolveItem* __restrict__ items, int nitems, const NodeDev* __restrict__ nodes,
+                                                 const int* __restrict__ rows_all, const double* __restrict__ fac,
+                                                 const double* __restrict__ dinv, const double* __restrict__ zv,
+                                                 double* __restrict__ xp, double* __restrict__ scratch, int* __restrict__ tickets,
+                                                 const int* __restrict__ slot_of_item, int* __restrict__ xdone,
+                                                 const int* __restrict__ epoch_ptr, int* __restrict__ abort_flag) {
+    const int epoch = *epoch_ptr;
+    extern __shared__ double smt[];
+    double* Ds = smt;
+    double* Ps = smt + B200_MAXP * B200_MAXP;
+    __shared__ double t[B200_MAXP], x2[B200_SLICE];
+    __shared__ int s_flag;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
+    // items are stored in forward (level-ascending) order: walk them backwards
+    for (int itx = nitems - 1 - (int)blockIdx.x; itx >= 0; itx -= gridDim.x) {
+        const SolveItem it = items[itx];
+        const NodeDev nd = nodes[it.node];
+        const int p = nd.p, u = nd.u;
+        const int nsl = slices_of(u);
+        {
+            const double* D = dinv + nd.Doff;
+            for (int e = tid; e < p * p; e += nt) cp_async8(Ds + e, D + e);
+            const int r = tid & (B200_SLICE - 1), g = tid >> 7;
+            if (r < it.nrows) {
+                const double* src = fac + nd.Uoff + it.r0 + r;
+                for (int k = g; k < p; k += 2) cp_async8(Ps + k * B200_SLICE + r, src + (long long)k * u);
+            }
+        }
+        if (tid == 0) {
+            const int par = nd.pad; // parent front (or -1)
+            s_flag = (par < 0) ? 1 : (wait_counter_ge(&xdone[par], epoch, abort_flag) ? 1 : 0);
+        }
+        __syncthreads();
+        if (!s_flag) return;
+        const int* rows = rows_all + nd.rows_ptr + it.r0;
+        if (tid < it.nrows) x2[tid] = __ldcg(xp + rows[tid]);
+        cp_async_wait_all();
+        __syncthreads();
+        const int slot = slot_of_item[itx];
+        double* part = scratch + ((long long)slot + it.slice) * B200_MAXP;
+        for (int k = warp; k < p; k += nwarps) {
+            const double* col = Ps + k * B200_SLICE;
+            double s = 0.0;
+            for (int j = lane; j < it.nrows; j += 32) s += col[j] * x2[j];
+            for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+            if (lane == 0) part[k] = s;
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            int ticket = atomicAdd(&tickets[slot], 1);
+            s_flag = (ticket == nsl - 1);
+        }
+        __syncthreads();
+        if (s_flag) { // last slice of this front: reduce the partials in slice order and finish the pivot block
+            __threadfence();
+            if (tid < p) {
+                double s = zv[nd.c0 + tid];
+                const double* base = scratch + (long long)slot * B200_MAXP;
+                for (int sl = 0; sl < nsl; sl++) s -= __ldcg(base + (long long)sl * B200_MAXP + tid);
+                t[tid] = s;
+            }
+            if (tid == 0) tickets[slot] = 0;
+            __syncthreads();
+            if (tid < p) {
+                double s = 0.0;
+                for (int m = tid; m < p; m++) s += Ds[tid + m * p] * t[m];
+                xp[nd.c0 + tid] = s;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence();
+                atomicExch(&xdone[it.node], epoch);
+            }
+        }
+        __syncthreads(); // shared buffers are reused by the next item
+    }
+}
+
+} // namespace b200
