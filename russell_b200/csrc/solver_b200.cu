@@ -73,6 +73,7 @@ struct InterfaceB200 {
     int use_graph = 1;
     int schur_variant = 1; // 0 = FMA, 1 = DMMA
     int use_fused = 1;     // fronts with f <= B200_FUSED_MAXF go through k_front_fused
+    int diag_variant = 1;  // 0 = shared-memory LU (k_diag), 1 = register-resident LU with implicit pivoting (k_diag_reg)
     int nrefine = 2;
     double ir_tol = 1e-11;
     double pivot_eps = 1e-13;
@@ -266,7 +267,7 @@ size_t smem_diag(int) { return (size_t)(B200_MAXP * (B200_MAXP + 1)) * sizeof(do
 size_t smem_invert(int pmax) { return (size_t)(pmax * (pmax | 1) + pmax * pmax) * sizeof(double); }
 size_t smem_panel(int W) { return (size_t)(W * W + B200_TR * W) * sizeof(double) + W * sizeof(int); }
 size_t smem_schur_fma(int W) { return (size_t)2 * W * B200_TS * sizeof(double); }
-size_t smem_schur_dmma() { return (size_t)2 * B200_MAXP * (B200_TS + 1) * sizeof(double); }
+size_t smem_schur_dmma() { return (size_t)2 * B200_MAXP * (B200_TS + 8) * sizeof(double); }
 
 // enqueue the per-level numeric kernels: fused fronts (one launch per size class), then the big-front path
 // (assembly -> pivot block -> panels -> Schur complement)
@@ -293,8 +294,12 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
             k_assemble<<<na, 256, 0, s->stream>>>(s->d_asm + lv.asm_ptr[l], s->d_nodes, s->d_child_idx, s->d_rel, s->d_asm_ranges, s->d_fac, s->d_cb);
             cnt++;
         }
-        k_diag<<<nbig, 512, smem_diag(W), s->stream>>>(s->d_fact_nodes + fp[NFC], s->d_nodes, s->d_fac,
-                                                         s->d_lperm, s->d_upiv, s->d_amax, s->pivot_eps, s->d_counters);
+        if (s->diag_variant == 1)
+            k_diag_reg<<<nbig, 512, 0, s->stream>>>(s->d_fact_nodes + fp[NFC], s->d_nodes, s->d_fac, s->d_lperm, s->d_upiv, s->d_amax,
+                                                    s->pivot_eps, s->d_counters);
+        else
+            k_diag<<<nbig, 512, smem_diag(W), s->stream>>>(s->d_fact_nodes + fp[NFC], s->d_nodes, s->d_fac,
+                                                           s->d_lperm, s->d_upiv, s->d_amax, s->pivot_eps, s->d_counters);
         cnt++;
         int np = lv.panel_ptr[l + 1] - lv.panel_ptr[l];
         if (np > 0) {
@@ -475,6 +480,7 @@ struct InterfaceB200* solver_b200_new(void) {
     if ((e = getenv("B200_SCHUR_VARIANT"))) s->schur_variant = atoi(e);
     if ((e = getenv("B200_USE_FUSED"))) s->use_fused = atoi(e);
     if ((e = getenv("B200_USE_TOP"))) s->use_top = atoi(e);
+    if ((e = getenv("B200_DIAG_VARIANT"))) s->diag_variant = atoi(e);
     if ((e = getenv("B200_PANEL_WIDTH"))) s->opt_panel_width = atoi(e);
     if ((e = getenv("B200_ND_LEAF"))) s->opt_nd_leaf = atoi(e);
     return s;
@@ -503,6 +509,7 @@ int32_t solver_b200_set_option(struct InterfaceB200* s, const char* key, double 
     else if (k == "schur_variant") s->schur_variant = (int)value;
     else if (k == "use_fused") s->use_fused = value != 0.0;
     else if (k == "use_top") s->use_top = value != 0.0;
+    else if (k == "diag_variant") s->diag_variant = (int)value;
     else if (k == "force_no_matching") s->force_no_matching = value != 0.0;
     else if (k == "device") {
         // re-home the handle: the stream and the timing events belong to a device

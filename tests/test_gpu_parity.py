@@ -256,6 +256,20 @@ def test_factor_panels_match_host_walk_lower_and_saddle():
     _factor_compare(rb.CooMatrix.from_triplets(n, n, ai, aj, ax), {})
 
 
+@pytest.mark.parametrize("opts", [{"diag_variant": 0}, {"diag_variant": 1}, {"use_fused": 0}, {"use_top": 0}, {"schur_variant": 0, "use_fused": 0}])
+def test_kernel_variants_match_host_walk(opts):
+    # every alternative code path (shared-memory vs register-resident pivot-block LU, fused vs multi-kernel fronts,
+    # persistent vs per-level sweeps) against the scalar walk, on a grid with fronts above the fused limit
+    n, ai, aj, ax = helpers.convection_diffusion_triplets(140)
+    coo = rb.CooMatrix.from_triplets(n, n, ai, aj, ax)
+    sol = _factor_compare(coo, opts)
+    b = np.sin(np.arange(n) + 1.0)
+    x = np.zeros(n)
+    sol.solve(x, b)
+    a = oracle.full_scipy_matrix(n, n, ai, aj, ax)
+    assert np.linalg.norm(b - a @ x) / np.linalg.norm(b) <= TOL_RESIDUAL
+
+
 def test_graph_replay_equals_direct_launches():
     coo = helpers.laplacian_2d_coo(90)
     b = np.cos(np.arange(coo.nrow))
