@@ -73,6 +73,7 @@ struct InterfaceB200 {
     int use_graph = 1;
     int schur_variant = 1; // 0 = FMA, 1 = DMMA
     int use_fused = 1;     // fronts with f <= B200_FUSED_MAXF go through k_front_fused
+    int fuse_chain = 1;    // chain links receive their child's Schur complement directly (no k_assemble pass)
     int diag_variant = 1;  // 0 = shared-memory LU (k_diag), 1 = register-resident LU with implicit pivoting (k_diag_reg)
     int nrefine = 2;
     double ir_tol = 1e-11;
@@ -198,6 +199,19 @@ void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::ve
             if (f <= FC_MAXF[c]) return c;
         return NFC;
     };
+    // a front is fed by the fused Schur epilogue of its single child when it is a later panel of a split supernode
+    // (update set of the child == this front, identity relative indices) and both run on the multi-kernel path
+    auto chain_fused = [&](int v) {
+        if (!s->fuse_chain || s->schur_variant != 1) return false;
+        if (P.child_ptr[v + 1] - P.child_ptr[v] != 1) return false;
+        const int c = P.child_idx[P.child_ptr[v]];
+        if (P.u[c] != P.p[v] + P.u[v]) return false;
+        if (fclass(P.p[v] + P.u[v]) != NFC || fclass(P.p[c] + P.u[c]) != NFC) return false;
+        const int* rel = &P.rel[P.rows_ptr[c]];
+        for (int i = 0; i < P.u[c]; i++)
+            if (rel[i] != i) return false;
+        return true;
+    };
     auto sclass = [&](int f) {
         for (int c = 0; c < NSC; c++)
             if (f <= SC_MAXF[c]) return c;
@@ -229,7 +243,7 @@ void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::ve
             const int p = P.p[v], u = P.u[v], f = p + u;
             if (fclass(f) != NFC) continue; // fused fronts need no work items
             const int nch = P.child_ptr[v + 1] - P.child_ptr[v];
-            if (nch > 0) {
+            if (nch > 0 && !chain_fused(v)) {
                 double total = 0;
                 for (int c = P.child_ptr[v]; c < P.child_ptr[v + 1]; c++) {
                     double uc = P.u[P.child_idx[c]];
@@ -253,8 +267,10 @@ void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::ve
                 for (int r0 = 0; r0 < u; r0 += B200_TR) panel_items.push_back({v, r0, std::min(B200_TR, u - r0), 0});
                 for (int r0 = 0; r0 < u; r0 += B200_TR) panel_items.push_back({v, r0, std::min(B200_TR, u - r0), 1});
                 int nt = (u + B200_TS - 1) / B200_TS;
+                const int par = P.parent[v];
+                const int fuse_into = (par >= 0 && chain_fused(par)) ? par : -1;
                 for (int tj = 0; tj < nt; tj++)
-                    for (int ti = 0; ti < nt; ti++) schur_items.push_back({v, ti, tj, 0});
+                    for (int ti = 0; ti < nt; ti++) schur_items.push_back({v, ti, tj, fuse_into});
             }
         }
         lv.asm_ptr[l + 1] = (int)asm_items.size();
@@ -481,6 +497,7 @@ struct InterfaceB200* solver_b200_new(void) {
     if ((e = getenv("B200_USE_FUSED"))) s->use_fused = atoi(e);
     if ((e = getenv("B200_USE_TOP"))) s->use_top = atoi(e);
     if ((e = getenv("B200_DIAG_VARIANT"))) s->diag_variant = atoi(e);
+    if ((e = getenv("B200_FUSE_CHAIN"))) s->fuse_chain = atoi(e);
     if ((e = getenv("B200_PANEL_WIDTH"))) s->opt_panel_width = atoi(e);
     if ((e = getenv("B200_ND_LEAF"))) s->opt_nd_leaf = atoi(e);
     return s;
@@ -510,6 +527,7 @@ int32_t solver_b200_set_option(struct InterfaceB200* s, const char* key, double 
     else if (k == "use_fused") s->use_fused = value != 0.0;
     else if (k == "use_top") s->use_top = value != 0.0;
     else if (k == "diag_variant") s->diag_variant = (int)value;
+    else if (k == "fuse_chain") s->fuse_chain = value != 0.0;
     else if (k == "force_no_matching") s->force_no_matching = value != 0.0;
     else if (k == "device") {
         // re-home the handle: the stream and the timing events belong to a device

@@ -256,7 +256,8 @@ def test_factor_panels_match_host_walk_lower_and_saddle():
     _factor_compare(rb.CooMatrix.from_triplets(n, n, ai, aj, ax), {})
 
 
-@pytest.mark.parametrize("opts", [{"diag_variant": 0}, {"diag_variant": 1}, {"use_fused": 0}, {"use_top": 0}, {"schur_variant": 0, "use_fused": 0}])
+@pytest.mark.parametrize("opts", [{"diag_variant": 0}, {"diag_variant": 1}, {"use_fused": 0}, {"use_top": 0}, {"fuse_chain": 0},
+                                  {"schur_variant": 0, "use_fused": 0}, {"panel_width": 16, "use_fused": 0}])
 def test_kernel_variants_match_host_walk(opts):
     # every alternative code path (shared-memory vs register-resident pivot-block LU, fused vs multi-kernel fronts,
     # persistent vs per-level sweeps) against the scalar walk, on a grid with fronts above the fused limit
