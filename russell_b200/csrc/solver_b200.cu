@@ -57,6 +57,7 @@ struct LevelLists {
     std::vector<int> fact_ptr;
     // solve_ptr[l*NSC+c .. +1] inside d_solve_nodes
     std::vector<int> solve_ptr;
+    std::vector<int> solve_threads, solve_pmax; // per level: block size and largest pivot count of the small launch
     std::vector<int> big_ptr; // nlevels+1: slices of the big solve class inside d_big_items
     std::vector<int> inv_ptr; // NIC+1: fronts by pivot-count class inside d_inv_nodes
     std::vector<size_t> fused_smem; // per (level, class): dynamic shared memory of the fused launch
@@ -192,6 +193,8 @@ void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::ve
     lv.schur_ptr.assign(P.nlevels + 1, 0);
     lv.fact_ptr.assign((size_t)P.nlevels * (NFC + 1) + 1, 0);
     lv.solve_ptr.assign((size_t)P.nlevels * NSC + 1, 0);
+    lv.solve_threads.assign(P.nlevels, 32);
+    lv.solve_pmax.assign(P.nlevels, 1);
     lv.fused_smem.assign((size_t)P.nlevels * NFC, 0);
     auto fclass = [&](int f) {
         if (!s->use_fused) return NFC;
@@ -231,12 +234,25 @@ void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::ve
             }
             lv.fact_ptr[(size_t)l * (NFC + 1) + c + 1] = (int)fact_nodes.size();
         }
-        for (int c = 0; c < NSC; c++) {
+        {
+            // solve phase: ONE launch per level for all fronts below the "big" threshold (block size chosen from the
+            // level's largest such front), plus the sliced launch for big fronts
+            int maxf = 0, maxp = 0;
             for (int e = P.level_ptr[l]; e < P.level_ptr[l + 1]; e++) {
                 const int v = P.level_nodes[e];
-                if (sclass(P.p[v] + P.u[v]) == c) solve_nodes.push_back(v);
+                const int f = P.p[v] + P.u[v];
+                if (sclass(f) < NSC - 1) maxf = std::max(maxf, f), maxp = std::max(maxp, P.p[v]);
             }
-            lv.solve_ptr[(size_t)l * NSC + c + 1] = (int)solve_nodes.size();
+            lv.solve_threads[l] = maxf <= 32 ? 32 : (maxf <= 64 ? 64 : 128);
+            lv.solve_pmax[l] = std::max(maxp, 1);
+            for (int c = 0; c < NSC; c++) {
+                for (int e = P.level_ptr[l]; e < P.level_ptr[l + 1]; e++) {
+                    const int v = P.level_nodes[e];
+                    const int cls = sclass(P.p[v] + P.u[v]) < NSC - 1 ? 0 : NSC - 1; // everything small goes to slot 0
+                    if (cls == c) solve_nodes.push_back(v);
+                }
+                lv.solve_ptr[(size_t)l * NSC + c + 1] = (int)solve_nodes.size();
+            }
         }
         for (int e = P.level_ptr[l]; e < P.level_ptr[l + 1]; e++) {
             const int v = P.level_nodes[e];
@@ -365,7 +381,7 @@ int enqueue_sweep_levels(InterfaceB200* s, int* launches) {
         for (int c = 0; c < NSC - 1; c++) {
             int a = lv.solve_ptr[(size_t)l * NSC + c], b = lv.solve_ptr[(size_t)l * NSC + c + 1];
             if (b > a) {
-                k_fwd<<<b - a, SC_THREADS[c], (size_t)SC_MAXP[c] * SC_MAXP[c] * sizeof(double), s->stream>>>(s->d_solve_nodes + a, s->d_nodes, s->d_child_idx, s->d_rel, s->d_fac,
+                k_fwd<<<b - a, lv.solve_threads[l], (size_t)lv.solve_pmax[l] * lv.solve_pmax[l] * sizeof(double), s->stream>>>(s->d_solve_nodes + a, s->d_nodes, s->d_child_idx, s->d_rel, s->d_fac,
                                                              s->d_dinv, s->d_lperm, s->d_y, s->d_z, s->d_wv);
                 cnt++;
             }
@@ -387,7 +403,7 @@ int enqueue_sweep_levels(InterfaceB200* s, int* launches) {
         for (int c = 0; c < NSC - 1; c++) {
             int a = lv.solve_ptr[(size_t)l * NSC + c], b = lv.solve_ptr[(size_t)l * NSC + c + 1];
             if (b > a) {
-                k_bwd<<<b - a, SC_THREADS[c], (size_t)SC_MAXP[c] * SC_MAXP[c] * sizeof(double), s->stream>>>(s->d_solve_nodes + a, s->d_nodes, s->d_rows, s->d_fac, s->d_dinv, s->d_z, s->d_xp);
+                k_bwd<<<b - a, lv.solve_threads[l], (size_t)lv.solve_pmax[l] * lv.solve_pmax[l] * sizeof(double), s->stream>>>(s->d_solve_nodes + a, s->d_nodes, s->d_rows, s->d_fac, s->d_dinv, s->d_z, s->d_xp);
                 cnt++;
             }
         }

@@ -32,13 +32,12 @@ __device__ __forceinline__ void cp_async_wait_all() {
 __device__ __forceinline__ bool wait_counter_ge(const int* counter, int target, int* abort_flag) {
     const volatile int* vc = counter;
     const volatile int* va = abort_flag;
-    for (int it = 0; it < (1 << 22); it++) {
+    for (int it = 0; it < (1 << 24); it++) { // ~0.5 us per probe: a few seconds before giving up
         if (*vc >= target) {
             __threadfence();
             return true;
         }
         if ((it & 255) == 255 && *va) return false;
-        __nanosleep(32);
     }
     atomicExch(abort_flag, 1);
     return false;
@@ -108,11 +107,18 @@ __global__ void __launch_bounds__(256) k_fwd_top(const SolveItem* __restrict__ i
         __syncthreads();
         if (tid < p) t1[tid] = tp;
         __syncthreads();
-        if (tid < p) {
-            double s = t1[tid];
-            for (int m = 0; m < tid; m++) s += Ds[tid + m * p] * t1[m];
-            z[tid] = s;
-            if (it.slice == 0) zv[nd.c0 + tid] = s;
+        {   // z = inv(L11) t1: four threads per row (fixed partition + fixed shuffle order: deterministic)
+            const int k = tid >> 2, part = tid & 3;
+            double s = 0.0;
+            if (k < p)
+                for (int m = part; m < k; m += 4) s += Ds[k + m * p] * t1[m];
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (k < p && part == 0) {
+                s += t1[k];
+                z[k] = s;
+                if (it.slice == 0) zv[nd.c0 + k] = s;
+            }
         }
         __syncthreads();
         {
@@ -199,10 +205,14 @@ __global__ void __launch_bounds__(256) k_bwd_top(const SolveItem* __restrict__ i
             }
             if (tid == 0) tickets[slot] = 0;
             __syncthreads();
-            if (tid < p) {
+            {   // x1 = inv(U11) t: four threads per row
+                const int k = tid >> 2, part = tid & 3;
                 double s = 0.0;
-                for (int m = tid; m < p; m++) s += Ds[tid + m * p] * t[m];
-                xp[nd.c0 + tid] = s;
+                if (k < p)
+                    for (int m = k + part; m < p; m += 4) s += Ds[k + m * p] * t[m];
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                if (k < p && part == 0) xp[nd.c0 + k] = s;
             }
             __syncthreads();
             if (tid == 0) {
