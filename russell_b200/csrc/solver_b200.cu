@@ -74,6 +74,7 @@ struct InterfaceB200 {
     int use_graph = 1;
     int schur_variant = 1; // 0 = FMA, 1 = DMMA
     int use_fused = 1;     // fronts with f <= B200_FUSED_MAXF go through k_front_fused
+    int fused_maxf = B200_FUSED_MAXF; // fronts above this order take the multi-kernel path
     int fuse_chain = 1;    // chain links receive their child's Schur complement directly (no k_assemble pass)
     int diag_variant = 1;  // 0 = shared-memory LU (k_diag), 1 = register-resident LU with implicit pivoting (k_diag_reg)
     int nrefine = 2;
@@ -197,7 +198,7 @@ void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::ve
     lv.solve_pmax.assign(P.nlevels, 1);
     lv.fused_smem.assign((size_t)P.nlevels * NFC, 0);
     auto fclass = [&](int f) {
-        if (!s->use_fused) return NFC;
+        if (!s->use_fused || f > s->fused_maxf) return NFC;
         for (int c = 0; c < NFC; c++)
             if (f <= FC_MAXF[c]) return c;
         return NFC;
@@ -514,6 +515,7 @@ struct InterfaceB200* solver_b200_new(void) {
     if ((e = getenv("B200_USE_TOP"))) s->use_top = atoi(e);
     if ((e = getenv("B200_DIAG_VARIANT"))) s->diag_variant = atoi(e);
     if ((e = getenv("B200_FUSE_CHAIN"))) s->fuse_chain = atoi(e);
+    if ((e = getenv("B200_FUSED_MAXF"))) s->fused_maxf = std::max(0, std::min(atoi(e), B200_FUSED_MAXF));
     if ((e = getenv("B200_PANEL_WIDTH"))) s->opt_panel_width = atoi(e);
     if ((e = getenv("B200_ND_LEAF"))) s->opt_nd_leaf = atoi(e);
     return s;
@@ -544,6 +546,7 @@ int32_t solver_b200_set_option(struct InterfaceB200* s, const char* key, double 
     else if (k == "use_top") s->use_top = value != 0.0;
     else if (k == "diag_variant") s->diag_variant = (int)value;
     else if (k == "fuse_chain") s->fuse_chain = value != 0.0;
+    else if (k == "fused_maxf") s->fused_maxf = std::max(0, std::min((int)value, B200_FUSED_MAXF));
     else if (k == "force_no_matching") s->force_no_matching = value != 0.0;
     else if (k == "device") {
         // re-home the handle: the stream and the timing events belong to a device

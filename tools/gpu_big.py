@@ -25,7 +25,12 @@ def run(k, lower, opts, reps=3):
     return sol
 
 if __name__ == "__main__":
-    if "--profile" in sys.argv:
+    if "--sweep" in sys.argv:
+        # tuning sweep over a runtime option at config-2 size
+        key = sys.argv[sys.argv.index("--sweep") + 1]
+        for val in sys.argv[sys.argv.index("--sweep") + 2:]:
+            run(1000, False, {key: float(val)}, reps=2)
+    elif "--profile" in sys.argv:
         k = int(sys.argv[sys.argv.index("--profile") + 1])
         run(k, False, {"use_graph": 0}, reps=1)
     else:
