@@ -74,7 +74,7 @@ struct InterfaceB200 {
     int use_graph = 1;
     int schur_variant = 1; // 0 = FMA, 1 = DMMA
     int use_fused = 1;     // fronts with f <= B200_FUSED_MAXF go through k_front_fused
-    int fused_maxf = B200_FUSED_MAXF; // fronts above this order take the multi-kernel path
+    int fused_maxf = 48;   // fronts above this order take the multi-kernel path (measured optimum at config 2)
     int fuse_chain = 1;    // chain links receive their child's Schur complement directly (no k_assemble pass)
     int diag_variant = 1;  // 0 = shared-memory LU (k_diag), 1 = register-resident LU with implicit pivoting (k_diag_reg)
     int nrefine = 2;
@@ -97,6 +97,7 @@ struct InterfaceB200 {
     SolveItem* d_big_items = nullptr;
     int* d_big_slot = nullptr;
     // persistent top-of-tree sweep (sweep_top.cuh)
+    int top_max_nodes = 96; // levels with at most this many fronts belong to the persistent sweep region
     int use_top = 1, ltop = 0, n_top_items = 0, top_grid = 0, n_slots = 0;
     bool sweep_dirty = false;          // a persistent sweep aborted: counters must be re-armed
     std::vector<int> cdone_init;       // host copy of the initial completion counters
@@ -260,8 +261,8 @@ void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::ve
             const int p = P.p[v], u = P.u[v], f = p + u;
             if (fclass(f) != NFC) continue; // fused fronts need no work items
             const int nch = P.child_ptr[v + 1] - P.child_ptr[v];
-            if (nch > 0 && !chain_fused(v)) {
-                double total = 0;
+            if (!chain_fused(v)) {
+                double total = (double)u * u * 0.25; // clearing the contribution block counts as work too
                 for (int c = P.child_ptr[v]; c < P.child_ptr[v + 1]; c++) {
                     double uc = P.u[P.child_idx[c]];
                     total += uc * uc;
@@ -546,6 +547,7 @@ int32_t solver_b200_set_option(struct InterfaceB200* s, const char* key, double 
     else if (k == "use_top") s->use_top = value != 0.0;
     else if (k == "diag_variant") s->diag_variant = (int)value;
     else if (k == "fuse_chain") s->fuse_chain = value != 0.0;
+    else if (k == "top_max_nodes") s->top_max_nodes = std::max(1, (int)value);
     else if (k == "fused_maxf") s->fused_maxf = std::max(0, std::min((int)value, B200_FUSED_MAXF));
     else if (k == "force_no_matching") s->force_no_matching = value != 0.0;
     else if (k == "device") {
@@ -671,7 +673,7 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     s->ltop = P.nlevels;
     if (s->use_top) {
         int l = P.nlevels;
-        while (l > 0 && P.level_ptr[l] - P.level_ptr[l - 1] <= 96) l--;
+        while (l > 0 && P.level_ptr[l] - P.level_ptr[l - 1] <= s->top_max_nodes) l--;
         if (P.nlevels - l >= 4) s->ltop = l; // worth it only when a real chain of levels is replaced
     }
     for (int l = s->ltop; l < P.nlevels; l++)
@@ -844,7 +846,6 @@ int32_t solver_b200_factorize_device(struct InterfaceB200* s, const double* d_va
         CUDA_TRY(cudaMemcpyAsync(s->d_vals, d_values, (size_t)s->nnz_in * sizeof(double), cudaMemcpyDeviceToDevice, s->stream), B200_ERROR_CUDA_MEMCPY);
     cudaEventRecord(s->ev[0], s->stream);
     CUDA_TRY(cudaMemsetAsync(s->d_fac, 0, (size_t)P.fac_size * sizeof(double), s->stream), B200_ERROR_NUM_FACTORIZATION + 1);
-    CUDA_TRY(cudaMemsetAsync(s->d_cb, 0, std::max<size_t>((size_t)P.cb_size, 1) * sizeof(double), s->stream), B200_ERROR_NUM_FACTORIZATION + 1);
     CUDA_TRY(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(int), s->stream), B200_ERROR_NUM_FACTORIZATION + 1);
     CUDA_TRY(cudaMemsetAsync(s->d_amax, 0, sizeof(unsigned long long), s->stream), B200_ERROR_NUM_FACTORIZATION + 1);
     k_scatter_values<<<grid_for(s->fnnz), 256, 0, s->stream>>>(s->fnnz, s->d_a_src, s->d_a_dst, s->d_a_scl, s->d_vals, s->d_fac, s->d_amax);
