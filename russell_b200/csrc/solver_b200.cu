@@ -97,7 +97,7 @@ struct InterfaceB200 {
     SolveItem* d_big_items = nullptr;
     int* d_big_slot = nullptr;
     // persistent top-of-tree sweep (sweep_top.cuh)
-    int top_max_nodes = 96; // levels with at most this many fronts belong to the persistent sweep region
+    int top_max_nodes = 1600; // (measured optimum at config 2) levels with at most this many fronts belong to the persistent sweep region
     int use_top = 1, ltop = 0, n_top_items = 0, top_grid = 0, n_slots = 0;
     bool sweep_dirty = false;          // a persistent sweep aborted: counters must be re-armed
     std::vector<int> cdone_init;       // host copy of the initial completion counters
