@@ -42,6 +42,23 @@ def laplacian_csr(k, lower=False):
     return coo, csr.pointers.copy(), csr.indices[:n].copy(), csr.values[:n].copy()
 
 
+def measured_traffic(grid):
+    """DRAM bytes (read + write) of one SpTRSV sweep from the committed ncu capture of the same workload
+    (profiles/*_sptrsv_traffic.json, written from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`);
+    None when no capture of this grid size is committed."""
+    import glob
+    best = (None, None)
+    for f in sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "*_sptrsv_traffic.json"))):
+        try:
+            with open(f) as fh:
+                d = json.load(fh)
+            if int(d.get("grid", -1)) == int(grid):
+                best = (float(d["sptrsv_sweep_traffic_bytes"]), "profiles/" + os.path.basename(f))
+        except Exception:
+            pass
+    return best
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -62,7 +79,7 @@ class ClockSampler:
     def start(self):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -160,7 +177,7 @@ def workload_config(k, gpus):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--grid", type=int, default=1000)
     ap.add_argument("--impl", default="b200")
@@ -289,6 +306,7 @@ def main():
     if rank == 0:
         hbm_peak, peak_src = measured_peaks()
         sptrsv_gbs = st["sptrsv_bytes"] / (parts["sptrsv"] * 1e-3) / 1e9
+        traffic, traffic_src = measured_traffic(k)
         spmv_gbs = st["spmv_bytes"] / (parts["spmv"] * 1e-3) / 1e9 if parts["spmv"] > 0 else None
         line = {
             "metric": "factorize+solve/sec", "value": world * K / (ms_dev * 1e-3), "unit": "systems/s", "n_gpus": world,
@@ -303,7 +321,7 @@ def main():
             "clocks": clocks,
             "roofline": {"kernel": "SpTRSV sweep (k_fwd + k_bwd over all tree levels, one forward+backward solve)",
                          "bound": "hbm", "achieved": sptrsv_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": sptrsv_gbs / hbm_peak,
-                         "peak_source": peak_src, "traffic": None,
+                         "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes": st["sptrsv_bytes"], "ms": parts["sptrsv"]},
             "phases_ms": {"factorize_device": parts["fact"], "solve_device": parts["solve"], "sptrsv_sweep": parts["sptrsv"],
                           "residual_spmv": parts["spmv"], "initialize_once_s": t_init,

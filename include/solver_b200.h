@@ -36,7 +36,7 @@ extern "C" {
 #define B200_ERROR_CUDA_MALLOC 100               /* constants.h:22 */
 #define B200_ERROR_CUDA_MEMCPY 200               /* constants.h:23 */
 #define B200_ERROR_CUDA_SYNCHRONIZE 300          /* constants.h:24 */
-#define B200_ERROR_ANALYSIS 700                  /* phase offset like ERROR_CUDSS_SYM_FACTORIZATION; +1 structurally singular, +2 invalid input */
+#define B200_ERROR_ANALYSIS 700                  /* phase offset like ERROR_CUDSS_SYM_FACTORIZATION; +1 structurally singular, +2 invalid CSR, +3 invalid COO, +4 COO not lower */
 #define B200_ERROR_NUM_FACTORIZATION 800         /* phase offset like ERROR_CUDSS_NUM_FACTORIZATION; +1 kernel launch failure, +2 non-finite values */
 #define B200_ERROR_SOLVE 900                     /* phase offset like ERROR_CUDSS_SOLVE; +1 kernel launch failure, +7 refinement failed */
 
@@ -80,6 +80,25 @@ int32_t solver_b200_solve(struct InterfaceB200 *solver, double *x, const double 
 /* device-resident variants: pointers are DEVICE pointers on the handle's device; no host<->device copies */
 int32_t solver_b200_factorize_device(struct InterfaceB200 *solver, const double *d_values);
 int32_t solver_b200_solve_device(struct InterfaceB200 *solver, double *d_x, const double *d_rhs);
+
+/* COO-level boundary extension.  The reference's wrapper re-runs CsrMatrix::update_from_coo on the
+ * HOST on every factorize (russell_sparse/src/solver_cudss.rs:209, csr_matrix.rs:359-480: counting sort + duplicate
+ * summation, tens of ms at 5M triplets).  Here the triplet STRUCTURE is analysed once (CSR built on the host with the
+ * same duplicate-summation order, plus a triplet->CSR-slot map), and every refactorization only ships the raw triplet
+ * VALUES: a device kernel sums the duplicates of every CSR slot in their order of appearance (bit-identical to the host
+ * conversion) and the numeric factorization follows.
+ * initialize_coo takes the same option arguments as solver_b200_initialize; with general_symmetric (Sym::YesLower)
+ * the triplets must satisfy j <= i (B200_ERROR_ANALYSIS+4 otherwise); +3 = index out of range / empty.
+ * factorize_coo_device takes a DEVICE pointer to nnz_coo values (e.g. an assembly kernel's output). */
+int32_t solver_b200_initialize_coo(struct InterfaceB200 *solver,
+                                   int32_t ordering, int32_t matching, int32_t pivoting,
+                                   double pivot_epsilon, int32_t refinement_nstep, double hybrid_memory_factor,
+                                   int32_t verbose, int32_t general_symmetric, int32_t positive_definite,
+                                   int32_t ndim, int32_t nnz_coo, const int32_t *indices_i, const int32_t *indices_j,
+                                   const double *values);
+int32_t solver_b200_factorize_coo(struct InterfaceB200 *solver, int32_t *effective_matching,
+                                  int32_t *effective_pivoting, int32_t verbose, const double *coo_values);
+int32_t solver_b200_factorize_coo_device(struct InterfaceB200 *solver, const double *d_coo_values);
 
 /* residual r = rhs - A x with the CSR SpMV kernel; returns ||r||_2 / ||rhs||_2 through *rel_residual
  * (russell's VerifyLinSys / the north-star accuracy metric).  Host pointers. */

@@ -326,6 +326,8 @@ _B200_ERRORS = {  # same spirit as handle_cudss_error_code (solver_cudss.rs:501-
     300: "cudaStreamSynchronize failed in the C code (B200)",
     701: "B200 analysis failed: matrix is structurally singular",
     702: "B200 analysis failed: invalid CSR structure",
+    703: "B200 analysis failed: invalid COO structure (index out of range or empty)",
+    704: "B200 analysis failed: Sym::YesLower requires triplets with j <= i",
     801: "B200 numeric factorization failed: kernel launch failure",
     802: "B200 numeric factorization failed: matrix values are not finite",
     901: "B200 solve failed: kernel launch failure",
@@ -363,11 +365,15 @@ class SolverB200:
                   "ms_solve_device", "ms_sptrsv_device", "ms_spmv_device", "launches_factorize", "launches_solve",
                   "sptrsv_bytes", "spmv_bytes", "matched", "t_match_s", "last_backward_error"]
 
-    def __init__(self):
+    def __init__(self, coo_boundary=True):
+        """coo_boundary=True: the triplet structure is analysed once (solver_b200_initialize_coo) and every later
+        factorize ships only the raw triplet values, summed into CSR slots on the device (solver_b200_factorize_coo);
+        False: the reference's data flow, host CsrMatrix::update_from_coo on every call (solver_cudss.rs:209)."""
         self._lib = _lib.load()
         self.solver = self._lib.solver_b200_new()
         if not self.solver:
             raise StrError("c-code failed to allocate the B200 solver")
+        self.coo_boundary = bool(coo_boundary)
         self.csr = None
         self.initialized = False
         self.factorized = False
@@ -403,7 +409,8 @@ class SolverB200:
                 raise StrError("subsequent factorizations must use the same matrix (nnz differs)")
             if params is not None:
                 raise StrError("subsequent factorizations must not change LinSolParams")
-            self.csr.update_from_coo(self._trim(mat))
+            if not self.coo_boundary:
+                self.csr.update_from_coo(self._trim(mat))
         else:
             if mat.nrow != mat.ncol:
                 raise StrError("the matrix must be square")
@@ -414,7 +421,8 @@ class SolverB200:
             self.initialized_sym = mat.symmetric
             self.initialized_ndim = mat.nrow
             self.initialized_nnz = mat.nnz
-            self.csr = CsrMatrix.from_coo(self._trim(mat))
+            if not self.coo_boundary:
+                self.csr = CsrMatrix.from_coo(self._trim(mat))
         csr = self.csr
         par = params if params is not None else LinSolParams()
         pivot_epsilon = par.pivot_epsilon if par.pivot_epsilon is not None else -1.0
@@ -429,20 +437,34 @@ class SolverB200:
         verbose = 1 if par.verbose else 0
         general_symmetric = 1 if mat.symmetric == Sym.YesLower else 0
         positive_definite = 1 if (par.positive_definite and mat.symmetric == Sym.YesLower) else 0
+        import ctypes
+        if self.coo_boundary:
+            tm = self._trim(mat)
+            coo_i = np.ascontiguousarray(tm.indices_i[: mat.nnz], dtype=np.int32)
+            coo_j = np.ascontiguousarray(tm.indices_j[: mat.nnz], dtype=np.int32)
+            coo_v = np.ascontiguousarray(tm.values[: mat.nnz], dtype=np.float64)
         if not self.initialized:
             t0 = time.perf_counter_ns()
-            status = self._lib.solver_b200_initialize(
-                self.solver, b200_ordering(par.ordering), b200_matching(par.matching), b200_pivoting(par.pivoting),
-                pivot_epsilon, refinement_nstep, hybrid, verbose, general_symmetric, positive_definite,
-                _to_i32(csr.nrow), ptr(csr.pointers, p_i32), ptr(csr.indices, p_i32), ptr(csr.values, p_f64))
+            if self.coo_boundary:
+                status = self._lib.solver_b200_initialize_coo(
+                    self.solver, b200_ordering(par.ordering), b200_matching(par.matching), b200_pivoting(par.pivoting),
+                    pivot_epsilon, refinement_nstep, hybrid, verbose, general_symmetric, positive_definite,
+                    _to_i32(mat.nrow), _to_i32(mat.nnz), ptr(coo_i, p_i32), ptr(coo_j, p_i32), ptr(coo_v, p_f64))
+            else:
+                status = self._lib.solver_b200_initialize(
+                    self.solver, b200_ordering(par.ordering), b200_matching(par.matching), b200_pivoting(par.pivoting),
+                    pivot_epsilon, refinement_nstep, hybrid, verbose, general_symmetric, positive_definite,
+                    _to_i32(csr.nrow), ptr(csr.pointers, p_i32), ptr(csr.indices, p_i32), ptr(csr.values, p_f64))
             if status != 0:
                 raise StrError(handle_b200_error_code(status))
             self.time_initialize_ns = time.perf_counter_ns() - t0
             self.initialized = True
         em, ep = _lib.c_i32(0), _lib.c_i32(0)
         t0 = time.perf_counter_ns()
-        import ctypes
-        status = self._lib.solver_b200_factorize(self.solver, ctypes.byref(em), ctypes.byref(ep), verbose, ptr(csr.values, p_f64))
+        if self.coo_boundary:
+            status = self._lib.solver_b200_factorize_coo(self.solver, ctypes.byref(em), ctypes.byref(ep), verbose, ptr(coo_v, p_f64))
+        else:
+            status = self._lib.solver_b200_factorize(self.solver, ctypes.byref(em), ctypes.byref(ep), verbose, ptr(csr.values, p_f64))
         if status != 0:
             raise StrError(handle_b200_error_code(status))
         self.time_factorize_ns = time.perf_counter_ns() - t0

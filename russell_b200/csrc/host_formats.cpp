@@ -55,6 +55,41 @@ int32_t b200_coo_to_csr(int32_t nrow, int32_t ncol, int32_t nnz, const int32_t* 
     return 0;
 }
 
+// Same conversion, additionally returning the triplet -> slot map: seg_ptr[nslots+1] / seg_idx[nnz] list, for every
+// CSR slot, the triplets summed into it in order of appearance.  (row_pointers, col_indices, values) as above.
+int32_t b200_coo_to_csr_map(int32_t nrow, int32_t ncol, int32_t nnz, const int32_t* ai, const int32_t* aj, const double* ax,
+                            int32_t* ptr, int32_t* idx, double* val, int32_t* seg_ptr, int32_t* seg_idx) {
+    if (nnz < 1) return -2;
+    std::vector<int32_t> start(nrow + 1, 0);
+    for (int32_t k = 0; k < nnz; k++) {
+        if (ai[k] < 0 || ai[k] >= nrow || aj[k] < 0 || aj[k] >= ncol) return -1;
+        start[ai[k] + 1]++;
+    }
+    for (int32_t i = 0; i < nrow; i++) start[i + 1] += start[i];
+    std::vector<int32_t> order(nnz), fill(start.begin(), start.end() - 1);
+    for (int32_t k = 0; k < nnz; k++) order[fill[ai[k]]++] = k;
+    int32_t out = 0, w = 0;
+    ptr[0] = 0;
+    seg_ptr[0] = 0;
+    for (int32_t i = 0; i < nrow; i++) {
+        int32_t* b = order.data() + start[i];
+        int32_t* e = order.data() + start[i + 1];
+        std::stable_sort(b, e, [&](int32_t x, int32_t y) { return aj[x] < aj[y]; });
+        for (int32_t* q = b; q != e;) {
+            const int32_t j = aj[*q];
+            double s = ax[*q];
+            seg_idx[w++] = *q;
+            for (++q; q != e && aj[*q] == j; ++q) s += ax[*q], seg_idx[w++] = *q;
+            idx[out] = j;
+            val[out] = s;
+            out++;
+            seg_ptr[out] = w;
+        }
+        ptr[i + 1] = out;
+    }
+    return 0;
+}
+
 int32_t b200_coo_to_csc(int32_t nrow, int32_t ncol, int32_t nnz, const int32_t* ai, const int32_t* aj, const double* ax,
                         int32_t* ptr, int32_t* idx, double* val) {
     // columns of A are the rows of A^T; the duplicate-summation order (order of appearance) is unchanged

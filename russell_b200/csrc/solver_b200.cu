@@ -115,6 +115,10 @@ struct InterfaceB200 {
     int n_rowblk = 0;
     // device: numeric
     double *d_vals = nullptr, *d_fullvals = nullptr;
+    // COO-level boundary (solver_b200_initialize_coo): triplet -> CSR-slot map and a staging buffer for raw triplet values
+    int nnz_coo = 0;
+    int *d_seg_ptr = nullptr, *d_seg_idx = nullptr;
+    double* d_coo_vals = nullptr;
     const double* spmv_vals = nullptr; // mirrored values (symmetric input) or d_vals (general input)
     double *d_fac = nullptr, *d_cb = nullptr, *d_dinv = nullptr, *d_upiv = nullptr;
     int* d_lperm = nullptr;
@@ -167,6 +171,7 @@ void release_device(InterfaceB200* s) {
     dfree(s->d_rowperm), dfree(s->d_colperm), dfree(s->d_rscale), dfree(s->d_cscale);
     dfree(s->d_full_ptr), dfree(s->d_full_col), dfree(s->d_full_src), dfree(s->d_rowblk);
     dfree(s->d_vals), dfree(s->d_fullvals);
+    dfree(s->d_seg_ptr), dfree(s->d_seg_idx), dfree(s->d_coo_vals);
     dfree(s->d_fac), dfree(s->d_cb), dfree(s->d_dinv), dfree(s->d_upiv), dfree(s->d_lperm);
     dfree(s->d_counters), dfree(s->d_amax);
     dfree(s->d_b), dfree(s->d_x), dfree(s->d_r), dfree(s->d_y), dfree(s->d_z), dfree(s->d_xp), dfree(s->d_wv);
@@ -895,6 +900,66 @@ int32_t solver_b200_factorize(struct InterfaceB200* s, int32_t* effective_matchi
             printf("solver_b200_factorize: WARNING: %d pivot(s) perturbed (matrix may be (nearly) singular)\n", s->n_perturbed);
         printf("solver_b200_factorize: numeric factorization completed in %.3f ms (device)\n", s->ms_factorize);
     }
+    return rc;
+}
+
+// ---- COO-level boundary: what CsrMatrix::update_from_coo + solver_cudss_factorize do together
+// (russell_sparse/src/solver_cudss.rs:195-290), with the per-factorize conversion moved to the device.
+extern "C" int32_t b200_coo_to_csr_map(int32_t nrow, int32_t ncol, int32_t nnz, const int32_t* ai, const int32_t* aj,
+                                       const double* ax, int32_t* ptr, int32_t* idx, double* val, int32_t* seg_ptr,
+                                       int32_t* seg_idx);
+
+int32_t solver_b200_initialize_coo(struct InterfaceB200* s, int32_t ordering, int32_t matching, int32_t pivoting,
+                                   double pivot_epsilon, int32_t refinement_nstep, double hybrid_memory_factor,
+                                   int32_t verbose, int32_t general_symmetric, int32_t positive_definite, int32_t ndim,
+                                   int32_t nnz_coo, const int32_t* indices_i, const int32_t* indices_j, const double* values) {
+    if (!s || !indices_i || !indices_j || !values) return B200_ERROR_NULL_POINTER;
+    if (s->initialized) return B200_ERROR_ALREADY_INITIALIZED;
+    if (ndim < 1 || nnz_coo < 1) return B200_ERROR_ANALYSIS + 3;
+    if (general_symmetric || positive_definite)
+        for (int32_t k = 0; k < nnz_coo; k++)
+            if (indices_j[k] > indices_i[k]) return B200_ERROR_ANALYSIS + 4; // Sym::YesLower promised: j <= i
+    std::vector<int32_t> ptr((size_t)ndim + 1), idx((size_t)nnz_coo), seg_ptr((size_t)nnz_coo + 1), seg_idx((size_t)nnz_coo);
+    std::vector<double> val((size_t)nnz_coo);
+    if (b200_coo_to_csr_map(ndim, ndim, nnz_coo, indices_i, indices_j, values, ptr.data(), idx.data(), val.data(),
+                            seg_ptr.data(), seg_idx.data()) != 0)
+        return B200_ERROR_ANALYSIS + 3;
+    int32_t rc = solver_b200_initialize(s, ordering, matching, pivoting, pivot_epsilon, refinement_nstep, hybrid_memory_factor,
+                                        verbose, general_symmetric, positive_definite, ndim, ptr.data(), idx.data(), val.data());
+    if (rc != B200_SUCCESSFUL_EXIT) return rc;
+    const int nslots = ptr[ndim];
+    s->nnz_coo = nnz_coo;
+    cudaError_t e = cudaMalloc(&s->d_seg_ptr, ((size_t)nslots + 1) * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_seg_idx, (size_t)nnz_coo * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_coo_vals, (size_t)nnz_coo * sizeof(double));
+    if (e != cudaSuccess) return B200_ERROR_CUDA_MALLOC;
+    CUDA_TRY(cudaMemcpyAsync(s->d_seg_ptr, seg_ptr.data(), ((size_t)nslots + 1) * sizeof(int), cudaMemcpyHostToDevice, s->stream), B200_ERROR_CUDA_MEMCPY);
+    CUDA_TRY(cudaMemcpyAsync(s->d_seg_idx, seg_idx.data(), (size_t)nnz_coo * sizeof(int), cudaMemcpyHostToDevice, s->stream), B200_ERROR_CUDA_MEMCPY);
+    CUDA_TRY(cudaStreamSynchronize(s->stream), B200_ERROR_CUDA_SYNCHRONIZE);
+    return B200_SUCCESSFUL_EXIT;
+}
+
+int32_t solver_b200_factorize_coo_device(struct InterfaceB200* s, const double* d_coo_values) {
+    if (!s) return B200_ERROR_NULL_POINTER;
+    if (!s->initialized || !s->d_seg_ptr) return B200_ERROR_NEED_INITIALIZATION;
+    if (!d_coo_values) return B200_ERROR_NULL_POINTER;
+    CUDA_TRY(cudaSetDevice(s->device), B200_ERROR_NOT_AVAILABLE);
+    k_coo_to_csr_values<<<grid_for(s->nnz_in), 256, 0, s->stream>>>(s->nnz_in, s->d_seg_ptr, s->d_seg_idx, d_coo_values, s->d_vals);
+    return solver_b200_factorize_device(s, s->d_vals);
+}
+
+int32_t solver_b200_factorize_coo(struct InterfaceB200* s, int32_t* effective_matching, int32_t* effective_pivoting,
+                                  int32_t verbose, const double* coo_values) {
+    if (!s) return B200_ERROR_NULL_POINTER;
+    if (!s->initialized || !s->d_seg_ptr) return B200_ERROR_NEED_INITIALIZATION;
+    if (!coo_values) return B200_ERROR_NULL_POINTER;
+    s->verbose = verbose;
+    CUDA_TRY(cudaSetDevice(s->device), B200_ERROR_NOT_AVAILABLE);
+    CUDA_TRY(cudaMemcpyAsync(s->d_coo_vals, coo_values, (size_t)s->nnz_coo * sizeof(double), cudaMemcpyHostToDevice, s->stream), B200_ERROR_CUDA_MEMCPY);
+    int32_t rc = solver_b200_factorize_coo_device(s, s->d_coo_vals);
+    if (effective_matching) *effective_matching = s->effective_matching;
+    if (effective_pivoting) *effective_pivoting = s->effective_pivoting;
+    if (rc == 0 && verbose) printf("solver_b200_factorize_coo: numeric factorization completed in %.3f ms (device)\n", s->ms_factorize);
     return rc;
 }
 

@@ -372,6 +372,72 @@ def test_unsymmetric_values_and_refactorization_with_new_values():
         assert np.max(np.abs(x - xs)) <= 1e-9 * np.max(np.abs(xs))
 
 
+@pytest.mark.parametrize("lower", [False, True])
+def test_coo_boundary_device_conversion_is_bit_identical_to_host_conversion(lower):
+    # solver_b200_factorize_coo (device duplicate summation) against solver_b200_factorize fed by the host
+    # CsrMatrix::update_from_coo clone: identical CSR values => identical factors => identical solutions, bit for bit
+    rng = np.random.default_rng(21)
+    n, ai, aj, ax = helpers.convection_diffusion_triplets(60)
+    if lower:
+        n, ai, aj, ax = helpers.laplacian_2d_triplets(60, lower=True)
+    # finite-element style duplicates: split every entry into 1..4 pieces at random positions of the triplet list
+    reps = rng.integers(1, 5, len(ax))
+    di, dj = np.repeat(ai, reps), np.repeat(aj, reps)
+    perm = rng.permutation(len(di))
+    di, dj = di[perm].astype(np.int32), dj[perm].astype(np.int32)
+    sym = rb.Sym.YesLower if lower else rb.Sym.No
+    b = rng.standard_normal(n)
+    sols = {}
+    for coo_boundary in (True, False):
+        sol = rb.SolverB200(coo_boundary=coo_boundary)
+        coo = rb.CooMatrix.from_triplets(n, n, di, dj, np.zeros(len(di)), sym)
+        xs = []
+        for trial in range(3):  # refactorizations with new values reuse the map
+            r2 = np.random.default_rng(100 + trial)
+            w = r2.random(len(di)) + 0.1
+            coo.values[: coo.nnz] = (np.repeat(ax, reps)[perm]) * w * (1.0 + trial)
+            sol.factorize(coo)
+            x = np.zeros(n)
+            sol.solve(x, b)
+            xs.append(x.copy())
+            a = oracle.full_scipy_matrix(n, n, di, dj, coo.values[: coo.nnz], "YesLower" if lower else "No")
+            assert np.linalg.norm(b - a @ x) / np.linalg.norm(b) <= TOL_RESIDUAL
+        sols[coo_boundary] = xs
+    for xa, xb in zip(sols[True], sols[False]):
+        assert np.array_equal(xa, xb)
+
+
+def test_coo_boundary_errors():
+    import ctypes
+    from russell_b200 import _lib
+
+    lib = _lib.load()
+    P = lambda a, t: a.ctypes.data_as(ctypes.POINTER(t))
+    i = np.array([0, 1, 0], np.int32)
+    j = np.array([0, 1, 1], np.int32)
+    v = np.array([1.0, 2.0, 3.0])
+    s = lib.solver_b200_new()
+    args = lambda ii, jj, sym: (s, 0, 0, 0, -1.0, -1, -1.0, 0, sym, 0, 2, 3, P(ii, ctypes.c_int32), P(jj, ctypes.c_int32), P(v, ctypes.c_double))
+    assert lib.solver_b200_factorize_coo(s, None, None, 0, P(v, ctypes.c_double)) == 500000  # need initialization
+    assert lib.solver_b200_initialize_coo(*args(i, j, 1)) == 704  # upper entry under Sym::YesLower
+    bad = np.array([0, 5, 0], np.int32)
+    assert lib.solver_b200_initialize_coo(*args(bad, j, 0)) == 703
+    assert lib.solver_b200_initialize_coo(*args(i, j, 0)) == 0
+    assert lib.solver_b200_initialize_coo(*args(i, j, 0)) == 700000  # already initialized
+    assert lib.solver_b200_factorize_coo(s, None, None, 0, None) == 100000
+    assert lib.solver_b200_factorize_coo(s, None, None, 0, P(v, ctypes.c_double)) == 0
+    x, b = np.zeros(2), np.array([4.0, 2.0])
+    assert lib.solver_b200_solve(s, P(x, ctypes.c_double), P(b, ctypes.c_double), 0) == 0
+    assert np.allclose(x, [1.0, 1.0], atol=1e-15)
+    lib.solver_b200_drop(s)
+    # a handle initialised through the CSR entry point has no triplet map
+    s2 = lib.solver_b200_new()
+    rp, ci = np.array([0, 2, 3], np.int32), np.array([0, 1, 1], np.int32)
+    assert lib.solver_b200_initialize(s2, 0, 0, 0, -1.0, -1, -1.0, 0, 0, 0, 2, P(rp, ctypes.c_int32), P(ci, ctypes.c_int32), P(v[[0, 2, 1]].copy(), ctypes.c_double)) == 0
+    assert lib.solver_b200_factorize_coo(s2, None, None, 0, P(v, ctypes.c_double)) == 500000
+    lib.solver_b200_drop(s2)
+
+
 def test_saddle_point_and_random_zero_diagonal():
     n, ai, aj, ax = helpers.saddle_point_triplets(40)
     coo = rb.CooMatrix.from_triplets(n, n, ai, aj, ax)

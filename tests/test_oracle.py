@@ -65,6 +65,39 @@ def test_product_converter_random_with_duplicates_bit_exact():
         assert np.array_equal(csr.row_pointers, bp2) and np.array_equal(csr.values[:n], bx2)
 
 
+def test_coo_slot_map_reproduces_the_conversion_bit_exact():
+    # the triplet -> CSR-slot map behind solver_b200_initialize_coo / k_coo_to_csr_values: summing the mapped
+    # triplets of every slot in map order must equal CsrMatrix::update_from_coo (csr_matrix.rs:431-459) bit for bit
+    import ctypes
+    from russell_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    for n, nnz in [(1, 4), (9, 60), (120, 4000), (2000, 30000)]:
+        ai = rng.integers(0, n, nnz).astype(np.int32)
+        aj = rng.integers(0, n, nnz).astype(np.int32)
+        ax = rng.standard_normal(nnz) * 10.0 ** rng.integers(-8, 8, nnz)
+        ptr_, idx, val = np.zeros(n + 1, np.int32), np.zeros(nnz, np.int32), np.zeros(nnz)
+        sp, si = np.zeros(nnz + 1, np.int32), np.zeros(nnz, np.int32)
+        P = lambda a, t: a.ctypes.data_as(ctypes.POINTER(t))
+        rc = lib.b200_coo_to_csr_map(n, n, nnz, P(ai, ctypes.c_int32), P(aj, ctypes.c_int32), P(ax, ctypes.c_double),
+                                     P(ptr_, ctypes.c_int32), P(idx, ctypes.c_int32), P(val, ctypes.c_double),
+                                     P(sp, ctypes.c_int32), P(si, ctypes.c_int32))
+        assert rc == 0
+        bp, bj, bx = oracle.coo_to_csr(n, n, ai, aj, ax)
+        m = int(ptr_[n])
+        assert np.array_equal(ptr_, bp) and np.array_equal(idx[:m], bj) and np.array_equal(val[:m], bx)
+        assert sp[m] == nnz and sorted(si.tolist()) == list(range(nnz))  # every triplet lands in exactly one slot
+        ax2 = rng.standard_normal(nnz)
+        _, _, bx2 = oracle.coo_to_csr(n, n, ai, aj, ax2)
+        for sl in range(m):
+            acc = ax2[si[sp[sl]]]
+            for t in range(sp[sl] + 1, sp[sl + 1]):
+                acc += ax2[si[t]]
+            assert acc == bx2[sl]
+            assert np.all(np.diff(si[sp[sl]:sp[sl + 1]]) > 0)  # order of appearance
+
+
 def test_converter_errors_mirror_reference():
     import russell_b200 as rb
 
