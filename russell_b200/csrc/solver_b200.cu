@@ -60,6 +60,8 @@ struct LevelLists {
     std::vector<int> solve_threads, solve_pmax; // per level: block size and largest pivot count of the small launch
     std::vector<int> big_ptr; // nlevels+1: slices of the big solve class inside d_big_items
     std::vector<int> inv_ptr; // NIC+1: fronts by pivot-count class inside d_inv_nodes
+    std::vector<int> inv_early; // NIC: per class, how many fronts (the first ones of the class) lie below level inv_split
+    int inv_split = -1;         // first level of the "narrow" top of the tree (few fronts per level); -1: no overlap
     std::vector<size_t> fused_smem; // per (level, class): dynamic shared memory of the fused launch
 };
 
@@ -73,6 +75,7 @@ struct InterfaceB200 {
     int opt_panel_width = 64, opt_nd_leaf = 96;
     int use_graph = 1;
     int schur_variant = 1; // 0 = FMA, 1 = DMMA
+    int panel_variant = 1; // 0 = k_panel (32-row tiles, barrier per column), 1 = k_panel_warp (thread per row, 128-row items)
     int use_fused = 1;     // fronts with f <= B200_FUSED_MAXF go through k_front_fused
     int fused_maxf = 48;   // fronts above this order take the multi-kernel path (measured optimum at config 2)
     int fuse_chain = 1;    // chain links receive their child's Schur complement directly (no k_assemble pass)
@@ -132,6 +135,9 @@ struct InterfaceB200 {
 
     cudaGraphExec_t g_fact = nullptr, g_sweep = nullptr;
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t side = nullptr;          // low-priority side stream: pivot-block inverses of the wide bottom of the tree
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr; //   run there, under the latency-bound chain of top-of-tree launches
+    int overlap_invert = 1;
 
     // stats
     int n_perturbed = 0;
@@ -287,8 +293,9 @@ void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::ve
                 }
             }
             if (u > 0) {
-                for (int r0 = 0; r0 < u; r0 += B200_TR) panel_items.push_back({v, r0, std::min(B200_TR, u - r0), 0});
-                for (int r0 = 0; r0 < u; r0 += B200_TR) panel_items.push_back({v, r0, std::min(B200_TR, u - r0), 1});
+                const int TR = (s->panel_variant == 1) ? B200_PW_ROWS : B200_TR;
+                for (int r0 = 0; r0 < u; r0 += TR) panel_items.push_back({v, r0, std::min(TR, u - r0), 0});
+                for (int r0 = 0; r0 < u; r0 += TR) panel_items.push_back({v, r0, std::min(TR, u - r0), 1});
                 int nt = (u + B200_TS - 1) / B200_TS;
                 const int par = P.parent[v];
                 const int fuse_into = (par >= 0 && chain_fused(par)) ? par : -1;
@@ -315,7 +322,20 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
     const LevelLists& lv = s->lv;
     const int W = s->opt_panel_width;
     int cnt = 0;
+    bool forked = false;
     for (int l = 0; l < P.nlevels; l++) {
+        if (l == lv.inv_split) { // fork: inverses of all fronts below this level, on the low-priority side stream
+            cudaEventRecord(s->ev_fork, s->stream);
+            cudaStreamWaitEvent(s->side, s->ev_fork, 0);
+            for (int c = 0; c < NIC; c++)
+                if (lv.inv_early[c] > 0) {
+                    k_invert<<<lv.inv_early[c], IC_THREADS[c], smem_invert(IC_MAXP[c]), s->side>>>(s->d_inv_nodes + lv.inv_ptr[c], s->d_nodes,
+                                                                                                    s->d_fac, s->d_dinv, IC_MAXP[c]);
+                    cnt++;
+                }
+            cudaEventRecord(s->ev_join, s->side);
+            forked = true;
+        }
         const int* fp = &lv.fact_ptr[(size_t)l * (NFC + 1)];
         for (int c = 0; c < NFC; c++) {
             int nn = fp[c + 1] - fp[c];
@@ -333,7 +353,10 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
             k_assemble<<<na, 256, 0, s->stream>>>(s->d_asm + lv.asm_ptr[l], s->d_nodes, s->d_child_idx, s->d_rel, s->d_asm_ranges, s->d_fac, s->d_cb);
             cnt++;
         }
-        if (s->diag_variant == 1)
+        if (s->diag_variant == 2)
+            k_diag_blk<<<nbig, 256, 0, s->stream>>>(s->d_fact_nodes + fp[NFC], s->d_nodes, s->d_fac, s->d_lperm, s->d_upiv, s->d_amax,
+                                                    s->pivot_eps, s->d_counters);
+        else if (s->diag_variant == 1)
             k_diag_reg<<<nbig, 512, 0, s->stream>>>(s->d_fact_nodes + fp[NFC], s->d_nodes, s->d_fac, s->d_lperm, s->d_upiv, s->d_amax,
                                                     s->pivot_eps, s->d_counters);
         else
@@ -342,7 +365,10 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
         cnt++;
         int np = lv.panel_ptr[l + 1] - lv.panel_ptr[l];
         if (np > 0) {
-            k_panel<<<np, 256, smem_panel(W), s->stream>>>(s->d_panel + lv.panel_ptr[l], s->d_nodes, s->d_fac, s->d_lperm);
+            if (s->panel_variant == 1)
+                k_panel_warp<<<np, 128, B200_PW_SMEM, s->stream>>>(s->d_panel + lv.panel_ptr[l], s->d_nodes, s->d_fac, s->d_lperm);
+            else
+                k_panel<<<np, 256, smem_panel(W), s->stream>>>(s->d_panel + lv.panel_ptr[l], s->d_nodes, s->d_fac, s->d_lperm);
             cnt++;
         }
         int nsch = lv.schur_ptr[l + 1] - lv.schur_ptr[l];
@@ -355,11 +381,13 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
         }
     }
     // pivot-block inverses of ALL fronts (solve phase only needs them): one batched launch per pivot-count class
+    if (forked) cudaStreamWaitEvent(s->stream, s->ev_join, 0); // join
     for (int c = 0; c < NIC; c++) {
-        int nn = lv.inv_ptr[c + 1] - lv.inv_ptr[c];
+        const int first = forked ? lv.inv_early[c] : 0;
+        int nn = lv.inv_ptr[c + 1] - lv.inv_ptr[c] - first;
         if (nn > 0) {
-            k_invert<<<nn, IC_THREADS[c], smem_invert(IC_MAXP[c]), s->stream>>>(s->d_inv_nodes + lv.inv_ptr[c], s->d_nodes, s->d_fac,
-                                                                                 s->d_dinv, IC_MAXP[c]);
+            k_invert<<<nn, IC_THREADS[c], smem_invert(IC_MAXP[c]), s->stream>>>(s->d_inv_nodes + lv.inv_ptr[c] + first, s->d_nodes,
+                                                                                 s->d_fac, s->d_dinv, IC_MAXP[c]);
             cnt++;
         }
     }
@@ -492,6 +520,22 @@ int32_t solver_b200_get_device(struct InterfaceB200* s) { return s ? s->device :
 
 const char* solver_b200_version(void) { return "solver_b200 0.1 (sm_100a, multifrontal LU f64)"; }
 
+static bool create_streams(InterfaceB200* s) {
+    int lo = 0, hi = 0; // numerically lower = higher priority
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, hi) != cudaSuccess) return false;
+    if (cudaStreamCreateWithPriority(&s->side, cudaStreamNonBlocking, lo) != cudaSuccess) return false;
+    if (cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) != cudaSuccess) return false;
+    if (cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming) != cudaSuccess) return false;
+    return true;
+}
+static void destroy_streams(InterfaceB200* s) {
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork), s->ev_fork = nullptr;
+    if (s->ev_join) cudaEventDestroy(s->ev_join), s->ev_join = nullptr;
+    if (s->side) cudaStreamDestroy(s->side), s->side = nullptr;
+    if (s->stream) cudaStreamDestroy(s->stream), s->stream = nullptr;
+}
+
 struct InterfaceB200* solver_b200_new(void) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
@@ -505,7 +549,8 @@ struct InterfaceB200* solver_b200_new(void) {
     const char* edev = getenv("B200_DEVICE"); // one process per GPU: the launcher may pin the device explicitly
     if (edev && atoi(edev) >= 0 && atoi(edev) < ndev) dev = atoi(edev);
     s->device = dev;
-    if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    if (cudaSetDevice(dev) != cudaSuccess || !create_streams(s)) {
+        destroy_streams(s);
         delete s;
         return nullptr;
     }
@@ -517,6 +562,8 @@ struct InterfaceB200* solver_b200_new(void) {
     const char* e;
     if ((e = getenv("B200_NO_GRAPH")) && atoi(e)) s->use_graph = 0;
     if ((e = getenv("B200_SCHUR_VARIANT"))) s->schur_variant = atoi(e);
+    if ((e = getenv("B200_PANEL_VARIANT"))) s->panel_variant = atoi(e);
+    if ((e = getenv("B200_OVERLAP_INVERT"))) s->overlap_invert = atoi(e);
     if ((e = getenv("B200_USE_FUSED"))) s->use_fused = atoi(e);
     if ((e = getenv("B200_USE_TOP"))) s->use_top = atoi(e);
     if ((e = getenv("B200_DIAG_VARIANT"))) s->diag_variant = atoi(e);
@@ -534,7 +581,7 @@ void solver_b200_drop(struct InterfaceB200* s) {
     release_device(s);
     for (int i = 0; i < 8; i++)
         if (s->ev[i]) cudaEventDestroy(s->ev[i]);
-    if (s->stream) cudaStreamDestroy(s->stream);
+    destroy_streams(s);
     delete s;
 }
 
@@ -548,6 +595,8 @@ int32_t solver_b200_set_option(struct InterfaceB200* s, const char* key, double 
     else if (k == "nd_leaf") s->opt_nd_leaf = std::max(4, (int)value);
     else if (k == "use_graph") s->use_graph = value != 0.0;
     else if (k == "schur_variant") s->schur_variant = (int)value;
+    else if (k == "panel_variant") s->panel_variant = (int)value;
+    else if (k == "overlap_invert") s->overlap_invert = (int)value;
     else if (k == "use_fused") s->use_fused = value != 0.0;
     else if (k == "use_top") s->use_top = value != 0.0;
     else if (k == "diag_variant") s->diag_variant = (int)value;
@@ -563,10 +612,9 @@ int32_t solver_b200_set_option(struct InterfaceB200* s, const char* key, double 
             cudaSetDevice(s->device);
             for (int i = 0; i < 8; i++)
                 if (s->ev[i]) cudaEventDestroy(s->ev[i]), s->ev[i] = nullptr;
-            if (s->stream) cudaStreamDestroy(s->stream), s->stream = nullptr;
+            destroy_streams(s);
             s->device = dev;
-            if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess)
-                return B200_ERROR_NOT_AVAILABLE;
+            if (cudaSetDevice(dev) != cudaSuccess || !create_streams(s)) return B200_ERROR_NOT_AVAILABLE;
             for (int i = 0; i < 8; i++)
                 if (cudaEventCreate(&s->ev[i]) != cudaSuccess) return B200_ERROR_NOT_AVAILABLE;
         }
@@ -712,13 +760,31 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     UP(d_fact_nodes, fact_nodes);
     UP(d_solve_nodes, solve_nodes);
     {
+        // the top of the tree is a chain of narrow levels (few fronts each, latency bound): the inverses of everything
+        // below it run on a side stream underneath that chain.  inv_split = first level from which no level has
+        // more than 128 multi-kernel fronts.
+        s->lv.inv_split = -1;
+        if (s->overlap_invert && P.nlevels > 8) {
+            int l = P.nlevels;
+            while (l > 0) {
+                const int* fp = &s->lv.fact_ptr[(size_t)(l - 1) * (NFC + 1)];
+                if (fp[NFC + 1] - fp[0] > 128) break;
+                l--;
+            }
+            if (l > 0 && P.nlevels - l >= 8) s->lv.inv_split = l;
+        }
         std::vector<int> inv_nodes;
         s->lv.inv_ptr.assign(NIC + 1, 0);
+        s->lv.inv_early.assign(NIC, 0);
         for (int c = 0; c < NIC; c++) {
-            for (int v = 0; v < P.nnodes; v++) {
-                int cls = 0;
-                while (cls < NIC - 1 && P.p[v] > IC_MAXP[cls]) cls++;
-                if (cls == c) inv_nodes.push_back(v);
+            for (int pass = 0; pass < 2; pass++) { // pass 0: fronts below the split (early), pass 1: the rest
+                for (int v = 0; v < P.nnodes; v++) {
+                    int cls = 0;
+                    while (cls < NIC - 1 && P.p[v] > IC_MAXP[cls]) cls++;
+                    const bool early = s->lv.inv_split >= 0 && P.level[v] < s->lv.inv_split;
+                    if (cls == c && early == (pass == 0)) inv_nodes.push_back(v);
+                }
+                if (pass == 0) s->lv.inv_early[c] = (int)inv_nodes.size() - s->lv.inv_ptr[c];
             }
             s->lv.inv_ptr[c + 1] = (int)inv_nodes.size();
         }
@@ -792,6 +858,7 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     CUDA_TRY(cudaFuncSetAttribute(k_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_invert(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_front_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused(B200_FUSED_MAXF, B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_panel(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
+    CUDA_TRY(cudaFuncSetAttribute(k_panel_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_PW_SMEM), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_schur_fma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_schur_fma(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_schur_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_schur_dmma()), B200_ERROR_NOT_AVAILABLE);
     (void)W;

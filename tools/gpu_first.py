@@ -24,7 +24,7 @@ def compare_factors(coo, opts, label):
         st = sol.device_stats()
         lib = _lib.load()
         nfac = int(st["fac_bytes"] / 8)
-        csr = sol.csr
+        csr = rb.CsrMatrix.from_coo(coo)
         sym_lower = coo.symmetric == rb.Sym.YesLower
         h = oracle.MfHandle(csr.nrow, csr.pointers, csr.indices, csr.values[:csr.nnz], sym_lower=sym_lower, ordering=0, matching=2,
                             panel_width=int(opts.get("panel_width", 0)), nd_leaf=int(opts.get("nd_leaf", 0)))
