@@ -53,6 +53,7 @@ static const int SC_MAXP[NSC] = {32, B200_MAXP, B200_MAXP};
 struct LevelLists {
     // offsets (nlevels+1) into the concatenated device item arrays (big fronts only)
     std::vector<int> asm_ptr, panel_ptr, schur_ptr;
+    std::vector<int> schur_crit; // per level: the first schur_crit[l] Schur tiles feed the NEXT level's pivot block and panels
     // fact_ptr[l*(NFC+1)+c .. +1]: nodes of level l and factorization class c inside d_fact_nodes (class NFC = big)
     std::vector<int> fact_ptr;
     // solve_ptr[l*NSC+c .. +1] inside d_solve_nodes
@@ -137,7 +138,10 @@ struct InterfaceB200 {
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaStream_t side = nullptr;          // low-priority side stream: pivot-block inverses of the wide bottom of the tree
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr; //   run there, under the latency-bound chain of top-of-tree launches
-    int overlap_invert = 1;
+    cudaEvent_t ev_la = nullptr, ev_rest = nullptr;   // look-ahead fork / join
+    int overlap_invert = 0;
+    int invert_variant = 1; // 0 = rank-1 sweeps with a barrier per step (k_invert), 1 = one thread per column (k_invert_col)
+    int lookahead = 1; // Schur tiles that do not feed the next level's pivot block / panels run on the side stream
 
     // stats
     int n_perturbed = 0;
@@ -204,6 +208,7 @@ void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::ve
     lv.asm_ptr.assign(P.nlevels + 1, 0);
     lv.panel_ptr.assign(P.nlevels + 1, 0);
     lv.schur_ptr.assign(P.nlevels + 1, 0);
+    lv.schur_crit.assign(P.nlevels, 0);
     lv.fact_ptr.assign((size_t)P.nlevels * (NFC + 1) + 1, 0);
     lv.solve_ptr.assign((size_t)P.nlevels * NSC + 1, 0);
     lv.solve_threads.assign(P.nlevels, 32);
@@ -293,7 +298,7 @@ void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::ve
                 }
             }
             if (u > 0) {
-                const int TR = (s->panel_variant == 1) ? B200_PW_ROWS : B200_TR;
+                const int TR = (s->panel_variant >= 1) ? B200_PW_ROWS : B200_TR;
                 for (int r0 = 0; r0 < u; r0 += TR) panel_items.push_back({v, r0, std::min(TR, u - r0), 0});
                 for (int r0 = 0; r0 < u; r0 += TR) panel_items.push_back({v, r0, std::min(TR, u - r0), 1});
                 int nt = (u + B200_TS - 1) / B200_TS;
@@ -306,11 +311,16 @@ void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::ve
         lv.asm_ptr[l + 1] = (int)asm_items.size();
         lv.panel_ptr[l + 1] = (int)panel_items.size();
         lv.schur_ptr[l + 1] = (int)schur_items.size();
+        // look-ahead order: tiles of chain links in tile row 0 / tile column 0 (they become the parent's pivot block and
+        // panels) first; everything else (the parent's contribution block, tiles of non-chain fronts) afterwards
+        auto first = schur_items.begin() + lv.schur_ptr[l];
+        auto mid = std::stable_partition(first, schur_items.end(), [](const SchurItem& t) { return t.parent >= 0 && (t.ti == 0 || t.tj == 0); });
+        lv.schur_crit[l] = (int)(mid - first);
     }
 }
 
 size_t smem_diag(int) { return (size_t)(B200_MAXP * (B200_MAXP + 1)) * sizeof(double) + B200_MAXP * sizeof(int); }
-size_t smem_invert(int pmax) { return (size_t)(pmax * (pmax | 1) + pmax * pmax) * sizeof(double); }
+size_t smem_invert(int pmax) { return (size_t)(2 * pmax * (pmax | 1)) * sizeof(double); }
 size_t smem_panel(int W) { return (size_t)(W * W + B200_TR * W) * sizeof(double) + W * sizeof(int); }
 size_t smem_schur_fma(int W) { return (size_t)2 * W * B200_TS * sizeof(double); }
 size_t smem_schur_dmma() { return (size_t)2 * B200_MAXP * (B200_TS + 8) * sizeof(double); }
@@ -322,21 +332,30 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
     const LevelLists& lv = s->lv;
     const int W = s->opt_panel_width;
     int cnt = 0;
-    bool forked = false;
+    bool forked = false, pending_rest = false;
     for (int l = 0; l < P.nlevels; l++) {
         if (l == lv.inv_split) { // fork: inverses of all fronts below this level, on the low-priority side stream
             cudaEventRecord(s->ev_fork, s->stream);
             cudaStreamWaitEvent(s->side, s->ev_fork, 0);
             for (int c = 0; c < NIC; c++)
                 if (lv.inv_early[c] > 0) {
-                    k_invert<<<lv.inv_early[c], IC_THREADS[c], smem_invert(IC_MAXP[c]), s->side>>>(s->d_inv_nodes + lv.inv_ptr[c], s->d_nodes,
-                                                                                                    s->d_fac, s->d_dinv, IC_MAXP[c]);
+                    // a few CTAs per SM only: the chain kernels of the main stream must always find free slots
+                    if (s->invert_variant == 1)
+                        k_invert_col<<<std::min(lv.inv_early[c], 148 * 4), 2 * IC_MAXP[c], smem_invert(IC_MAXP[c]), s->side>>>(
+                            s->d_inv_nodes + lv.inv_ptr[c], s->d_nodes, s->d_fac, s->d_dinv, IC_MAXP[c], lv.inv_early[c]);
+                    else
+                        k_invert<<<std::min(lv.inv_early[c], 148 * 4), IC_THREADS[c], smem_invert(IC_MAXP[c]), s->side>>>(
+                            s->d_inv_nodes + lv.inv_ptr[c], s->d_nodes, s->d_fac, s->d_dinv, IC_MAXP[c], lv.inv_early[c]);
                     cnt++;
                 }
             cudaEventRecord(s->ev_join, s->side);
             forked = true;
         }
         const int* fp = &lv.fact_ptr[(size_t)l * (NFC + 1)];
+        // fused fronts and the assembly kernel read their children's contribution blocks: wait for the side launch.
+        // A level made of chain links only goes straight to its pivot blocks (their inputs came from the critical tiles).
+        if (pending_rest && (fp[NFC] - fp[0] > 0 || lv.asm_ptr[l + 1] - lv.asm_ptr[l] > 0))
+            cudaStreamWaitEvent(s->stream, s->ev_rest, 0), pending_rest = false;
         for (int c = 0; c < NFC; c++) {
             int nn = fp[c + 1] - fp[c];
             if (nn > 0) {
@@ -353,7 +372,13 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
             k_assemble<<<na, 256, 0, s->stream>>>(s->d_asm + lv.asm_ptr[l], s->d_nodes, s->d_child_idx, s->d_rel, s->d_asm_ranges, s->d_fac, s->d_cb);
             cnt++;
         }
-        if (s->diag_variant == 2)
+        if (s->diag_variant == 4)
+            k_diag_w8<<<nbig, 256, 0, s->stream>>>(s->d_fact_nodes + fp[NFC], s->d_nodes, s->d_fac, s->d_lperm, s->d_upiv, s->d_amax,
+                                                   s->pivot_eps, s->d_counters);
+        else if (s->diag_variant == 3)
+            k_diag_reg2<<<nbig, 512, 0, s->stream>>>(s->d_fact_nodes + fp[NFC], s->d_nodes, s->d_fac, s->d_lperm, s->d_upiv, s->d_amax,
+                                                     s->pivot_eps, s->d_counters);
+        else if (s->diag_variant == 2)
             k_diag_blk<<<nbig, 256, 0, s->stream>>>(s->d_fact_nodes + fp[NFC], s->d_nodes, s->d_fac, s->d_lperm, s->d_upiv, s->d_amax,
                                                     s->pivot_eps, s->d_counters);
         else if (s->diag_variant == 1)
@@ -365,7 +390,9 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
         cnt++;
         int np = lv.panel_ptr[l + 1] - lv.panel_ptr[l];
         if (np > 0) {
-            if (s->panel_variant == 1)
+            if (s->panel_variant == 2)
+                k_panel_mma<<<np, 128, B200_PM_SMEM, s->stream>>>(s->d_panel + lv.panel_ptr[l], s->d_nodes, s->d_fac, s->d_lperm);
+            else if (s->panel_variant == 1)
                 k_panel_warp<<<np, 128, B200_PW_SMEM, s->stream>>>(s->d_panel + lv.panel_ptr[l], s->d_nodes, s->d_fac, s->d_lperm);
             else
                 k_panel<<<np, 256, smem_panel(W), s->stream>>>(s->d_panel + lv.panel_ptr[l], s->d_nodes, s->d_fac, s->d_lperm);
@@ -373,21 +400,42 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
         }
         int nsch = lv.schur_ptr[l + 1] - lv.schur_ptr[l];
         if (nsch > 0) {
-            if (s->schur_variant == 1)
-                k_schur_dmma<<<nsch, 256, smem_schur_dmma(), s->stream>>>(s->d_schur + lv.schur_ptr[l], s->d_nodes, s->d_fac, s->d_cb);
-            else
+            // every Schur tile of this level reads contribution blocks completed by the previous level's side launch
+            if (pending_rest) cudaStreamWaitEvent(s->stream, s->ev_rest, 0), pending_rest = false;
+            const int ncrit = lv.schur_crit[l];
+            const bool la = s->lookahead && s->schur_variant == 1 && ncrit > 0 && ncrit < nsch;
+            if (s->schur_variant == 1) {
+                if (la) { // fork before the critical tiles: the side launch only needs this level's panels
+                    cudaEventRecord(s->ev_la, s->stream);
+                    cudaStreamWaitEvent(s->side, s->ev_la, 0);
+                }
+                k_schur_dmma<<<la ? ncrit : nsch, 256, smem_schur_dmma(), s->stream>>>(s->d_schur + lv.schur_ptr[l], s->d_nodes, s->d_fac, s->d_cb);
+                if (la) {
+                    // lookahead == 2: the side launch asks for more shared memory than it needs, so only ONE of its CTAs fits
+                    // on an SM and the next level's pivot-block / panel CTAs always find registers and a slot
+                    k_schur_dmma<<<nsch - ncrit, 256, s->lookahead == 2 ? (size_t)120 * 1024 : smem_schur_dmma(), s->side>>>(
+                        s->d_schur + lv.schur_ptr[l] + ncrit, s->d_nodes, s->d_fac, s->d_cb);
+                    cudaEventRecord(s->ev_rest, s->side);
+                    pending_rest = true;
+                    cnt++;
+                }
+            } else
                 k_schur_fma<<<nsch, 256, smem_schur_fma(W), s->stream>>>(s->d_schur + lv.schur_ptr[l], s->d_nodes, s->d_fac, s->d_cb);
             cnt++;
         }
     }
-    // pivot-block inverses of ALL fronts (solve phase only needs them): one batched launch per pivot-count class
+    if (pending_rest) cudaStreamWaitEvent(s->stream, s->ev_rest, 0), pending_rest = false;
     if (forked) cudaStreamWaitEvent(s->stream, s->ev_join, 0); // join
     for (int c = 0; c < NIC; c++) {
         const int first = forked ? lv.inv_early[c] : 0;
         int nn = lv.inv_ptr[c + 1] - lv.inv_ptr[c] - first;
         if (nn > 0) {
-            k_invert<<<nn, IC_THREADS[c], smem_invert(IC_MAXP[c]), s->stream>>>(s->d_inv_nodes + lv.inv_ptr[c] + first, s->d_nodes,
-                                                                                 s->d_fac, s->d_dinv, IC_MAXP[c]);
+            if (s->invert_variant == 1)
+                k_invert_col<<<nn, 2 * IC_MAXP[c], smem_invert(IC_MAXP[c]), s->stream>>>(s->d_inv_nodes + lv.inv_ptr[c] + first, s->d_nodes,
+                                                                                          s->d_fac, s->d_dinv, IC_MAXP[c], nn);
+            else
+                k_invert<<<nn, IC_THREADS[c], smem_invert(IC_MAXP[c]), s->stream>>>(s->d_inv_nodes + lv.inv_ptr[c] + first, s->d_nodes,
+                                                                                     s->d_fac, s->d_dinv, IC_MAXP[c], nn);
             cnt++;
         }
     }
@@ -527,11 +575,15 @@ static bool create_streams(InterfaceB200* s) {
     if (cudaStreamCreateWithPriority(&s->side, cudaStreamNonBlocking, lo) != cudaSuccess) return false;
     if (cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) != cudaSuccess) return false;
     if (cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming) != cudaSuccess) return false;
+    if (cudaEventCreateWithFlags(&s->ev_la, cudaEventDisableTiming) != cudaSuccess) return false;
+    if (cudaEventCreateWithFlags(&s->ev_rest, cudaEventDisableTiming) != cudaSuccess) return false;
     return true;
 }
 static void destroy_streams(InterfaceB200* s) {
     if (s->ev_fork) cudaEventDestroy(s->ev_fork), s->ev_fork = nullptr;
     if (s->ev_join) cudaEventDestroy(s->ev_join), s->ev_join = nullptr;
+    if (s->ev_la) cudaEventDestroy(s->ev_la), s->ev_la = nullptr;
+    if (s->ev_rest) cudaEventDestroy(s->ev_rest), s->ev_rest = nullptr;
     if (s->side) cudaStreamDestroy(s->side), s->side = nullptr;
     if (s->stream) cudaStreamDestroy(s->stream), s->stream = nullptr;
 }
@@ -564,6 +616,8 @@ struct InterfaceB200* solver_b200_new(void) {
     if ((e = getenv("B200_SCHUR_VARIANT"))) s->schur_variant = atoi(e);
     if ((e = getenv("B200_PANEL_VARIANT"))) s->panel_variant = atoi(e);
     if ((e = getenv("B200_OVERLAP_INVERT"))) s->overlap_invert = atoi(e);
+    if ((e = getenv("B200_LOOKAHEAD"))) s->lookahead = atoi(e);
+    if ((e = getenv("B200_INVERT_VARIANT"))) s->invert_variant = atoi(e);
     if ((e = getenv("B200_USE_FUSED"))) s->use_fused = atoi(e);
     if ((e = getenv("B200_USE_TOP"))) s->use_top = atoi(e);
     if ((e = getenv("B200_DIAG_VARIANT"))) s->diag_variant = atoi(e);
@@ -597,6 +651,8 @@ int32_t solver_b200_set_option(struct InterfaceB200* s, const char* key, double 
     else if (k == "schur_variant") s->schur_variant = (int)value;
     else if (k == "panel_variant") s->panel_variant = (int)value;
     else if (k == "overlap_invert") s->overlap_invert = (int)value;
+    else if (k == "lookahead") s->lookahead = (int)value;
+    else if (k == "invert_variant") s->invert_variant = (int)value;
     else if (k == "use_fused") s->use_fused = value != 0.0;
     else if (k == "use_top") s->use_top = value != 0.0;
     else if (k == "diag_variant") s->diag_variant = (int)value;
@@ -856,11 +912,13 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     const int W = s->opt_panel_width;
     CUDA_TRY(cudaFuncSetAttribute(k_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_diag(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_invert(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
+    CUDA_TRY(cudaFuncSetAttribute(k_invert_col, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_invert(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_front_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused(B200_FUSED_MAXF, B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_panel(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_panel_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_PW_SMEM), B200_ERROR_NOT_AVAILABLE);
+    CUDA_TRY(cudaFuncSetAttribute(k_panel_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_PM_SMEM), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_schur_fma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_schur_fma(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
-    CUDA_TRY(cudaFuncSetAttribute(k_schur_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_schur_dmma()), B200_ERROR_NOT_AVAILABLE);
+    CUDA_TRY(cudaFuncSetAttribute(k_schur_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024), B200_ERROR_NOT_AVAILABLE);
     (void)W;
     if (s->n_top_items > 0) {
         CUDA_TRY(cudaFuncSetAttribute(k_fwd_top, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_TOP_SMEM), B200_ERROR_NOT_AVAILABLE);

@@ -261,7 +261,12 @@ def test_factor_panels_match_host_walk_lower_and_saddle():
                                   {"diag_variant": 2, "use_fused": 0}, {"diag_variant": 2, "panel_width": 20, "use_fused": 0},
                                   {"diag_variant": 2, "panel_width": 37, "use_fused": 0}, {"panel_variant": 1},
                                   {"panel_variant": 1, "use_fused": 0, "panel_width": 37}, {"panel_variant": 1, "use_fused": 0, "panel_width": 8},
-                                  {"overlap_invert": 0}, {"overlap_invert": 1, "use_graph": 0}])
+                                  {"overlap_invert": 0}, {"overlap_invert": 1, "use_graph": 0}, {"diag_variant": 3}, {"panel_variant": 2}, {"panel_variant": 0},
+                                  {"lookahead": 0}, {"lookahead": 1, "use_graph": 0}, {"lookahead": 2}, {"diag_variant": 4},
+                                  {"diag_variant": 4, "use_fused": 0, "panel_width": 37}, {"diag_variant": 4, "use_fused": 0, "panel_width": 5}, {"lookahead": 1, "overlap_invert": 1}, {"invert_variant": 0},
+                                  {"invert_variant": 1, "use_fused": 0, "panel_width": 37}, {"invert_variant": 1, "use_fused": 0, "panel_width": 5},
+                                  {"panel_variant": 2, "use_fused": 0, "panel_width": 37}, {"panel_variant": 2, "use_fused": 0, "panel_width": 5},
+                                  {"diag_variant": 3, "use_fused": 0, "panel_width": 37}, {"diag_variant": 3, "use_fused": 0, "panel_width": 5}])
 def test_kernel_variants_match_host_walk(opts):
     # every alternative code path (shared-memory vs register-resident pivot-block LU, fused vs multi-kernel fronts,
     # persistent vs per-level sweeps) against the scalar walk, on a grid with fronts above the fused limit
@@ -303,6 +308,12 @@ def test_blocked_pivot_block_kernel_is_bit_identical_to_the_rank1_kernel():
         f2, p2 = _raw_factors(coo, dict(extra, diag_variant=2))
         assert np.array_equal(p1, p2)
         assert np.array_equal(f1, f2)
+        f5, p5 = _raw_factors(coo, dict(extra, diag_variant=3))
+        assert np.array_equal(p1, p5)
+        assert np.array_equal(f1, f5)
+        f6, p6 = _raw_factors(coo, dict(extra, diag_variant=4))
+        assert np.array_equal(p1, p6)
+        assert np.array_equal(f1, f6)
         # thread-per-row triangular panel solves: same operation order as the tile kernel
         f3, p3 = _raw_factors(coo, dict(extra, diag_variant=1, panel_variant=0))
         f4, p4 = _raw_factors(coo, dict(extra, diag_variant=1, panel_variant=1))
