@@ -80,7 +80,7 @@ struct InterfaceB200 {
     int use_fused = 1;     // fronts with f <= B200_FUSED_MAXF go through k_front_fused
     int fused_maxf = 48;   // fronts above this order take the multi-kernel path (measured optimum at config 2)
     int fuse_chain = 1;    // chain links receive their child's Schur complement directly (no k_assemble pass)
-    int diag_variant = 1;  // 0 = shared-memory LU (k_diag), 1 = register-resident LU with implicit pivoting (k_diag_reg)
+    int diag_variant = 4;  // 0 = shared-memory LU (k_diag), 1 = register-resident LU with implicit pivoting (k_diag_reg)
     int nrefine = 2;
     double ir_tol = 1e-11;
     double pivot_eps = 1e-13;
@@ -140,8 +140,11 @@ struct InterfaceB200 {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr; //   run there, under the latency-bound chain of top-of-tree launches
     cudaEvent_t ev_la = nullptr, ev_rest = nullptr;   // look-ahead fork / join
     int overlap_invert = 0;
+    int fused_variant = 2;  // 0 = shared-memory LU (k_front_fused), 1 = register-resident (k_front_fused_w8) for f <= 64,
+                            // 2 = register-resident only for launches of at most fused_w8_max fronts (measured crossover)
+    int fused_w8_max = 2000;
     int invert_variant = 1; // 0 = rank-1 sweeps with a barrier per step (k_invert), 1 = one thread per column (k_invert_col)
-    int lookahead = 1; // Schur tiles that do not feed the next level's pivot block / panels run on the side stream
+    int lookahead = 0; // Schur tiles that do not feed the next level's pivot block / panels run on the side stream
 
     // stats
     int n_perturbed = 0;
@@ -359,9 +362,16 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
         for (int c = 0; c < NFC; c++) {
             int nn = fp[c + 1] - fp[c];
             if (nn > 0) {
-                k_front_fused<<<nn, FC_THREADS[c], lv.fused_smem[(size_t)l * NFC + c], s->stream>>>(
-                    s->d_fact_nodes + fp[c], s->d_nodes, s->d_child_idx, s->d_rel, s->d_fac, s->d_cb, s->d_lperm,
-                    s->d_upiv, s->d_amax, s->pivot_eps, s->d_counters);
+                // register-resident LU (one warp per 8 front columns): wins when the launch is latency bound (few fronts),
+                // loses to the leaner shared-memory kernel when tens of thousands of fronts compete for thread slots
+                if (FC_MAXF[c] <= 64 && (s->fused_variant == 1 || (s->fused_variant == 2 && nn <= s->fused_w8_max)))
+                    k_front_fused_w8<<<nn, 32 * ((FC_MAXF[c] + 7) / 8), lv.fused_smem[(size_t)l * NFC + c], s->stream>>>(
+                        s->d_fact_nodes + fp[c], s->d_nodes, s->d_child_idx, s->d_rel, s->d_fac, s->d_cb, s->d_lperm,
+                        s->d_upiv, s->d_amax, s->pivot_eps, s->d_counters);
+                else
+                    k_front_fused<<<nn, FC_THREADS[c], lv.fused_smem[(size_t)l * NFC + c], s->stream>>>(
+                        s->d_fact_nodes + fp[c], s->d_nodes, s->d_child_idx, s->d_rel, s->d_fac, s->d_cb, s->d_lperm,
+                        s->d_upiv, s->d_amax, s->pivot_eps, s->d_counters);
                 cnt++;
             }
         }
@@ -618,6 +628,7 @@ struct InterfaceB200* solver_b200_new(void) {
     if ((e = getenv("B200_OVERLAP_INVERT"))) s->overlap_invert = atoi(e);
     if ((e = getenv("B200_LOOKAHEAD"))) s->lookahead = atoi(e);
     if ((e = getenv("B200_INVERT_VARIANT"))) s->invert_variant = atoi(e);
+    if ((e = getenv("B200_FUSED_VARIANT"))) s->fused_variant = atoi(e);
     if ((e = getenv("B200_USE_FUSED"))) s->use_fused = atoi(e);
     if ((e = getenv("B200_USE_TOP"))) s->use_top = atoi(e);
     if ((e = getenv("B200_DIAG_VARIANT"))) s->diag_variant = atoi(e);
@@ -653,6 +664,8 @@ int32_t solver_b200_set_option(struct InterfaceB200* s, const char* key, double 
     else if (k == "overlap_invert") s->overlap_invert = (int)value;
     else if (k == "lookahead") s->lookahead = (int)value;
     else if (k == "invert_variant") s->invert_variant = (int)value;
+    else if (k == "fused_variant") s->fused_variant = (int)value;
+    else if (k == "fused_w8_max") s->fused_w8_max = (int)value;
     else if (k == "use_fused") s->use_fused = value != 0.0;
     else if (k == "use_top") s->use_top = value != 0.0;
     else if (k == "diag_variant") s->diag_variant = (int)value;
@@ -914,6 +927,7 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     CUDA_TRY(cudaFuncSetAttribute(k_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_invert(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_invert_col, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_invert(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_front_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused(B200_FUSED_MAXF, B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
+    CUDA_TRY(cudaFuncSetAttribute(k_front_fused_w8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused(64, B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_panel(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_panel_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_PW_SMEM), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_panel_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_PM_SMEM), B200_ERROR_NOT_AVAILABLE);

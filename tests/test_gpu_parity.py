@@ -262,7 +262,8 @@ def test_factor_panels_match_host_walk_lower_and_saddle():
                                   {"diag_variant": 2, "panel_width": 37, "use_fused": 0}, {"panel_variant": 1},
                                   {"panel_variant": 1, "use_fused": 0, "panel_width": 37}, {"panel_variant": 1, "use_fused": 0, "panel_width": 8},
                                   {"overlap_invert": 0}, {"overlap_invert": 1, "use_graph": 0}, {"diag_variant": 3}, {"panel_variant": 2}, {"panel_variant": 0},
-                                  {"lookahead": 0}, {"lookahead": 1, "use_graph": 0}, {"lookahead": 2}, {"diag_variant": 4},
+                                  {"lookahead": 0}, {"lookahead": 1, "use_graph": 0}, {"lookahead": 2}, {"diag_variant": 4}, {"fused_variant": 0},
+                                  {"fused_variant": 1, "fused_maxf": 64}, {"fused_variant": 1, "fused_maxf": 20, "panel_width": 13},
                                   {"diag_variant": 4, "use_fused": 0, "panel_width": 37}, {"diag_variant": 4, "use_fused": 0, "panel_width": 5}, {"lookahead": 1, "overlap_invert": 1}, {"invert_variant": 0},
                                   {"invert_variant": 1, "use_fused": 0, "panel_width": 37}, {"invert_variant": 1, "use_fused": 0, "panel_width": 5},
                                   {"panel_variant": 2, "use_fused": 0, "panel_width": 37}, {"panel_variant": 2, "use_fused": 0, "panel_width": 5},
@@ -314,6 +315,12 @@ def test_blocked_pivot_block_kernel_is_bit_identical_to_the_rank1_kernel():
         f6, p6 = _raw_factors(coo, dict(extra, diag_variant=4))
         assert np.array_equal(p1, p6)
         assert np.array_equal(f1, f6)
+    # register-resident fused fronts against the shared-memory ones
+    for extra in ({}, {"fused_maxf": 64}, {"fused_maxf": 30, "panel_width": 11}):
+        f7, p7 = _raw_factors(coo, dict(extra, fused_variant=0))
+        f8, p8 = _raw_factors(coo, dict(extra, fused_variant=1))
+        assert np.array_equal(p7, p8)
+        assert np.array_equal(f7, f8)
         # thread-per-row triangular panel solves: same operation order as the tile kernel
         f3, p3 = _raw_factors(coo, dict(extra, diag_variant=1, panel_variant=0))
         f4, p4 = _raw_factors(coo, dict(extra, diag_variant=1, panel_variant=1))
