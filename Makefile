@@ -6,7 +6,7 @@ NVFLAGS = -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-unused-fu
 CXXFLAGS = -O2 -std=c++17 -fPIC -Wall
 CSRC = russell_b200/csrc
 LIB = russell_b200/lib/libsolver_b200.so
-OBJ = build/solver_b200.o build/symbolic.o build/ordering.o build/matching.o build/host_formats.o
+OBJ = build/solver_b200.o build/complex_b200.o build/symbolic.o build/ordering.o build/matching.o build/host_formats.o
 
 all: $(LIB) oracle
 
@@ -17,6 +17,10 @@ $(LIB): $(OBJ)
 build/solver_b200.o: $(CSRC)/solver_b200.cu $(CSRC)/kernels.cuh $(CSRC)/plan.hpp include/solver_b200.h
 	mkdir -p build
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> build/ptxas_solver_b200.log || (cat build/ptxas_solver_b200.log; false)
+
+build/complex_b200.o: $(CSRC)/complex_b200.cu include/solver_b200.h
+	mkdir -p build
+	$(NVCC) $(NVFLAGS) -c $< -o $@
 
 build/%.o: $(CSRC)/%.cpp $(CSRC)/plan.hpp
 	mkdir -p build

@@ -152,6 +152,37 @@ int32_t solver_b200_debug_copy_factors(struct InterfaceB200 *solver, double *fac
 void *solver_b200_get_stream(struct InterfaceB200 *solver);
 int32_t solver_b200_get_device(struct InterfaceB200 *solver);
 
+/* ---- Complex64 twin ---------------------------------------------------------------------
+ * Replaces the reference's complex cuDSS shim, same shapes:
+ *   russell_sparse/src/complex_solver_cudss.rs:32-64          (Rust `extern "C"` block)
+ *   russell_sparse/c_code/interface_complex_cudss.cu:60-567   (complex_solver_cudss_{new,drop,initialize,factorize,solve})
+ * `values`, `x`, `rhs` point to Complex64 data = interleaved (re, im) f64 pairs (russell_lab::Complex64 is
+ * num_complex::Complex<f64>, #[repr(C)]): 2*nnz / 2*ndim doubles.  CSR contract as above (sorted columns, duplicates
+ * summed, lower triangle only when general_symmetric=1: complex SYMMETRIC, not Hermitian, like the reference).
+ * Implementation: equivalent real system of order 2n in interleaved unknowns (russell_b200/csrc/complex_b200.cu). */
+struct InterfaceComplexB200;
+struct InterfaceComplexB200 *complex_solver_b200_new(void);
+void complex_solver_b200_drop(struct InterfaceComplexB200 *solver);
+int32_t complex_solver_b200_initialize(struct InterfaceComplexB200 *solver,
+                                       int32_t ordering, int32_t matching, int32_t pivoting,
+                                       double pivot_epsilon, int32_t refinement_nstep, double hybrid_memory_factor,
+                                       int32_t verbose, int32_t general_symmetric, int32_t positive_definite,
+                                       int32_t ndim, const int32_t *row_pointers, const int32_t *col_indices,
+                                       const double *values /* Complex64[nnz] */);
+int32_t complex_solver_b200_factorize(struct InterfaceComplexB200 *solver, int32_t *effective_matching,
+                                      int32_t *effective_pivoting, int32_t verbose, const double *values /* Complex64[nnz] */);
+int32_t complex_solver_b200_solve(struct InterfaceComplexB200 *solver, double *x /* Complex64[ndim] out */,
+                                  const double *rhs /* Complex64[ndim] */, int32_t verbose);
+/* extensions, as for the real solver: device-resident variants, A x and residual through the SpMV kernel, stats and
+ * options of the underlying order-2n real handle */
+int32_t complex_solver_b200_factorize_device(struct InterfaceComplexB200 *solver, const double *d_values);
+int32_t complex_solver_b200_solve_device(struct InterfaceComplexB200 *solver, double *d_x, const double *d_rhs);
+int32_t complex_solver_b200_spmv(struct InterfaceComplexB200 *solver, double *y, const double *x);
+int32_t complex_solver_b200_residual(struct InterfaceComplexB200 *solver, const double *x, const double *rhs, double *rel_residual);
+int32_t complex_solver_b200_get_stats(struct InterfaceComplexB200 *solver, double *out, int32_t n_out);
+int32_t complex_solver_b200_set_option(struct InterfaceComplexB200 *solver, const char *key, double value);
+struct InterfaceB200 *complex_solver_b200_real_handle(struct InterfaceComplexB200 *solver);
+
 /* library identification string (static storage) */
 const char *solver_b200_version(void);
 

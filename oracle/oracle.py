@@ -55,6 +55,10 @@ def fmt():
         lib.oracle_csr_matvec.argtypes = [ctypes.c_int32, _i32p, _i32p, _f64p, ctypes.c_int32, ctypes.c_double, _f64p, _f64p]
         lib.oracle_coo_matvec.argtypes = [ctypes.c_int32, ctypes.c_int32, _i32p, _i32p, _f64p, ctypes.c_int32, ctypes.c_double, _f64p, _f64p]
         lib.oracle_verify.argtypes = [ctypes.c_int32, ctypes.c_int32, _i32p, _i32p, _f64p, ctypes.c_int32, _f64p, _f64p, _f64p]
+        lib.oracle_complex_coo_to_csr.argtypes = [ctypes.c_int32] * 3 + [_i32p, _i32p, _f64p, _i32p, _i32p, _f64p]
+        lib.oracle_complex_coo_to_csr.restype = ctypes.c_int32
+        lib.oracle_complex_coo_matvec.argtypes = [ctypes.c_int32, ctypes.c_int32, _i32p, _i32p, _f64p, ctypes.c_int32, _f64p, _f64p]
+        lib.oracle_complex_verify.argtypes = [ctypes.c_int32, ctypes.c_int32, _i32p, _i32p, _f64p, ctypes.c_int32, _f64p, _f64p, _f64p]
         _fmt = lib
     return _fmt
 
@@ -135,6 +139,46 @@ def verify(nrow, ai, aj, ax, x, rhs, mirror=False):
     rhs = np.ascontiguousarray(rhs, dtype=np.float64)
     out = np.zeros(4)
     fmt().oracle_verify(nrow, len(ax), _p(ai, _i32p), _p(aj, _i32p), _p(ax, _f64p), 1 if mirror else 0, _p(x, _f64p), _p(rhs, _f64p), _p(out, _f64p))
+    return dict(max_abs_a=out[0], max_abs_ax=out[1], max_abs_diff=out[2], relative_error=out[3])
+
+
+# ---- Complex64 twins --------------------------------------------------------------------------------------
+def complex_coo_to_csr(nrow, ncol, ai, aj, ax):
+    """ComplexCsrMatrix::update_from_coo (csr_matrix.rs:359-480 over Complex64) -> (row_pointers, col_indices, values)"""
+    ai = np.ascontiguousarray(ai, dtype=np.int32)
+    aj = np.ascontiguousarray(aj, dtype=np.int32)
+    ax = np.ascontiguousarray(ax, dtype=np.complex128)
+    nnz = len(ax)
+    bp = np.zeros(nrow + 1, dtype=np.int32)
+    bj = np.zeros(nnz, dtype=np.int32)
+    bx = np.zeros(nnz, dtype=np.complex128)
+    rc = fmt().oracle_complex_coo_to_csr(nrow, ncol, nnz, _p(ai, _i32p), _p(aj, _i32p), _p(ax, _f64p), _p(bp, _i32p), _p(bj, _i32p), _p(bx, _f64p))
+    if rc != 0:
+        raise ValueError("oracle_complex_coo_to_csr failed: %d" % rc)
+    n = bp[-1]
+    return bp, bj[:n].copy(), bx[:n].copy()
+
+
+def complex_coo_matvec(nrow, ai, aj, ax, u, mirror=False):
+    """ComplexCooMatrix::mat_vec_mul (coo_matrix.rs:547-565)"""
+    ai = np.ascontiguousarray(ai, dtype=np.int32)
+    aj = np.ascontiguousarray(aj, dtype=np.int32)
+    ax = np.ascontiguousarray(ax, dtype=np.complex128)
+    u = np.ascontiguousarray(u, dtype=np.complex128)
+    v = np.zeros(nrow, dtype=np.complex128)
+    fmt().oracle_complex_coo_matvec(nrow, len(ax), _p(ai, _i32p), _p(aj, _i32p), _p(ax, _f64p), 1 if mirror else 0, _p(u, _f64p), _p(v, _f64p))
+    return v
+
+
+def complex_verify(nrow, ai, aj, ax, x, rhs, mirror=False):
+    """VerifyLinSys::from_complex (verify_lin_sys.rs:104-146)"""
+    ai = np.ascontiguousarray(ai, dtype=np.int32)
+    aj = np.ascontiguousarray(aj, dtype=np.int32)
+    ax = np.ascontiguousarray(ax, dtype=np.complex128)
+    x = np.ascontiguousarray(x, dtype=np.complex128)
+    rhs = np.ascontiguousarray(rhs, dtype=np.complex128)
+    out = np.zeros(4)
+    fmt().oracle_complex_verify(nrow, len(ax), _p(ai, _i32p), _p(aj, _i32p), _p(ax, _f64p), 1 if mirror else 0, _p(x, _f64p), _p(rhs, _f64p), _p(out, _f64p))
     return dict(max_abs_a=out[0], max_abs_ax=out[1], max_abs_diff=out[2], relative_error=out[3])
 
 

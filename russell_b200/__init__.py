@@ -600,3 +600,10 @@ class VerifyLinSys:
         max_abs_ax = float(np.max(np.abs(ax)))
         max_abs_diff = float(np.max(np.abs(ax - rhs)))
         return VerifyLinSys(max_abs_a, max_abs_ax, max_abs_diff, max_abs_diff / (max_abs_a + 1.0))
+
+
+from .complex import (ComplexCooMatrix, ComplexCscMatrix, ComplexCsrMatrix, ComplexLinSolver,  # noqa: E402
+                      ComplexSolverB200, verify_from_complex)
+
+__all__ += ["ComplexCooMatrix", "ComplexCsrMatrix", "ComplexCscMatrix", "ComplexSolverB200", "ComplexLinSolver",
+            "verify_from_complex"]

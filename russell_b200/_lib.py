@@ -41,9 +41,26 @@ SIGNATURES = {
     "solver_b200_version": (ctypes.c_char_p, []),
     "solver_b200_get_stream": (p_void, [p_void]),
     "solver_b200_get_device": (c_i32, [p_void]),
+    # Complex64 twin (russell_b200/csrc/complex_b200.cu)
+    "complex_solver_b200_new": (p_void, []),
+    "complex_solver_b200_drop": (None, [p_void]),
+    "complex_solver_b200_initialize": (c_i32, [p_void, c_i32, c_i32, c_i32, c_f64, c_i32, c_f64, c_i32, c_i32, c_i32, c_i32,
+                                               p_i32, p_i32, p_f64]),
+    "complex_solver_b200_factorize": (c_i32, [p_void, p_i32, p_i32, c_i32, p_f64]),
+    "complex_solver_b200_solve": (c_i32, [p_void, p_f64, p_f64, c_i32]),
+    "complex_solver_b200_factorize_device": (c_i32, [p_void, p_void]),
+    "complex_solver_b200_solve_device": (c_i32, [p_void, p_void, p_void]),
+    "complex_solver_b200_spmv": (c_i32, [p_void, p_f64, p_f64]),
+    "complex_solver_b200_residual": (c_i32, [p_void, p_f64, p_f64, p_f64]),
+    "complex_solver_b200_get_stats": (c_i32, [p_void, p_f64, c_i32]),
+    "complex_solver_b200_set_option": (c_i32, [p_void, ctypes.c_char_p, c_f64]),
+    "complex_solver_b200_real_handle": (p_void, [p_void]),
     # host formats (russell_b200/csrc/host_formats.cpp)
     "b200_coo_to_csr": (c_i32, [c_i32, c_i32, c_i32, p_i32, p_i32, p_f64, p_i32, p_i32, p_f64]),
     "b200_coo_to_csc": (c_i32, [c_i32, c_i32, c_i32, p_i32, p_i32, p_f64, p_i32, p_i32, p_f64]),
+    "b200_complex_coo_to_csr": (c_i32, [c_i32, c_i32, c_i32, p_i32, p_i32, p_f64, p_i32, p_i32, p_f64]),
+    "b200_complex_coo_to_csc": (c_i32, [c_i32, c_i32, c_i32, p_i32, p_i32, p_f64, p_i32, p_i32, p_f64]),
+    "b200_complex_embed": (c_i32, [c_i32, p_i32, p_i32, p_f64, c_i32, p_i64, p_i32, p_i32, p_i32, p_f64]),
     "b200_mm_read": (c_i32, [ctypes.c_char_p, c_i32, p_i64, p_i32, p_i32, p_f64, c_i64]),
 }
 

@@ -19,13 +19,10 @@
 #include <string>
 #include <vector>
 
-extern "C" {
-
-// Converts triplets (with duplicates) to compressed rows.  ptr has nmajor+1 entries; idx/val have nnz slots,
-// of which the first ptr[nmajor] are valid on return.  Returns 0, or a negative error:
-//   -1 index out of range, -2 nnz < 1
-int32_t b200_coo_to_csr(int32_t nrow, int32_t ncol, int32_t nnz, const int32_t* ai, const int32_t* aj, const double* ax,
-                        int32_t* ptr, int32_t* idx, double* val) {
+// Converts triplets (with duplicates) to compressed rows; W doubles per value (1 = real, 2 = interleaved complex).
+template <int W>
+static int32_t coo_to_csr_impl(int32_t nrow, int32_t ncol, int32_t nnz, const int32_t* ai, const int32_t* aj, const double* ax,
+                               int32_t* ptr, int32_t* idx, double* val) {
     if (nnz < 1) return -2;
     std::vector<int32_t> start(nrow + 1, 0);
     for (int32_t k = 0; k < nnz; k++) {
@@ -44,15 +41,33 @@ int32_t b200_coo_to_csr(int32_t nrow, int32_t ncol, int32_t nnz, const int32_t* 
         std::stable_sort(b, e, [&](int32_t x, int32_t y) { return aj[x] < aj[y]; });
         for (int32_t* q = b; q != e;) {
             const int32_t j = aj[*q];
-            double s = ax[*q];
-            for (++q; q != e && aj[*q] == j; ++q) s += ax[*q]; // duplicates: summed in order of appearance
+            double s[W];
+            for (int c = 0; c < W; c++) s[c] = ax[(size_t)W * *q + c];
+            for (++q; q != e && aj[*q] == j; ++q) // duplicates: summed in order of appearance
+                for (int c = 0; c < W; c++) s[c] += ax[(size_t)W * *q + c];
             idx[out] = j;
-            val[out] = s;
+            for (int c = 0; c < W; c++) val[(size_t)W * out + c] = s[c];
             out++;
         }
         ptr[i + 1] = out;
     }
     return 0;
+}
+
+extern "C" {
+
+// Real triplets -> CSR.  ptr has nmajor+1 entries; idx/val have nnz slots, of which the first ptr[nmajor] are valid on
+// return.  Returns 0, or a negative error: -1 index out of range, -2 nnz < 1
+int32_t b200_coo_to_csr(int32_t nrow, int32_t ncol, int32_t nnz, const int32_t* ai, const int32_t* aj, const double* ax,
+                        int32_t* ptr, int32_t* idx, double* val) {
+    return coo_to_csr_impl<1>(nrow, ncol, nnz, ai, aj, ax, ptr, idx, val);
+}
+
+// Complex twin (ComplexCsrMatrix::update_from_coo is the same generic code, csr_matrix.rs:359-480 over Complex64):
+// ax / val hold interleaved (re, im) pairs, 2*nnz doubles.
+int32_t b200_complex_coo_to_csr(int32_t nrow, int32_t ncol, int32_t nnz, const int32_t* ai, const int32_t* aj,
+                                const double* ax, int32_t* ptr, int32_t* idx, double* val) {
+    return coo_to_csr_impl<2>(nrow, ncol, nnz, ai, aj, ax, ptr, idx, val);
 }
 
 // Same conversion, additionally returning the triplet -> slot map: seg_ptr[nslots+1] / seg_idx[nnz] list, for every
@@ -94,6 +109,70 @@ int32_t b200_coo_to_csc(int32_t nrow, int32_t ncol, int32_t nnz, const int32_t* 
                         int32_t* ptr, int32_t* idx, double* val) {
     // columns of A are the rows of A^T; the duplicate-summation order (order of appearance) is unchanged
     return b200_coo_to_csr(ncol, nrow, nnz, aj, ai, ax, ptr, idx, val);
+}
+
+int32_t b200_complex_coo_to_csc(int32_t nrow, int32_t ncol, int32_t nnz, const int32_t* ai, const int32_t* aj,
+                                const double* ax, int32_t* ptr, int32_t* idx, double* val) {
+    return b200_complex_coo_to_csr(ncol, nrow, nnz, aj, ai, ax, ptr, idx, val);
+}
+
+// ---- Complex64 -> real embedding (used by complex_b200.cu; exported so that the CPU tests can check it) -------------
+// The complex system A z = c becomes the real system of order 2n in interleaved unknowns: every complex entry a = ar + i ai
+// at (i, j) becomes the 2x2 block [ar -ai; ai ar] at rows (2i, 2i+1), columns (2j, 2j+1).  Input: complex CSR (sorted
+// columns, no duplicates; `lower` = only j <= i given, complex SYMMETRIC A = A^T, mirrored here).  Output: real CSR of
+// order 2n plus, per real slot, code = 4*source_slot + k with k: 0 -> +re, 1 -> -im, 2 -> +im, 3 -> +re.
+// Query mode (rptr == NULL): info[0] = full complex entries, info[1] = real entries.  rval may be NULL.
+// Returns 0, -1 invalid CSR, -2 the embedded matrix does not fit int32 indices.
+int32_t b200_complex_embed(int32_t n, const int32_t* rp, const int32_t* ci, const double* values, int32_t lower,
+                           int64_t* info, int32_t* rptr, int32_t* rcol, int32_t* code, double* rval) {
+    if (n < 1 || !rp || !ci || !info || rp[0] != 0 || rp[n] < 1) return -1;
+    if (n > (1 << 30) - 1) return -2;
+    std::vector<int64_t> fptr((size_t)n + 1, 0);
+    for (int32_t i = 0; i < n; i++) {
+        if (rp[i + 1] < rp[i]) return -1;
+        for (int32_t p = rp[i]; p < rp[i + 1]; p++) {
+            const int32_t j = ci[p];
+            if (j < 0 || j >= n || (lower && j > i)) return -1;
+            if (p > rp[i] && ci[p - 1] >= j) return -1; // sorted, no duplicates
+            fptr[i + 1]++;
+            if (lower && j != i) fptr[j + 1]++;
+        }
+    }
+    for (int32_t i = 0; i < n; i++) fptr[i + 1] += fptr[i];
+    const int64_t nfull = fptr[n];
+    info[0] = nfull, info[1] = 4 * nfull;
+    if (4 * nfull > 2147483647LL) return -2;
+    if (!rptr) return 0;
+    if (!rcol || !code) return -1;
+    std::vector<int32_t> fcol((size_t)nfull), fsrc((size_t)nfull);
+    std::vector<int64_t> fill(fptr.begin(), fptr.end() - 1);
+    // row i of the full matrix: its own entries (ascending), then the mirrored ones (j > i; ascending because the source
+    // rows are visited in ascending order)
+    for (int32_t i = 0; i < n; i++)
+        for (int32_t p = rp[i]; p < rp[i + 1]; p++) fcol[fill[i]] = ci[p], fsrc[fill[i]] = p, fill[i]++;
+    if (lower)
+        for (int32_t i = 0; i < n; i++)
+            for (int32_t p = rp[i]; p < rp[i + 1]; p++) {
+                const int32_t j = ci[p];
+                if (j != i) fcol[fill[j]] = i, fsrc[fill[j]] = p, fill[j]++;
+            }
+    int64_t w = 0;
+    rptr[0] = 0;
+    for (int32_t i = 0; i < n; i++)
+        for (int half = 0; half < 2; half++) { // half 0: real part of equation i, half 1: imaginary part
+            for (int64_t q = fptr[i]; q < fptr[i + 1]; q++) {
+                const int32_t j = fcol[q], src = fsrc[q];
+                const double re = values ? values[2 * (size_t)src] : 0.0, im = values ? values[2 * (size_t)src + 1] : 0.0;
+                rcol[w] = 2 * j, code[w] = 4 * src + (half ? 2 : 0);
+                if (rval) rval[w] = half ? im : re;
+                w++;
+                rcol[w] = 2 * j + 1, code[w] = 4 * src + (half ? 3 : 1);
+                if (rval) rval[w] = half ? re : -im;
+                w++;
+            }
+            rptr[2 * i + half + 1] = (int32_t)w;
+        }
+    return 0;
 }
 
 // ---- Matrix Market ----------------------------------------------------------------------------------

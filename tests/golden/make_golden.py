@@ -6,6 +6,7 @@ Nothing at test time reads /root/reference.
 
 Sources (cpmech/russell @ 44fc3f9):
   * russell_sparse/src/samples.rs            -> samples.json  (COO triplets + CSC + CSR + det per sample/variant)
+                                             -> complex_samples.json (the Complex* twins; values as [re, im] pairs)
   * russell_sparse/src/bin/solve_matrix_market.rs:307-372 -> bfwb62_x.json (62 golden solution values)
   * russell_sparse/data/matrix_market/*.mtx  -> copied verbatim as parser fixtures (data files, not code)
 """
@@ -22,12 +23,38 @@ def eval_num(expr):
     return float(eval(expr))
 
 
+def eval_val(expr):
+    """real literal -> float; cpx!(a, b) -> [a, b]"""
+    expr = expr.strip()
+    m = re.fullmatch(r"cpx!\((.+),(.+)\)", expr)
+    if m:
+        return [eval_num(m.group(1)), eval_num(m.group(2))]
+    return eval_num(expr)
+
+
+def split_items(buf):
+    """splits a vec![...] body at top-level commas (cpx!(a, b) holds a comma of its own)"""
+    items, depth, cur = [], 0, ""
+    for ch in buf:
+        if ch == "(":
+            depth += 1
+        elif ch == ")":
+            depth -= 1
+        if ch == "," and depth == 0:
+            items.append(cur)
+            cur = ""
+        else:
+            cur += ch
+    items.append(cur)
+    return [t.strip() for t in items if t.strip()]
+
+
 def strip_comment(line):
     k = line.find("//")
     return line if k < 0 else line[:k]
 
 
-def parse_samples():
+def parse_samples(want_complex=False):
     src = open(os.path.join(REF, "src/samples.rs")).read().split("\n")
     # locate real-valued sample functions
     starts = [i for i, l in enumerate(src) if re.match(r"\s*pub fn \w+\(", l)]
@@ -42,7 +69,7 @@ def parse_samples():
             k += 1
         hdr += src[k]
         name = re.search(r"pub fn (\w+)\(", hdr).group(1)
-        if "Complex" in hdr:
+        if ("Complex" in hdr) != want_complex:
             continue
         params = re.findall(r"(\w+): bool", hdr)
         body = src[k + 1:end]
@@ -113,7 +140,7 @@ def run_body(body, env):
         if m:
             rec["coo_i"].append(int(m.group(1)))
             rec["coo_j"].append(int(m.group(2)))
-            rec["coo_v"].append(eval_num(m.group(3)))
+            rec["coo_v"].append(eval_val(m.group(3)))
             continue
         m = re.match(r"let (values|row_indices|col_indices|col_pointers|row_pointers) = vec!\[(.*)$", line)
         if m:
@@ -125,7 +152,7 @@ def run_body(body, env):
         m = re.match(r"\(coo, csc, csr, (.+)\)$", line)
         if m:
             try:
-                rec["det"] = eval_num(m.group(1))
+                rec["det"] = eval_val(m.group(1))
             except ValueError:
                 rec["det"] = None  # rectangular samples carry a placeholder instead of a determinant
             continue
@@ -137,10 +164,10 @@ def run_body(body, env):
 
 def finish_vec(rec, name, buf):
     buf = buf[:buf.index("]")]
-    items = [t for t in (x.strip() for x in buf.split(",")) if t]
+    items = split_items(buf)
     if name == "values":
         key = "csc_values" if "csc_values" not in rec else "csr_values"
-        rec[key] = [eval_num(t) for t in items]
+        rec[key] = [eval_val(t) for t in items]
     else:
         rec[name] = [int(t) for t in items]
 
@@ -158,6 +185,10 @@ def main():
     samples = parse_samples()
     with open(os.path.join(OUT, "samples.json"), "w") as f:
         json.dump(samples, f, indent=1, sort_keys=True)
+    csamples = parse_samples(want_complex=True)
+    with open(os.path.join(OUT, "complex_samples.json"), "w") as f:
+        json.dump(csamples, f, indent=1, sort_keys=True)
+    print("complex samples:", len(csamples), sorted(csamples))
     with open(os.path.join(OUT, "bfwb62_x.json"), "w") as f:
         json.dump(parse_bfwb62_x(), f, indent=1)
     mm = os.path.join(OUT, "matrix_market")

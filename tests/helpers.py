@@ -88,3 +88,71 @@ def saddle_point_triplets(k, ncon=None):
             vals += [v, v]
     nt = n + ncon
     return nt, np.array(rows, dtype=np.int32), np.array(cols, dtype=np.int32), np.array(vals)
+
+
+def load_complex_samples():
+    with open(os.path.join(GOLDEN, "complex_samples.json")) as f:
+        return json.load(f)
+
+
+def complex_sample_coo(name):
+    """russell_b200.ComplexCooMatrix from a golden complex sample (Samples::<name>, russell_sparse/src/samples.rs)"""
+    from russell_b200 import ComplexCooMatrix, Sym
+
+    s = load_complex_samples()[name]
+    coo = ComplexCooMatrix(s["nrow"], s["ncol"], s["max_nnz"], Sym[s["sym"]])
+    for i, j, v in zip(s["coo_i"], s["coo_j"], s["coo_v"]):
+        coo.put(i, j, complex(*v))
+    return coo, s
+
+
+# Radau5 constants (russell_ode/src/radau5.rs:697-699)
+RADAU5_ALPHA = 2.6810828736277521338957907432111121010270319565630
+RADAU5_BETA = 3.0504301992474105694263776247875679044407041991795
+RADAU5_GAMMA = 3.6378342527444957322084185135777757979459360868739
+
+
+def brusselator_radau5_triplets(npoint, h=1e-4, alpha=0.1):
+    """The two Newton matrices Radau5 factorizes for the Brusselator PDE (BASELINE.json configs[3]):
+    K_real = (gamma/h) I - J and K_comp = ((alpha_r + i beta_r)/h) I - J, as COO triplets WITH duplicates in the
+    reference's order of `put` calls.
+
+    J restates Samples::brusselator_pde(alpha, npoint, second_book=true, ignore_diffusion=false)'s Jacobian at y0
+    (russell_ode/src/samples.rs:549-571,598-602): per grid point m (m = i + j*nx) the four reaction entries, then the
+    five-point molecule {2(kx/dx^2+ky/dy^2), -kx/dx^2 x2, -ky/dy^2 x2} with kx = ky = -alpha on a periodic grid
+    (russell_pde/src/fdm_2d.rs:944-979) for the U block and the V block; Radau5 then appends ndim diagonal entries
+    (russell_ode/src/radau5.rs:226-237).  Returns (ndim, ai, aj, k_real_values, k_comp_values): 16*npoint^2 triplets."""
+    nx = ny = npoint
+    s = nx * ny
+    ndim = 2 * s
+    dx = 1.0 / (nx - 1)
+    dy = 1.0 / (ny - 1)
+    kx = ky = -alpha
+    mol = np.array([2.0 * (kx / dx**2 + ky / dy**2), -kx / dx**2, -kx / dx**2, -ky / dy**2, -ky / dy**2])
+    m = np.arange(s, dtype=np.int64)
+    i, j = m % nx, m // nx
+    x, y = i * dx, j * dy
+    um = 22.0 * y * np.power(1.0 - y, 1.5)
+    vm = 27.0 * x * np.power(1.0 - x, 1.5)
+    um2 = um * um
+    fin_x, fin_y = nx - 1, ny - 1
+    nn = np.stack([m, np.where(i != 0, m - 1, m + fin_x), np.where(i != fin_x, m + 1, m - fin_x),
+                   np.where(j != 0, m - nx, m + fin_y * nx), np.where(j != fin_y, m + nx, m - fin_y * nx)], axis=1)
+    # per point: 4 reaction entries, then (m, n) and (s+m, s+n) interleaved for the 5 molecule entries
+    rows = np.empty((s, 14), dtype=np.int64)
+    cols = np.empty((s, 14), dtype=np.int64)
+    vals = np.empty((s, 14))
+    rows[:, 0], cols[:, 0], vals[:, 0] = m, m, -4.4 + 2.0 * um * vm
+    rows[:, 1], cols[:, 1], vals[:, 1] = m, s + m, um2
+    rows[:, 2], cols[:, 2], vals[:, 2] = s + m, m, 3.4 - 2.0 * um * vm
+    rows[:, 3], cols[:, 3], vals[:, 3] = s + m, s + m, -um2
+    for b in range(5):
+        rows[:, 4 + 2 * b], cols[:, 4 + 2 * b], vals[:, 4 + 2 * b] = m, nn[:, b], mol[b]
+        rows[:, 5 + 2 * b], cols[:, 5 + 2 * b], vals[:, 5 + 2 * b] = s + m, s + nn[:, b], mol[b]
+    d = np.arange(ndim, dtype=np.int64)
+    ai = np.concatenate([rows.ravel(), d]).astype(np.int32)
+    aj = np.concatenate([cols.ravel(), d]).astype(np.int32)
+    jv = -vals.ravel()  # K = -J + ...
+    k_real = np.concatenate([jv, np.full(ndim, RADAU5_GAMMA / h)])
+    k_comp = np.concatenate([jv.astype(np.complex128), np.full(ndim, complex(RADAU5_ALPHA / h, RADAU5_BETA / h))])
+    return ndim, ai, aj, k_real, k_comp

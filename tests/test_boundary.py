@@ -20,10 +20,11 @@ def header_text():
 
 def test_library_exports_every_declared_symbol():
     lib = _lib.load()
-    names = re.findall(r"\b((?:solver_b200|b200)_\w+)\s*\(", header_text())
+    names = re.findall(r"\b((?:complex_solver_b200|solver_b200|b200)_\w+)\s*\(", header_text())
     names = sorted(set(n for n in names if not n.startswith("B200_")))
     assert {"solver_b200_new", "solver_b200_drop", "solver_b200_initialize", "solver_b200_factorize",
-            "solver_b200_solve"} <= set(names)
+            "solver_b200_solve", "complex_solver_b200_new", "complex_solver_b200_drop", "complex_solver_b200_initialize",
+            "complex_solver_b200_factorize", "complex_solver_b200_solve"} <= set(names)
     for n in names:
         assert hasattr(lib, n), "missing export: " + n
     # and the ctypes prototypes cover the header
@@ -38,6 +39,10 @@ def test_five_entry_points_have_the_cudss_shim_shape():
     assert len(sig["solver_b200_factorize"][1]) == 5
     assert len(sig["solver_b200_solve"][1]) == 4
     assert sig["solver_b200_new"][1] == [] and len(sig["solver_b200_drop"][1]) == 1
+    # complex_solver_cudss.rs:32-64: the complex twin has the same shapes
+    assert len(sig["complex_solver_b200_initialize"][1]) == 14
+    assert len(sig["complex_solver_b200_factorize"][1]) == 5
+    assert len(sig["complex_solver_b200_solve"][1]) == 4
 
 
 def test_status_codes_match_reference_constants():
@@ -57,6 +62,9 @@ def test_null_handle_is_rejected_not_dereferenced():
     assert lib.solver_b200_factorize(None, None, None, 0, None) == 100000
     assert lib.solver_b200_solve(None, None, None, 0) == 100000
     assert lib.solver_b200_initialize(None, 0, 0, 0, -1.0, -1, -1.0, 0, 0, 0, 1, None, None, None) == 100000
+    assert lib.complex_solver_b200_factorize(None, None, None, 0, None) == 100000
+    assert lib.complex_solver_b200_solve(None, None, None, 0) == 100000
+    lib.complex_solver_b200_drop(None)
     lib.solver_b200_drop(None)  # NULL-safe like solver_cudss_drop (interface_cudss.cu:126-129)
 
 
@@ -106,6 +114,9 @@ def test_no_device_means_no_solver_not_a_cpu_fallback():
         rb.SolverB200()
     with pytest.raises(rb.StrError):
         rb.LinSolver(rb.Genie.B200)
+    assert _lib.load().complex_solver_b200_new() is None
+    with pytest.raises(rb.StrError, match="c-code failed to allocate the B200 solver"):
+        rb.ComplexSolverB200()
 
 
 def test_product_does_not_import_the_oracle():

@@ -1,0 +1,190 @@
+"""CPU tests of the Complex64 twin: host formats against the reference's complex fixtures,
+the oracle's complex functions pinned to the reference's complex known answers, the real embedding the CUDA path
+factorizes (checked densely and by the scalar walk of the front plan), and the Radau5/Brusselator matrix generator.
+No CUDA compute here."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import helpers
+import russell_b200 as rb
+from oracle import oracle
+from russell_b200 import _lib
+from russell_b200._lib import p_f64, p_i32, p_i64, ptr
+
+CS = helpers.load_complex_samples()
+
+# (sample, rhs, x_correct, tolerance, reference test)
+COMPLEX_KATS = [
+    ("complex_symmetric_3x3_lower", [-3 + 3j, 2 - 2j, 9 + 7j], [1 + 1j, 2 - 2j, 3 + 3j], 1e-14,
+     "complex_lin_solver.rs:199-204"),
+    ("complex_symmetric_3x3_full", [-3 + 3j, 2 - 2j, 9 + 7j], [1 + 1j, 2 - 2j, 3 + 3j], 1e-14,
+     "complex_solver_umfpack.rs:600-610, complex_lin_solver.rs:221-226"),
+    ("umfpack_complex_unsymmetric_5x5", [8.0, 45.0, -3.0, 3.0, 19.0], [1.0, 2.0, 3.0, 4.0, 5.0], 1e-12,
+     "complex_solver_cudss.rs:556-585 (colamd/matching variants reach 1e-12)"),
+    ("mkl_complex_positive_definite_5x5_lower", [1.0, 2.0, 3.0, 4.0, 5.0],
+     [-979.0 / 3.0, 983.0, 1961.0 / 12.0, 398.0, 123.0 / 2.0], 1e-10, "complex_solver_cudss.rs:653-677"),
+]
+
+
+def dense_of(s):
+    a = np.zeros((s["nrow"], s["ncol"]), dtype=np.complex128)
+    for i, j, v in zip(s["coo_i"], s["coo_j"], s["coo_v"]):
+        a[i, j] += complex(*v)
+        if s["sym"] in ("YesLower", "YesUpper") and i != j:
+            a[j, i] += complex(*v)
+    return a
+
+
+def embed(csr, lower):
+    """calls the product's b200_complex_embed (the host half of complex_solver_b200_initialize)"""
+    lib = _lib.load()
+    n, nnz = csr.nrow, csr.nnz
+    vals = np.ascontiguousarray(csr.values[:nnz])
+    info = np.zeros(2, dtype=np.int64)
+    rc = lib.b200_complex_embed(n, ptr(csr.pointers, p_i32), ptr(csr.indices, p_i32), ptr(vals, p_f64), int(lower),
+                                ptr(info, p_i64), None, None, None, None)
+    assert rc == 0
+    nreal = int(info[1])
+    rptr = np.zeros(2 * n + 1, dtype=np.int32)
+    rcol = np.zeros(nreal, dtype=np.int32)
+    code = np.zeros(nreal, dtype=np.int32)
+    rval = np.zeros(nreal)
+    rc = lib.b200_complex_embed(n, ptr(csr.pointers, p_i32), ptr(csr.indices, p_i32), ptr(vals, p_f64), int(lower),
+                                ptr(info, p_i64), ptr(rptr, p_i32), ptr(rcol, p_i32), ptr(code, p_i32), ptr(rval, p_f64))
+    assert rc == 0
+    return rptr, rcol, code, rval, vals
+
+
+@pytest.mark.parametrize("name", sorted(CS))
+def test_complex_coo_to_csr_csc_match_reference_fixtures_bit_exactly(name):
+    coo, s = helpers.complex_sample_coo(name)
+    want_csr = np.array([complex(*v) for v in s["csr_values"]])
+    want_csc = np.array([complex(*v) for v in s["csc_values"]])
+    csr = rb.ComplexCsrMatrix.from_coo(coo)
+    n = csr.nnz
+    assert list(csr.row_pointers) == s["row_pointers"] and list(csr.col_indices[:n]) == s["col_indices"]
+    assert np.array_equal(csr.values[:n], want_csr)
+    csc = rb.ComplexCscMatrix.from_coo(coo)
+    assert list(csc.col_pointers) == s["col_pointers"] and list(csc.row_indices[:n]) == s["row_indices"]
+    assert np.array_equal(csc.values[:n], want_csc)
+    # the oracle's restatement agrees with the same fixtures (pins the oracle)
+    bp, bj, bx = oracle.complex_coo_to_csr(s["nrow"], s["ncol"], s["coo_i"], s["coo_j"], [complex(*v) for v in s["coo_v"]])
+    assert list(bp) == s["row_pointers"] and list(bj) == s["col_indices"] and np.array_equal(bx, want_csr)
+
+
+def test_complex_coo_guards():
+    # same guards and messages as the real CooMatrix (coo_matrix.rs:173-198,324-352)
+    with pytest.raises(rb.StrError, match="nrow must be ≥ 1"):
+        rb.ComplexCooMatrix(0, 1, 1)
+    coo = rb.ComplexCooMatrix(2, 2, 1, rb.Sym.YesLower)
+    with pytest.raises(rb.StrError, match="j > i is incorrect for lower triangular storage"):
+        coo.put(0, 1, 1j)
+    coo.put(1, 0, 2 + 1j)
+    with pytest.raises(rb.StrError, match="max number of items has been reached"):
+        coo.put(1, 1, 1.0)
+    assert coo.get_values()[0] == 2 + 1j and coo.values.dtype == np.complex128
+
+
+def test_oracle_complex_verify_matches_reference_numbers():
+    # verify_lin_sys.rs:253-275 (new_complex_matrix_works)
+    s = CS["complex_rectangular_4x3"]
+    vals = [complex(*v) for v in s["coo_v"]]
+    x = np.array([1 + 2j, 2 - 1j, 1j])
+    rhs = np.array([-6 + 14j, -1 + 2j, 14 + 6j, 1 + 2j])
+    v = oracle.complex_verify(4, s["coo_i"], s["coo_j"], vals, x, rhs)
+    assert abs(v["max_abs_a"] - 7.0710678118654755) <= 1e-15 and abs(v["max_abs_ax"] - 15.231546211727817) <= 1e-15
+    assert v["max_abs_diff"] <= 1e-15 and v["relative_error"] <= 1e-15
+    rhs[3] = 1.0
+    v = oracle.complex_verify(4, s["coo_i"], s["coo_j"], vals, x, rhs)
+    assert abs(v["max_abs_diff"] - 2.0) <= 1e-15 and abs(v["relative_error"] - 2.0 / (7.0710678118654755 + 1.0)) <= 1e-15
+
+
+@pytest.mark.parametrize("name,rhs,xc,tol,src", COMPLEX_KATS)
+def test_oracle_complex_lu_is_pinned_to_the_reference_known_answers(name, rhs, xc, tol, src):
+    s = CS[name]
+    a = dense_of(s)
+    import scipy.sparse as sp
+
+    x = oracle.lu_solve(sp.csc_matrix(a), np.array(rhs, dtype=np.complex128))
+    assert np.max(np.abs(x - np.array(xc))) <= tol * max(1.0, np.max(np.abs(xc))), src
+    # determinant fixture of the sample (samples.rs) agrees with the dense matrix
+    assert abs(np.linalg.det(a) - complex(*s["det"])) <= 1e-12 * abs(complex(*s["det"]))
+
+
+@pytest.mark.parametrize("name", [k for k in sorted(CS) if CS[k]["nrow"] == CS[k]["ncol"] and CS[k]["sym"] != "YesUpper"])
+def test_embedding_is_the_2x2_block_matrix(name):
+    coo, s = helpers.complex_sample_coo(name)
+    csr = rb.ComplexCsrMatrix.from_coo(coo)
+    rptr, rcol, code, rval, vals = embed(csr, s["sym"] == "YesLower")
+    a = dense_of(s)
+    n2 = 2 * s["nrow"]
+    want = np.zeros((n2, n2))
+    want[0::2, 0::2], want[0::2, 1::2], want[1::2, 0::2], want[1::2, 1::2] = a.real, -a.imag, a.imag, a.real
+    got = np.zeros((n2, n2))
+    for i in range(n2):
+        cols = rcol[rptr[i]:rptr[i + 1]]
+        assert np.all(np.diff(cols) > 0)  # sorted rows, no duplicates: the CSR contract of solver_b200_initialize
+        got[i, cols] = rval[rptr[i]:rptr[i + 1]]
+    assert np.array_equal(got, want)
+    # the slot map k_complex_expand applies on the device reproduces the values bit for bit
+    flat = vals.view(np.float64)
+    k, src = code & 3, code >> 2
+    assert np.array_equal(np.where(k == 1, -flat[2 * src + 1], np.where(k == 2, flat[2 * src + 1], flat[2 * src])), rval)
+
+
+def test_embed_rejects_bad_csr():
+    lib = _lib.load()
+    info = np.zeros(2, dtype=np.int64)
+    rp = np.array([0, 2, 3], dtype=np.int32)
+    v = np.zeros(6)
+    for ci in ([1, 0, 1], [0, 0, 1], [0, 2, 1]):  # unsorted, duplicate, out of range
+        c = np.array(ci, dtype=np.int32)
+        assert lib.b200_complex_embed(2, ptr(rp, p_i32), ptr(c, p_i32), ptr(v, p_f64), 0, ptr(info, p_i64), None, None, None, None) == -1
+    c = np.array([0, 1, 1], dtype=np.int32)  # j > i with the lower-triangle promise
+    assert lib.b200_complex_embed(2, ptr(rp, p_i32), ptr(c, p_i32), ptr(v, p_f64), 1, ptr(info, p_i64), None, None, None, None) == -1
+    assert lib.b200_complex_embed(2, ptr(rp, p_i32), ptr(c, p_i32), ptr(v, p_f64), 0, ptr(info, p_i64), None, None, None, None) == 0
+    assert list(info) == [3, 12]
+
+
+@pytest.mark.parametrize("name,rhs,xc,tol,src", COMPLEX_KATS)
+def test_scalar_walk_of_the_embedded_system_reproduces_the_known_answers(name, rhs, xc, tol, src):
+    # the same host analysis + front plan the CUDA kernels execute, walked on the CPU (oracle/mf_host.cpp), applied to
+    # the embedded real system: validates matching/ordering on matrices with explicit-zero block entries
+    coo, s = helpers.complex_sample_coo(name)
+    csr = rb.ComplexCsrMatrix.from_coo(coo)
+    rptr, rcol, _, rval, _ = embed(csr, s["sym"] == "YesLower")
+    b = np.array(rhs, dtype=np.complex128)
+    rc, x, st = oracle.mf_solve(2 * s["nrow"], rptr, rcol, rval, b.view(np.float64))
+    assert rc == 0
+    assert np.max(np.abs(x.view(np.complex128) - np.array(xc))) <= tol * max(1.0, np.max(np.abs(xc))), src
+
+
+def test_brusselator_radau5_matrices():
+    # BASELINE.json configs[3] generator: sizes from SURVEY 8 (C4) and K = c I - J structure
+    npoint = 9
+    ndim, ai, aj, kr, kc = helpers.brusselator_radau5_triplets(npoint, h=1e-4)
+    s = npoint * npoint
+    assert ndim == 2 * s and len(ai) == 14 * s + ndim
+    bp, bj, bx = oracle.coo_to_csr(ndim, ndim, ai, aj, kr)
+    assert bp[-1] == 6 * ndim  # 6 unique entries per row (~3.0M unique at npoint 500)
+    cp, cj, cx = oracle.complex_coo_to_csr(ndim, ndim, ai, aj, kc)
+    assert np.array_equal(cp, bp) and np.array_equal(cj, bj)
+    # same -J, different shift: K_comp - K_real = ((alpha - gamma) + i beta)/h on the diagonal only
+    d = cx - bx
+    diag = bj == np.repeat(np.arange(ndim), 6)
+    assert np.allclose(d[~diag], 0.0) and np.allclose(d[diag], complex(helpers.RADAU5_ALPHA - helpers.RADAU5_GAMMA, helpers.RADAU5_BETA) / 1e-4)
+    # periodic 5-point rows sum: row sums of -J's diffusion part vanish, so K_real row sum = gamma/h - reaction terms
+    import scipy.sparse as sp
+
+    a = sp.csr_matrix((bx, bj, bp), shape=(ndim, ndim))
+    y = np.linspace(0, 1, npoint)
+    um = np.tile(22.0 * y * (1 - y) ** 1.5, (npoint, 1)).T.ravel()  # U depends on y = j*dy, m = i + j*nx
+    vm = np.tile(27.0 * y * (1 - y) ** 1.5, (npoint, 1)).ravel()    # V depends on x = i*dx
+    rs = np.asarray(a.sum(axis=1)).ravel()
+    assert np.allclose(rs[:s], helpers.RADAU5_GAMMA / 1e-4 - (-4.4 + 2 * um * vm) - um * um, rtol=1e-12)
+    # both systems are solved by the scalar walk (real) / embedded scalar walk (complex) to the north-star residual
+    b = np.ones(ndim)
+    rc, x, st = oracle.mf_solve(ndim, bp, bj, bx, b)
+    assert rc == 0 and np.linalg.norm(b - a @ x) / np.linalg.norm(b) <= 1e-10
