@@ -147,6 +147,11 @@ int32_t solver_b200_set_option(struct InterfaceB200 *solver, const char *key, do
 int32_t solver_b200_debug_copy_factors(struct InterfaceB200 *solver, double *fac, int64_t fac_len,
                                        double *dinv, int64_t dinv_len, int32_t *lperm, int64_t n);
 
+/* debug/profiling: per-item %globaltimer timestamps (ns) of the last persistent top-of-tree sweeps -- 4 per item (start,
+ * dependency satisfied, end, unused), the forward items first, then the backward ones (2 * 4 * n values); desc gets
+ * (front, level, slice, rows) per item.  Needs set_option("trace", 1) before initialize.  Returns the item count. */
+int32_t solver_b200_debug_trace(struct InterfaceB200 *solver, unsigned long long *out, int32_t *desc, int32_t cap);
+
 /* the CUDA stream (cudaStream_t) every kernel of this handle is launched on, and its device ordinal: lets a
  * caller bracket calls with its own CUDA events (bench.py) or order its own work after ours */
 void *solver_b200_get_stream(struct InterfaceB200 *solver);

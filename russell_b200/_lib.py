@@ -38,6 +38,7 @@ SIGNATURES = {
     "solver_b200_get_stats": (c_i32, [p_void, p_f64, c_i32]),
     "solver_b200_set_option": (c_i32, [p_void, ctypes.c_char_p, c_f64]),
     "solver_b200_debug_copy_factors": (c_i32, [p_void, p_f64, c_i64, p_f64, c_i64, p_i32, c_i64]),
+    "solver_b200_debug_trace": (c_i32, [p_void, ctypes.POINTER(ctypes.c_uint64), p_i32, c_i32]),
     "solver_b200_version": (ctypes.c_char_p, []),
     "solver_b200_get_stream": (p_void, [p_void]),
     "solver_b200_get_device": (c_i32, [p_void]),

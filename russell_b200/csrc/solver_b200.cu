@@ -102,6 +102,14 @@ struct InterfaceB200 {
     int* d_big_slot = nullptr;
     // persistent top-of-tree sweep (sweep_top.cuh)
     int top_max_nodes = 1600; // (measured optimum at config 2) levels with at most this many fronts belong to the persistent sweep region
+    // bottom of the tree: one CTA per small subtree (k_fwd_subtree / k_bwd_subtree)
+    int use_subtree = 1, subtree_maxf = 96, subtree_budget = 16384; // eligibility: every front f <= maxf, p <= B200_ST_PMAX, stored entries <= budget
+    std::vector<char> in_sub;   // per front: handled by a subtree CTA in the solve phase
+    int n_subtrees = 0;
+    int2* d_subtrees = nullptr; // (first, root) node ranges, largest first
+    unsigned long long* d_trace = nullptr; // optional per-item timestamps of the persistent sweeps (option "trace")
+    int want_trace = 0;
+    int top_variant = 2;      // 1 = k_fwd_top/k_bwd_top, 2 = k_fwd_top2/k_bwd_top2 (descriptors and indices loaded before the dependency wait)
     int use_top = 1, ltop = 0, n_top_items = 0, top_grid = 0, n_slots = 0;
     bool sweep_dirty = false;          // a persistent sweep aborted: counters must be re-armed
     std::vector<int> cdone_init;       // host copy of the initial completion counters
@@ -178,6 +186,8 @@ void release_device(InterfaceB200* s) {
     if (s->g_sweep) cudaGraphExecDestroy(s->g_sweep), s->g_sweep = nullptr;
     dfree(s->d_nodes), dfree(s->d_rows), dfree(s->d_rel), dfree(s->d_child_idx), dfree(s->d_fact_nodes), dfree(s->d_solve_nodes), dfree(s->d_inv_nodes);
     dfree(s->d_asm), dfree(s->d_panel), dfree(s->d_schur);
+    dfree(s->d_trace);
+    dfree(s->d_subtrees);
     dfree(s->d_big_items), dfree(s->d_big_slot), dfree(s->d_top_items), dfree(s->d_top_ranges), dfree(s->d_top_slot),
     dfree(s->d_cdone), dfree(s->d_xdone), dfree(s->d_epoch), dfree(s->d_abort), dfree(s->d_asm_ranges), dfree(s->d_big_ranges), dfree(s->d_big_scratch), dfree(s->d_big_tickets);
     dfree(s->d_a_src), dfree(s->d_a_dst), dfree(s->d_a_scl);
@@ -262,6 +272,7 @@ void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::ve
             for (int e = P.level_ptr[l]; e < P.level_ptr[l + 1]; e++) {
                 const int v = P.level_nodes[e];
                 const int f = P.p[v] + P.u[v];
+                if (s->in_sub[v]) continue; // walked by a subtree CTA
                 if (sclass(f) < NSC - 1) maxf = std::max(maxf, f), maxp = std::max(maxp, P.p[v]);
             }
             lv.solve_threads[l] = maxf <= 32 ? 32 : (maxf <= 64 ? 64 : 128);
@@ -270,7 +281,7 @@ void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::ve
                 for (int e = P.level_ptr[l]; e < P.level_ptr[l + 1]; e++) {
                     const int v = P.level_nodes[e];
                     const int cls = sclass(P.p[v] + P.u[v]) < NSC - 1 ? 0 : NSC - 1; // everything small goes to slot 0
-                    if (cls == c) solve_nodes.push_back(v);
+                    if (cls == c && !s->in_sub[v]) solve_nodes.push_back(v);
                 }
                 lv.solve_ptr[(size_t)l * NSC + c + 1] = (int)solve_nodes.size();
             }
@@ -455,11 +466,23 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
 
 __global__ void k_bump_epoch(int* epoch) { *epoch += 1; }
 void k_fwd_top_launch(InterfaceB200* s) {
+    if (s->top_variant >= 2) {
+        k_fwd_top2<<<s->top_grid, 256, B200_TOP_SMEM, s->stream>>>(s->d_top_items, s->n_top_items, s->d_nodes, s->d_rel, s->d_fac, s->d_dinv,
+                                                                 s->d_lperm, s->d_top_ranges, s->d_y, s->d_z, s->d_wv, s->d_cdone, s->d_epoch,
+                                                                 s->d_abort, s->d_trace);
+        return;
+    }
     k_fwd_top<<<s->top_grid, 256, B200_TOP_SMEM, s->stream>>>(s->d_top_items, s->n_top_items, s->d_nodes, s->d_child_idx, s->d_rel, s->d_fac,
                                                             s->d_dinv, s->d_lperm, s->d_top_ranges, s->d_y, s->d_z, s->d_wv, s->d_cdone,
                                                             s->d_epoch, s->d_abort);
 }
 void k_bwd_top_launch(InterfaceB200* s) {
+    if (s->top_variant >= 2) {
+        k_bwd_top2<<<s->top_grid, 256, B200_TOP_SMEM, s->stream>>>(s->d_top_items, s->n_top_items, s->d_nodes, s->d_rows, s->d_fac, s->d_dinv,
+                                                                 s->d_z, s->d_xp, s->d_big_scratch, s->d_big_tickets, s->d_top_slot,
+                                                                 s->d_xdone, s->d_epoch, s->d_abort, s->d_trace ? s->d_trace + 4 * (size_t)s->n_top_items : nullptr);
+        return;
+    }
     k_bwd_top<<<s->top_grid, 256, B200_TOP_SMEM, s->stream>>>(s->d_top_items, s->n_top_items, s->d_nodes, s->d_rows, s->d_fac, s->d_dinv,
                                                             s->d_z, s->d_xp, s->d_big_scratch, s->d_big_tickets, s->d_top_slot, s->d_xdone,
                                                             s->d_epoch, s->d_abort);
@@ -470,6 +493,11 @@ int enqueue_sweep_levels(InterfaceB200* s, int* launches) {
     const LevelLists& lv = s->lv;
     int cnt = 0;
     const int lsplit = s->n_top_items > 0 ? s->ltop : P.nlevels; // levels >= lsplit run in the persistent kernels
+    if (s->n_subtrees > 0) {
+        k_fwd_subtree<<<s->n_subtrees, B200_ST_THREADS, 0, s->stream>>>(s->d_subtrees, s->d_nodes, s->d_child_idx, s->d_rel, s->d_fac, s->d_dinv,
+                                                                         s->d_lperm, s->d_y, s->d_z, s->d_wv);
+        cnt++;
+    }
     for (int l = 0; l < lsplit; l++) {
         for (int c = 0; c < NSC - 1; c++) {
             int a = lv.solve_ptr[(size_t)l * NSC + c], b = lv.solve_ptr[(size_t)l * NSC + c + 1];
@@ -506,6 +534,10 @@ int enqueue_sweep_levels(InterfaceB200* s, int* launches) {
                                                   s->d_big_scratch, s->d_big_tickets, s->d_big_slot + lv.big_ptr[l]);
             cnt++;
         }
+    }
+    if (s->n_subtrees > 0) {
+        k_bwd_subtree<<<s->n_subtrees, B200_ST_THREADS, 0, s->stream>>>(s->d_subtrees, s->d_nodes, s->d_rows, s->d_fac, s->d_dinv, s->d_z, s->d_xp);
+        cnt++;
     }
     if (launches) *launches = cnt;
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
@@ -631,6 +663,10 @@ struct InterfaceB200* solver_b200_new(void) {
     if ((e = getenv("B200_FUSED_VARIANT"))) s->fused_variant = atoi(e);
     if ((e = getenv("B200_USE_FUSED"))) s->use_fused = atoi(e);
     if ((e = getenv("B200_USE_TOP"))) s->use_top = atoi(e);
+    if ((e = getenv("B200_TOP_VARIANT"))) s->top_variant = atoi(e);
+    if ((e = getenv("B200_USE_SUBTREE"))) s->use_subtree = atoi(e);
+    if ((e = getenv("B200_SUBTREE_MAXF"))) s->subtree_maxf = atoi(e);
+    if ((e = getenv("B200_SUBTREE_BUDGET"))) s->subtree_budget = atoi(e);
     if ((e = getenv("B200_DIAG_VARIANT"))) s->diag_variant = atoi(e);
     if ((e = getenv("B200_FUSE_CHAIN"))) s->fuse_chain = atoi(e);
     if ((e = getenv("B200_FUSED_MAXF"))) s->fused_maxf = std::max(0, std::min(atoi(e), B200_FUSED_MAXF));
@@ -668,6 +704,11 @@ int32_t solver_b200_set_option(struct InterfaceB200* s, const char* key, double 
     else if (k == "fused_w8_max") s->fused_w8_max = (int)value;
     else if (k == "use_fused") s->use_fused = value != 0.0;
     else if (k == "use_top") s->use_top = value != 0.0;
+    else if (k == "top_variant") s->top_variant = (int)value;
+    else if (k == "trace") s->want_trace = value != 0.0;
+    else if (k == "use_subtree") s->use_subtree = value != 0.0;
+    else if (k == "subtree_maxf") s->subtree_maxf = std::max(1, (int)value);
+    else if (k == "subtree_budget") s->subtree_budget = std::max(1, (int)value);
     else if (k == "diag_variant") s->diag_variant = (int)value;
     else if (k == "fuse_chain") s->fuse_chain = value != 0.0;
     else if (k == "top_max_nodes") s->top_max_nodes = std::max(1, (int)value);
@@ -739,6 +780,36 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
         d.Loff = P.Loff[v], d.Uoff = P.Uoff[v], d.Coff = P.Coff[v], d.Doff = P.Doff[v], d.rows_ptr = P.rows_ptr[v];
         d.pad = P.parent[v]; // parent front (used by the persistent backward sweep)
     }
+    // solve phase, bottom of the tree: maximal subtrees made of small fronts only.  Nodes are in postorder, so the
+    // subtree rooted at v is the contiguous range [v - size + 1, v].
+    std::vector<int2> subtrees;
+    s->in_sub.assign(P.nnodes, 0);
+    if (s->use_subtree) {
+        std::vector<int64_t> ent(P.nnodes);
+        std::vector<int> size(P.nnodes, 1);
+        std::vector<char> elig(P.nnodes, 1);
+        for (int v = 0; v < P.nnodes; v++) { // children precede parents: ent/size/elig of v are final when v is visited
+            ent[v] += (int64_t)P.p[v] * (P.p[v] + 2 * (int64_t)P.u[v]);
+            if (P.p[v] + P.u[v] > s->subtree_maxf || P.p[v] > B200_ST_PMAX || ent[v] > s->subtree_budget) elig[v] = 0;
+            const int par = P.parent[v];
+            if (par >= 0) {
+                ent[par] += ent[v], size[par] += size[v];
+                if (!elig[v]) elig[par] = 0;
+            }
+        }
+        std::vector<std::pair<int64_t, int>> roots;
+        for (int v = 0; v < P.nnodes; v++)
+            if (elig[v] && (P.parent[v] < 0 || !elig[P.parent[v]])) roots.push_back({-ent[v], v});
+        if ((int)roots.size() >= 64) { // worth a launch of its own
+            std::sort(roots.begin(), roots.end()); // largest first: the long subtrees start early
+            for (auto& r : roots) {
+                const int v = r.second;
+                subtrees.push_back(make_int2(v - size[v] + 1, v));
+                for (int w = v - size[v] + 1; w <= v; w++) s->in_sub[w] = 1;
+            }
+        }
+    }
+    s->n_subtrees = (int)subtrees.size();
     std::vector<AsmItem> asm_items;
     std::vector<PanelItem> panel_items;
     std::vector<SchurItem> schur_items;
@@ -794,13 +865,17 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     std::vector<int> top_ranges, top_slot, cdone_init(P.nnodes, 1 << 30);
     s->ltop = P.nlevels;
     if (s->use_top) {
+        std::vector<int> cnt(P.nlevels, 0); // fronts per level outside the subtree region
+        for (int v = 0; v < P.nnodes; v++)
+            if (!s->in_sub[v]) cnt[P.level[v]]++;
         int l = P.nlevels;
-        while (l > 0 && P.level_ptr[l] - P.level_ptr[l - 1] <= s->top_max_nodes) l--;
+        while (l > 0 && cnt[l - 1] <= s->top_max_nodes) l--;
         if (P.nlevels - l >= 4) s->ltop = l; // worth it only when a real chain of levels is replaced
     }
     for (int l = s->ltop; l < P.nlevels; l++)
         for (int e = P.level_ptr[l]; e < P.level_ptr[l + 1]; e++) {
             const int v = P.level_nodes[e];
+            if (s->in_sub[v]) continue; // done by the subtree kernel before the persistent sweep starts (counter pre-set)
             const int u = P.u[v], pv = P.p[v];
             const int nsl = std::max(1, (u + B200_SLICE - 1) / B200_SLICE);
             cdone_init[v] = 0;
@@ -812,9 +887,15 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
                 for (int c = P.child_ptr[v]; c < P.child_ptr[v + 1]; c++) {
                     const int ch = P.child_idx[c];
                     const int* rel = &P.rel[P.rows_ptr[ch]];
+                    // B200_TOP_REC ints per (item, child): see sweep_top.cuh
                     top_ranges.push_back((int)(std::lower_bound(rel, rel + P.u[ch], pv) - rel));
                     top_ranges.push_back((int)(std::lower_bound(rel, rel + P.u[ch], pv + r0) - rel));
                     top_ranges.push_back((int)(std::lower_bound(rel, rel + P.u[ch], pv + r0 + nrows) - rel));
+                    top_ranges.push_back(ch);
+                    top_ranges.push_back((int)(uint32_t)((uint64_t)P.rows_ptr[ch] & 0xffffffffu));
+                    top_ranges.push_back((int)(uint32_t)((uint64_t)P.rows_ptr[ch] >> 32));
+                    top_ranges.push_back(std::max(1, (P.u[ch] + B200_SLICE - 1) / B200_SLICE));
+                    top_ranges.push_back(0);
                 }
             }
             nslots += nsl;
@@ -866,6 +947,7 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     UP(d_big_slot, big_slot);
     UP(d_asm_ranges, asm_ranges);
     UP(d_big_ranges, big_ranges);
+    UP(d_subtrees, subtrees);
     UP(d_top_items, top_items);
     UP(d_top_ranges, top_ranges);
     UP(d_top_slot, top_slot);
@@ -918,6 +1000,10 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     CUDA_TRY(cudaMemset(s->d_epoch, 0, sizeof(int)), B200_ERROR_CUDA_MALLOC);
     CUDA_TRY(cudaMemset(s->d_abort, 0, sizeof(int)), B200_ERROR_CUDA_MALLOC);
 #undef DM
+    if (s->want_trace && s->n_top_items > 0) { // must precede the first graph capture of the sweep (the pointer is a kernel argument)
+        CUDA_TRY(cudaMalloc((void**)&s->d_trace, 8 * (size_t)s->n_top_items * sizeof(unsigned long long)), B200_ERROR_CUDA_MALLOC);
+        CUDA_TRY(cudaMemset(s->d_trace, 0, 8 * (size_t)s->n_top_items * sizeof(unsigned long long)), B200_ERROR_CUDA_MALLOC);
+    }
     CUDA_TRY(cudaMallocHost((void**)&s->h_norms, 4 * sizeof(double)), B200_ERROR_MALLOC);
     CUDA_TRY(cudaMallocHost((void**)&s->h_counters, 16 * sizeof(int)), B200_ERROR_MALLOC);
 
@@ -937,10 +1023,16 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     if (s->n_top_items > 0) {
         CUDA_TRY(cudaFuncSetAttribute(k_fwd_top, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_TOP_SMEM), B200_ERROR_NOT_AVAILABLE);
         CUDA_TRY(cudaFuncSetAttribute(k_bwd_top, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_TOP_SMEM), B200_ERROR_NOT_AVAILABLE);
+        CUDA_TRY(cudaFuncSetAttribute(k_fwd_top2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_TOP_SMEM), B200_ERROR_NOT_AVAILABLE);
+        CUDA_TRY(cudaFuncSetAttribute(k_bwd_top2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_TOP_SMEM), B200_ERROR_NOT_AVAILABLE);
         int occ_f = 0, occ_b = 0, nsm = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_fwd_top, 256, B200_TOP_SMEM), B200_ERROR_NOT_AVAILABLE);
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_bwd_top, 256, B200_TOP_SMEM), B200_ERROR_NOT_AVAILABLE);
         CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device), B200_ERROR_NOT_AVAILABLE);
+        if (s->top_variant >= 2) {
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_fwd_top2, 256, B200_TOP_SMEM), B200_ERROR_NOT_AVAILABLE);
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_bwd_top2, 256, B200_TOP_SMEM), B200_ERROR_NOT_AVAILABLE);
+        }
         int occ = std::min(occ_f, occ_b);
         if (occ < 1) s->n_top_items = 0; // cannot guarantee co-residency: fall back to per-level launches
         s->top_grid = std::max(1, std::min(s->n_top_items, occ * nsm));
@@ -1282,6 +1374,29 @@ int32_t solver_b200_get_stats(struct InterfaceB200* s, double* out, int32_t n_ou
     v[B200_STAT_LAST_BACKWARD_ERROR] = s->last_backward_error;
     for (int i = 0; i < n_out && i < B200_STAT_COUNT; i++) out[i] = v[i];
     return B200_SUCCESSFUL_EXIT;
+}
+
+// debug/profiling: per-item timestamps (ns, %globaltimer) of the last persistent sweeps, 4 per item (start, dependency
+// satisfied, end, unused), forward items first then backward; item descriptors (node, level, slice, nrows) in `desc`.
+// Needs set_option("trace", 1) before initialize.  Returns the number of items (<= cap) or a negative value.
+int32_t solver_b200_debug_trace(struct InterfaceB200* s, unsigned long long* out, int32_t* desc, int32_t cap) {
+    if (!s || !s->d_trace || !s->initialized) return -1;
+    cudaSetDevice(s->device);
+    cudaStreamSynchronize(s->stream);
+    const int n = std::min(cap, s->n_top_items);
+    if (out) {
+        cudaMemcpy(out, s->d_trace, 4 * (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+        cudaMemcpy(out + 4 * (size_t)n, s->d_trace + 4 * (size_t)s->n_top_items, 4 * (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    }
+    if (desc) {
+        std::vector<SolveItem> items(s->n_top_items);
+        cudaMemcpy(items.data(), s->d_top_items, items.size() * sizeof(SolveItem), cudaMemcpyDeviceToHost);
+        for (int i = 0; i < n; i++) {
+            desc[4 * i] = items[i].node, desc[4 * i + 1] = s->plan.level[items[i].node];
+            desc[4 * i + 2] = items[i].slice, desc[4 * i + 3] = items[i].nrows;
+        }
+    }
+    return s->n_top_items;
 }
 
 int32_t solver_b200_debug_copy_factors(struct InterfaceB200* s, double* fac, int64_t fac_len, double* dinv,
