@@ -76,6 +76,8 @@ struct InterfaceB200 {
     int opt_panel_width = 64, opt_nd_leaf = 96;
     int use_graph = 1;
     int schur_variant = 1; // 0 = FMA, 1 = DMMA
+    int use_leaf_reg = 1;    // leaf fronts of order <= 32: k_leaf_reg (one warp per front, registers only)
+    int panel_row_max = 160; // launches of at most this many 128-row panel items use k_panel_row (one warp per four rows)
     int panel_variant = 1; // 0 = k_panel (32-row tiles, barrier per column), 1 = k_panel_warp (thread per row, 128-row items)
     int use_fused = 1;     // fronts with f <= B200_FUSED_MAXF go through k_front_fused
     int fused_maxf = 48;   // fronts above this order take the multi-kernel path (measured optimum at config 2)
@@ -107,6 +109,7 @@ struct InterfaceB200 {
     std::vector<char> in_sub;   // per front: handled by a subtree CTA in the solve phase
     int n_subtrees = 0;
     int2* d_subtrees = nullptr; // (first, root) node ranges, largest first
+    ChildRec* d_child_rec = nullptr;
     unsigned long long* d_trace = nullptr; // optional per-item timestamps of the persistent sweeps (option "trace")
     int want_trace = 0;
     int top_variant = 2;      // 1 = k_fwd_top/k_bwd_top, 2 = k_fwd_top2/k_bwd_top2 (descriptors and indices loaded before the dependency wait)
@@ -188,6 +191,7 @@ void release_device(InterfaceB200* s) {
     dfree(s->d_asm), dfree(s->d_panel), dfree(s->d_schur);
     dfree(s->d_trace);
     dfree(s->d_subtrees);
+    dfree(s->d_child_rec);
     dfree(s->d_big_items), dfree(s->d_big_slot), dfree(s->d_top_items), dfree(s->d_top_ranges), dfree(s->d_top_slot),
     dfree(s->d_cdone), dfree(s->d_xdone), dfree(s->d_epoch), dfree(s->d_abort), dfree(s->d_asm_ranges), dfree(s->d_big_ranges), dfree(s->d_big_scratch), dfree(s->d_big_tickets);
     dfree(s->d_a_src), dfree(s->d_a_dst), dfree(s->d_a_scl);
@@ -375,7 +379,11 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
             if (nn > 0) {
                 // register-resident LU (one warp per 8 front columns): wins when the launch is latency bound (few fronts),
                 // loses to the leaner shared-memory kernel when tens of thousands of fronts compete for thread slots
-                if (FC_MAXF[c] <= 64 && (s->fused_variant == 1 || (s->fused_variant == 2 && nn <= s->fused_w8_max)))
+                if (l == 0 && s->use_leaf_reg && FC_MAXF[c] <= 32) // leaves (level 0 = no children), whole front in one warp's registers
+                    k_leaf_reg<<<(nn + B200_LEAF_WARPS - 1) / B200_LEAF_WARPS, 32 * B200_LEAF_WARPS, 0, s->stream>>>(
+                        s->d_fact_nodes + fp[c], nn, s->d_nodes, s->d_fac, s->d_cb, s->d_lperm, s->d_upiv, s->d_amax, s->pivot_eps,
+                        s->d_counters);
+                else if (FC_MAXF[c] <= 64 && (s->fused_variant == 1 || (s->fused_variant == 2 && nn <= s->fused_w8_max)))
                     k_front_fused_w8<<<nn, 32 * ((FC_MAXF[c] + 7) / 8), lv.fused_smem[(size_t)l * NFC + c], s->stream>>>(
                         s->d_fact_nodes + fp[c], s->d_nodes, s->d_child_idx, s->d_rel, s->d_fac, s->d_cb, s->d_lperm,
                         s->d_upiv, s->d_amax, s->pivot_eps, s->d_counters);
@@ -413,6 +421,8 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
         if (np > 0) {
             if (s->panel_variant == 2)
                 k_panel_mma<<<np, 128, B200_PM_SMEM, s->stream>>>(s->d_panel + lv.panel_ptr[l], s->d_nodes, s->d_fac, s->d_lperm);
+            else if (s->panel_variant == 1 && np <= s->panel_row_max) // few rows: the launch is latency bound
+                k_panel_row<<<np * 4, 256, 0, s->stream>>>(s->d_panel + lv.panel_ptr[l], s->d_nodes, s->d_fac, s->d_lperm);
             else if (s->panel_variant == 1)
                 k_panel_warp<<<np, 128, B200_PW_SMEM, s->stream>>>(s->d_panel + lv.panel_ptr[l], s->d_nodes, s->d_fac, s->d_lperm);
             else
@@ -494,7 +504,7 @@ int enqueue_sweep_levels(InterfaceB200* s, int* launches) {
     int cnt = 0;
     const int lsplit = s->n_top_items > 0 ? s->ltop : P.nlevels; // levels >= lsplit run in the persistent kernels
     if (s->n_subtrees > 0) {
-        k_fwd_subtree<<<s->n_subtrees, B200_ST_THREADS, 0, s->stream>>>(s->d_subtrees, s->d_nodes, s->d_child_idx, s->d_rel, s->d_fac, s->d_dinv,
+        k_fwd_subtree<<<s->n_subtrees, B200_ST_THREADS, 0, s->stream>>>(s->d_subtrees, s->d_nodes, s->d_child_rec, s->d_rel, s->d_fac, s->d_dinv,
                                                                          s->d_lperm, s->d_y, s->d_z, s->d_wv);
         cnt++;
     }
@@ -657,6 +667,8 @@ struct InterfaceB200* solver_b200_new(void) {
     if ((e = getenv("B200_NO_GRAPH")) && atoi(e)) s->use_graph = 0;
     if ((e = getenv("B200_SCHUR_VARIANT"))) s->schur_variant = atoi(e);
     if ((e = getenv("B200_PANEL_VARIANT"))) s->panel_variant = atoi(e);
+    if ((e = getenv("B200_PANEL_ROW_MAX"))) s->panel_row_max = atoi(e);
+    if ((e = getenv("B200_USE_LEAF_REG"))) s->use_leaf_reg = atoi(e);
     if ((e = getenv("B200_OVERLAP_INVERT"))) s->overlap_invert = atoi(e);
     if ((e = getenv("B200_LOOKAHEAD"))) s->lookahead = atoi(e);
     if ((e = getenv("B200_INVERT_VARIANT"))) s->invert_variant = atoi(e);
@@ -697,6 +709,8 @@ int32_t solver_b200_set_option(struct InterfaceB200* s, const char* key, double 
     else if (k == "use_graph") s->use_graph = value != 0.0;
     else if (k == "schur_variant") s->schur_variant = (int)value;
     else if (k == "panel_variant") s->panel_variant = (int)value;
+    else if (k == "panel_row_max") s->panel_row_max = (int)value;
+    else if (k == "use_leaf_reg") s->use_leaf_reg = value != 0.0;
     else if (k == "overlap_invert") s->overlap_invert = (int)value;
     else if (k == "lookahead") s->lookahead = (int)value;
     else if (k == "invert_variant") s->invert_variant = (int)value;
@@ -790,7 +804,7 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
         std::vector<char> elig(P.nnodes, 1);
         for (int v = 0; v < P.nnodes; v++) { // children precede parents: ent/size/elig of v are final when v is visited
             ent[v] += (int64_t)P.p[v] * (P.p[v] + 2 * (int64_t)P.u[v]);
-            if (P.p[v] + P.u[v] > s->subtree_maxf || P.p[v] > B200_ST_PMAX || ent[v] > s->subtree_budget) elig[v] = 0;
+            if (P.p[v] + P.u[v] > std::min(s->subtree_maxf, B200_ST_FMAX) || P.p[v] > B200_ST_PMAX || ent[v] > s->subtree_budget) elig[v] = 0;
             const int par = P.parent[v];
             if (par >= 0) {
                 ent[par] += ent[v], size[par] += size[v];
@@ -948,6 +962,14 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     UP(d_asm_ranges, asm_ranges);
     UP(d_big_ranges, big_ranges);
     UP(d_subtrees, subtrees);
+    {
+        std::vector<ChildRec> child_rec(P.child_idx.size());
+        for (size_t e = 0; e < P.child_idx.size(); e++) {
+            const int c = P.child_idx[e];
+            child_rec[e].c = c, child_rec[e].u = P.u[c], child_rec[e].rows_ptr = P.rows_ptr[c];
+        }
+        UP(d_child_rec, child_rec);
+    }
     UP(d_top_items, top_items);
     UP(d_top_ranges, top_ranges);
     UP(d_top_slot, top_slot);
