@@ -110,9 +110,14 @@ struct InterfaceB200 {
     int n_subtrees = 0;
     int2* d_subtrees = nullptr; // (first, root) node ranges, largest first
     ChildRec* d_child_rec = nullptr;
+    bool fac_cleared = false;      // the host entry points clear the factor arena on the side stream, under their H2D copy
+    int invert_all = 0;            // 1: explicit pivot-block inverses for every front (the subtree kernels do not need them)
+    std::vector<int> inv_skip_ptr; // NIC+1: fronts whose inverses are skipped, by class, inside d_inv_skip
+    int* d_inv_skip = nullptr;
     unsigned long long* d_trace = nullptr; // optional per-item timestamps of the persistent sweeps (option "trace")
     int want_trace = 0;
-    int top_variant = 2;      // 1 = k_fwd_top/k_bwd_top, 2 = k_fwd_top2/k_bwd_top2 (descriptors and indices loaded before the dependency wait)
+    int *d_node_slot = nullptr, *d_bdone = nullptr; // k_bwd_top3: scratch slot base per front, partial-products-done counters
+    int top_variant = 3;      // 1 = k_fwd_top/k_bwd_top, 2 = k_fwd_top2/k_bwd_top2 (descriptors and indices loaded before the dependency wait), 3 = k_fwd_top2/k_bwd_top3 (children finish their parent: one hop per level)
     int use_top = 1, ltop = 0, n_top_items = 0, top_grid = 0, n_slots = 0;
     bool sweep_dirty = false;          // a persistent sweep aborted: counters must be re-armed
     std::vector<int> cdone_init;       // host copy of the initial completion counters
@@ -149,6 +154,7 @@ struct InterfaceB200 {
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaStream_t side = nullptr;          // low-priority side stream: pivot-block inverses of the wide bottom of the tree
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr; //   run there, under the latency-bound chain of top-of-tree launches
+    cudaEvent_t ev_clr0 = nullptr, ev_clr1 = nullptr; // fork / join of the factor-arena clear that runs under the H2D copy
     cudaEvent_t ev_la = nullptr, ev_rest = nullptr;   // look-ahead fork / join
     int overlap_invert = 0;
     int fused_variant = 2;  // 0 = shared-memory LU (k_front_fused), 1 = register-resident (k_front_fused_w8) for f <= 64,
@@ -191,7 +197,9 @@ void release_device(InterfaceB200* s) {
     dfree(s->d_asm), dfree(s->d_panel), dfree(s->d_schur);
     dfree(s->d_trace);
     dfree(s->d_subtrees);
+    dfree(s->d_node_slot), dfree(s->d_bdone);
     dfree(s->d_child_rec);
+    dfree(s->d_inv_skip);
     dfree(s->d_big_items), dfree(s->d_big_slot), dfree(s->d_top_items), dfree(s->d_top_ranges), dfree(s->d_top_slot),
     dfree(s->d_cdone), dfree(s->d_xdone), dfree(s->d_epoch), dfree(s->d_abort), dfree(s->d_asm_ranges), dfree(s->d_big_ranges), dfree(s->d_big_scratch), dfree(s->d_big_tickets);
     dfree(s->d_a_src), dfree(s->d_a_dst), dfree(s->d_a_scl);
@@ -487,6 +495,12 @@ void k_fwd_top_launch(InterfaceB200* s) {
                                                             s->d_epoch, s->d_abort);
 }
 void k_bwd_top_launch(InterfaceB200* s) {
+    if (s->top_variant >= 3) {
+        k_bwd_top3<<<s->top_grid, 256, B200_TOP3_SMEM, s->stream>>>(s->d_top_items, s->n_top_items, s->d_nodes, s->d_rows, s->d_fac, s->d_dinv,
+                                                                  s->d_z, s->d_xp, s->d_big_scratch, s->d_node_slot, s->d_bdone, s->d_epoch,
+                                                                  s->d_abort, s->d_trace ? s->d_trace + 4 * (size_t)s->n_top_items : nullptr);
+        return;
+    }
     if (s->top_variant >= 2) {
         k_bwd_top2<<<s->top_grid, 256, B200_TOP_SMEM, s->stream>>>(s->d_top_items, s->n_top_items, s->d_nodes, s->d_rows, s->d_fac, s->d_dinv,
                                                                  s->d_z, s->d_xp, s->d_big_scratch, s->d_big_tickets, s->d_top_slot,
@@ -628,11 +642,15 @@ static bool create_streams(InterfaceB200* s) {
     if (cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) != cudaSuccess) return false;
     if (cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming) != cudaSuccess) return false;
     if (cudaEventCreateWithFlags(&s->ev_la, cudaEventDisableTiming) != cudaSuccess) return false;
+    if (cudaEventCreateWithFlags(&s->ev_clr0, cudaEventDisableTiming) != cudaSuccess) return false;
+    if (cudaEventCreateWithFlags(&s->ev_clr1, cudaEventDisableTiming) != cudaSuccess) return false;
     if (cudaEventCreateWithFlags(&s->ev_rest, cudaEventDisableTiming) != cudaSuccess) return false;
     return true;
 }
 static void destroy_streams(InterfaceB200* s) {
     if (s->ev_fork) cudaEventDestroy(s->ev_fork), s->ev_fork = nullptr;
+    if (s->ev_clr0) cudaEventDestroy(s->ev_clr0), s->ev_clr0 = nullptr;
+    if (s->ev_clr1) cudaEventDestroy(s->ev_clr1), s->ev_clr1 = nullptr;
     if (s->ev_join) cudaEventDestroy(s->ev_join), s->ev_join = nullptr;
     if (s->ev_la) cudaEventDestroy(s->ev_la), s->ev_la = nullptr;
     if (s->ev_rest) cudaEventDestroy(s->ev_rest), s->ev_rest = nullptr;
@@ -721,6 +739,7 @@ int32_t solver_b200_set_option(struct InterfaceB200* s, const char* key, double 
     else if (k == "top_variant") s->top_variant = (int)value;
     else if (k == "trace") s->want_trace = value != 0.0;
     else if (k == "use_subtree") s->use_subtree = value != 0.0;
+    else if (k == "invert_all") s->invert_all = value != 0.0;
     else if (k == "subtree_maxf") s->subtree_maxf = std::max(1, (int)value);
     else if (k == "subtree_budget") s->subtree_budget = std::max(1, (int)value);
     else if (k == "diag_variant") s->diag_variant = (int)value;
@@ -876,7 +895,7 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
 
     // persistent top-of-tree sweep: all levels above the last "wide" level (more than 96 fronts)
     std::vector<SolveItem> top_items;
-    std::vector<int> top_ranges, top_slot, cdone_init(P.nnodes, 1 << 30);
+    std::vector<int> top_ranges, top_slot, cdone_init(P.nnodes, 1 << 30), node_slot(P.nnodes, -1);
     s->ltop = P.nlevels;
     if (s->use_top) {
         std::vector<int> cnt(P.nlevels, 0); // fronts per level outside the subtree region
@@ -893,6 +912,7 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
             const int u = P.u[v], pv = P.p[v];
             const int nsl = std::max(1, (u + B200_SLICE - 1) / B200_SLICE);
             cdone_init[v] = 0;
+            node_slot[v] = nslots;
             for (int sl = 0; sl < nsl; sl++) {
                 const int r0 = sl * B200_SLICE;
                 const int nrows = std::max(0, std::min(B200_SLICE, u - r0));
@@ -946,6 +966,7 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
                     int cls = 0;
                     while (cls < NIC - 1 && P.p[v] > IC_MAXP[cls]) cls++;
                     const bool early = s->lv.inv_split >= 0 && P.level[v] < s->lv.inv_split;
+                    if (s->in_sub[v] && !s->invert_all) continue; // the subtree kernels substitute with L11 / U11 directly
                     if (cls == c && early == (pass == 0)) inv_nodes.push_back(v);
                 }
                 if (pass == 0) s->lv.inv_early[c] = (int)inv_nodes.size() - s->lv.inv_ptr[c];
@@ -953,6 +974,18 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
             s->lv.inv_ptr[c + 1] = (int)inv_nodes.size();
         }
         UP(d_inv_nodes, inv_nodes);
+        // the fronts skipped above, by class: their inverses are only computed on demand (solver_b200_debug_copy_factors)
+        std::vector<int> skip_nodes;
+        s->inv_skip_ptr.assign(NIC + 1, 0);
+        for (int c = 0; c < NIC; c++) {
+            for (int v = 0; v < P.nnodes; v++) {
+                int cls = 0;
+                while (cls < NIC - 1 && P.p[v] > IC_MAXP[cls]) cls++;
+                if (cls == c && s->in_sub[v] && !s->invert_all) skip_nodes.push_back(v);
+            }
+            s->inv_skip_ptr[c + 1] = (int)skip_nodes.size();
+        }
+        UP(d_inv_skip, skip_nodes);
     }
     UP(d_asm, asm_items);
     UP(d_panel, panel_items);
@@ -973,6 +1006,7 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     UP(d_top_items, top_items);
     UP(d_top_ranges, top_ranges);
     UP(d_top_slot, top_slot);
+    UP(d_node_slot, node_slot);
     UP(d_cdone, cdone_init);
     s->cdone_init = cdone_init;
     s->n_slots = nslots;
@@ -1016,6 +1050,8 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     CUDA_TRY(cudaMemset(s->d_big_tickets, 0, (size_t)std::max(nslots, 1) * sizeof(int)), B200_ERROR_CUDA_MALLOC);
     DM(d_norms, 4, double);
     DM(d_xdone, P.nnodes, int);
+    DM(d_bdone, P.nnodes, int);
+    CUDA_TRY(cudaMemset(s->d_bdone, 0, (size_t)std::max(P.nnodes, 1) * sizeof(int)), B200_ERROR_CUDA_MALLOC);
     DM(d_epoch, 1, int);
     DM(d_abort, 1, int);
     CUDA_TRY(cudaMemset(s->d_xdone, 0, (size_t)std::max(P.nnodes, 1) * sizeof(int)), B200_ERROR_CUDA_MALLOC);
@@ -1047,6 +1083,7 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
         CUDA_TRY(cudaFuncSetAttribute(k_bwd_top, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_TOP_SMEM), B200_ERROR_NOT_AVAILABLE);
         CUDA_TRY(cudaFuncSetAttribute(k_fwd_top2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_TOP_SMEM), B200_ERROR_NOT_AVAILABLE);
         CUDA_TRY(cudaFuncSetAttribute(k_bwd_top2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_TOP_SMEM), B200_ERROR_NOT_AVAILABLE);
+        CUDA_TRY(cudaFuncSetAttribute(k_bwd_top3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_TOP3_SMEM), B200_ERROR_NOT_AVAILABLE);
         int occ_f = 0, occ_b = 0, nsm = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_fwd_top, 256, B200_TOP_SMEM), B200_ERROR_NOT_AVAILABLE);
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_bwd_top, 256, B200_TOP_SMEM), B200_ERROR_NOT_AVAILABLE);
@@ -1055,6 +1092,8 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_fwd_top2, 256, B200_TOP_SMEM), B200_ERROR_NOT_AVAILABLE);
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_bwd_top2, 256, B200_TOP_SMEM), B200_ERROR_NOT_AVAILABLE);
         }
+        if (s->top_variant >= 3)
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_bwd_top3, 256, B200_TOP3_SMEM), B200_ERROR_NOT_AVAILABLE);
         int occ = std::min(occ_f, occ_b);
         if (occ < 1) s->n_top_items = 0; // cannot guarantee co-residency: fall back to per-level launches
         s->top_grid = std::max(1, std::min(s->n_top_items, occ * nsm));
@@ -1094,6 +1133,7 @@ int32_t solver_b200_factorize_device(struct InterfaceB200* s, const double* d_va
     if (s->sweep_dirty) { // re-arm the dependency counters of the persistent sweep after an aborted solve
         CUDA_TRY(cudaMemcpyAsync(s->d_cdone, s->cdone_init.data(), s->cdone_init.size() * sizeof(int), cudaMemcpyHostToDevice, s->stream), B200_ERROR_CUDA_MEMCPY);
         CUDA_TRY(cudaMemsetAsync(s->d_xdone, 0, (size_t)std::max(P.nnodes, 1) * sizeof(int), s->stream), B200_ERROR_CUDA_MEMCPY);
+        CUDA_TRY(cudaMemsetAsync(s->d_bdone, 0, (size_t)std::max(P.nnodes, 1) * sizeof(int), s->stream), B200_ERROR_CUDA_MEMCPY);
         CUDA_TRY(cudaMemsetAsync(s->d_epoch, 0, sizeof(int), s->stream), B200_ERROR_CUDA_MEMCPY);
         CUDA_TRY(cudaMemsetAsync(s->d_abort, 0, sizeof(int), s->stream), B200_ERROR_CUDA_MEMCPY);
         CUDA_TRY(cudaMemsetAsync(s->d_big_tickets, 0, (size_t)std::max(s->n_slots, 1) * sizeof(int), s->stream), B200_ERROR_CUDA_MEMCPY);
@@ -1103,7 +1143,9 @@ int32_t solver_b200_factorize_device(struct InterfaceB200* s, const double* d_va
     if (d_values != s->d_vals)
         CUDA_TRY(cudaMemcpyAsync(s->d_vals, d_values, (size_t)s->nnz_in * sizeof(double), cudaMemcpyDeviceToDevice, s->stream), B200_ERROR_CUDA_MEMCPY);
     cudaEventRecord(s->ev[0], s->stream);
-    CUDA_TRY(cudaMemsetAsync(s->d_fac, 0, (size_t)P.fac_size * sizeof(double), s->stream), B200_ERROR_NUM_FACTORIZATION + 1);
+    if (!s->fac_cleared)
+        CUDA_TRY(cudaMemsetAsync(s->d_fac, 0, (size_t)P.fac_size * sizeof(double), s->stream), B200_ERROR_NUM_FACTORIZATION + 1);
+    s->fac_cleared = false;
     CUDA_TRY(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(int), s->stream), B200_ERROR_NUM_FACTORIZATION + 1);
     CUDA_TRY(cudaMemsetAsync(s->d_amax, 0, sizeof(unsigned long long), s->stream), B200_ERROR_NUM_FACTORIZATION + 1);
     k_scatter_values<<<grid_for(s->fnnz), 256, 0, s->stream>>>(s->fnnz, s->d_a_src, s->d_a_dst, s->d_a_scl, s->d_vals, s->d_fac, s->d_amax);
@@ -1137,6 +1179,20 @@ int32_t solver_b200_factorize_device(struct InterfaceB200* s, const double* d_va
     return B200_SUCCESSFUL_EXIT;
 }
 
+// host entry points: the factor arena (hundreds of MB) is cleared on the side stream WHILE the copy engine brings the new
+// values over PCIe on the main stream; the main stream then waits for the clear before the numeric kernels start
+static void clear_fac_under_h2d(InterfaceB200* s) {
+    if (!s->side || !s->ev_clr0 || !s->ev_clr1) return;
+    if (cudaEventRecord(s->ev_clr0, s->stream) != cudaSuccess) return; // (orders the clear after the previous solve's reads)
+    cudaStreamWaitEvent(s->side, s->ev_clr0, 0);
+    if (cudaMemsetAsync(s->d_fac, 0, (size_t)s->plan.fac_size * sizeof(double), s->side) != cudaSuccess) return;
+    cudaEventRecord(s->ev_clr1, s->side);
+    s->fac_cleared = true;
+}
+static void join_clear(InterfaceB200* s) {
+    if (s->fac_cleared) cudaStreamWaitEvent(s->stream, s->ev_clr1, 0);
+}
+
 int32_t solver_b200_factorize(struct InterfaceB200* s, int32_t* effective_matching, int32_t* effective_pivoting,
                               int32_t verbose, const double* values) {
     if (!s) return B200_ERROR_NULL_POINTER;
@@ -1144,7 +1200,9 @@ int32_t solver_b200_factorize(struct InterfaceB200* s, int32_t* effective_matchi
     if (!values) return B200_ERROR_NULL_POINTER;
     s->verbose = verbose;
     CUDA_TRY(cudaSetDevice(s->device), B200_ERROR_NOT_AVAILABLE);
+    clear_fac_under_h2d(s);
     CUDA_TRY(cudaMemcpyAsync(s->d_vals, values, (size_t)s->nnz_in * sizeof(double), cudaMemcpyHostToDevice, s->stream), B200_ERROR_CUDA_MEMCPY);
+    join_clear(s);
     int32_t rc = solver_b200_factorize_device(s, s->d_vals);
     if (effective_matching) *effective_matching = s->effective_matching;
     if (effective_pivoting) *effective_pivoting = s->effective_pivoting;
@@ -1208,7 +1266,9 @@ int32_t solver_b200_factorize_coo(struct InterfaceB200* s, int32_t* effective_ma
     if (!coo_values) return B200_ERROR_NULL_POINTER;
     s->verbose = verbose;
     CUDA_TRY(cudaSetDevice(s->device), B200_ERROR_NOT_AVAILABLE);
+    clear_fac_under_h2d(s);
     CUDA_TRY(cudaMemcpyAsync(s->d_coo_vals, coo_values, (size_t)s->nnz_coo * sizeof(double), cudaMemcpyHostToDevice, s->stream), B200_ERROR_CUDA_MEMCPY);
+    join_clear(s);
     int32_t rc = solver_b200_factorize_coo_device(s, s->d_coo_vals);
     if (effective_matching) *effective_matching = s->effective_matching;
     if (effective_pivoting) *effective_pivoting = s->effective_pivoting;
@@ -1426,6 +1486,15 @@ int32_t solver_b200_debug_copy_factors(struct InterfaceB200* s, double* fac, int
     if (!s) return B200_ERROR_NULL_POINTER;
     if (!s->factorized) return B200_ERROR_NEED_FACTORIZATION;
     CUDA_TRY(cudaSetDevice(s->device), B200_ERROR_NOT_AVAILABLE);
+    if (dinv && !s->inv_skip_ptr.empty() && s->inv_skip_ptr[NIC] > 0) { // inverses the solve phase never needed: compute them now
+        for (int c = 0; c < NIC; c++) {
+            const int nn = s->inv_skip_ptr[c + 1] - s->inv_skip_ptr[c];
+            if (nn > 0)
+                k_invert_col<<<nn, 2 * IC_MAXP[c], smem_invert(IC_MAXP[c]), s->stream>>>(s->d_inv_skip + s->inv_skip_ptr[c], s->d_nodes, s->d_fac,
+                                                                                          s->d_dinv, IC_MAXP[c], nn);
+        }
+        CUDA_TRY(cudaStreamSynchronize(s->stream), B200_ERROR_CUDA_SYNCHRONIZE);
+    }
     if (fac) CUDA_TRY(cudaMemcpy(fac, s->d_fac, std::min<int64_t>(fac_len, s->plan.fac_size) * sizeof(double), cudaMemcpyDeviceToHost), B200_ERROR_CUDA_MEMCPY);
     if (dinv) CUDA_TRY(cudaMemcpy(dinv, s->d_dinv, std::min<int64_t>(dinv_len, s->plan.dinv_size) * sizeof(double), cudaMemcpyDeviceToHost), B200_ERROR_CUDA_MEMCPY);
     if (lperm) CUDA_TRY(cudaMemcpy(lperm, s->d_lperm, std::min<int64_t>(n, s->n) * sizeof(int), cudaMemcpyDeviceToHost), B200_ERROR_CUDA_MEMCPY);

@@ -45,6 +45,7 @@ __device__ __forceinline__ bool wait_counter_ge(const int* counter, int target, 
 
 // dynamic shared memory: D (MAXP*MAXP) | panel slice (SLICE*MAXP) doubles
 #define B200_TOP_SMEM ((size_t)(B200_MAXP * B200_MAXP + B200_SLICE * B200_MAXP) * sizeof(double))
+#define B200_TOP3_SMEM ((size_t)(B200_SLICE * B200_MAXP) * sizeof(double)) // k_bwd_top3 stages the U slice only
 
 // per (item, child) record of the forward sweep, built on the host: head count, slice begin, slice end (positions in the
 // child's update list), child front, offset of the child's update list in rel[] / wv[] (two halves of an int64), number
@@ -458,6 +459,158 @@ __global__ void __launch_bounds__(256) k_bwd_top2(const SolveItem* __restrict__ 
             }
         }
         if (trace && tid == 0) trace[4 * (long long)itx + 2] = gtime();
+        __syncthreads(); // shared buffers are reused by the next item
+    }
+}
+
+// ---- v3 backward sweep (default): the CONSUMER finishes its parent's pivot block ---------------------------------------
+// In k_bwd_top/k_bwd_top2 a chain link costs two cross-CTA hops: slices -> (ticket) -> last slice reduces the partial
+// dot products, applies inv(U11), publishes x1 -> children.  The trace (profiles/r01m_trace_*) shows 7.5 us per level for
+// it against 3.5 us for the single-hop forward sweep.  Here a front's slices only publish their partial dot products
+// (release: fence + atomicAdd on bdone[front]); every slice CTA of every CHILD waits for that counter, loads the nsl x p
+// partials and redundantly evaluates x1 = inv(U11) (z - sum of partials) for its PARENT with inv(U11) held in registers
+// (loaded before the wait) -- the same arithmetic in the same order in every CTA, so the values are identical.  One hop
+// per level.  x1 is written to xp by slice 0 of each child before that child releases its own counter (so that deeper
+// descendants, which gather it from xp, see it) and by the front's own last slice (which covers fronts whose children
+// live outside the persistent region).
+__global__ void __launch_bounds__(256) k_bwd_top3(const SolveItem* __restrict__ items, int nitems, const NodeDev* __restrict__ nodes,
+                                                  const int* __restrict__ rows_all, const double* __restrict__ fac,
+                                                  const double* __restrict__ dinv, const double* __restrict__ zv,
+                                                  double* __restrict__ xp, double* __restrict__ scratch,
+                                                  const int* __restrict__ node_slot, int* __restrict__ bdone,
+                                                  const int* __restrict__ epoch_ptr, int* __restrict__ abort_flag,
+                                                  unsigned long long* __restrict__ trace) {
+    const int epoch = *epoch_ptr;
+    extern __shared__ double smt[];
+    double* Ps = smt; // this slice of the U panel: Ps[k * SLICE + r]
+    __shared__ double t[B200_MAXP], xpar[B200_MAXP], x2[B200_SLICE];
+    __shared__ int s_flag;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    const int gk = tid >> 2, gpart = tid & 3; // GEMV layout: four threads per row
+    for (int itx = nitems - 1 - (int)blockIdx.x; itx >= 0; itx -= gridDim.x) {
+        const SolveItem it = items[itx];
+        const NodeDev nd = nodes[it.node];
+        const int p = nd.p, u = nd.u;
+        const int nsl = slices_of(u);
+        {
+            const int r = tid & (B200_SLICE - 1), g = tid >> 7;
+            if (r < it.nrows) {
+                const double* src = fac + nd.Uoff + it.r0 + r;
+                for (int k = g; k < p; k += 2) cp_async8(Ps + k * B200_SLICE + r, src + (long long)k * u);
+            }
+        }
+        // ---- everything static is loaded before the wait: own row indices and slot, the parent's descriptor, z and inv(U11)
+        const int par = nd.pad;
+        const int rr = tid < it.nrows ? rows_all[nd.rows_ptr + it.r0 + tid] : -1;
+        const int slot = node_slot[it.node];
+        int pp = 0, nslp = 0, slotp = 0, c0p = 0;
+        double dreg[16], zp = 0.0;
+#pragma unroll
+        for (int q = 0; q < 16; q++) dreg[q] = 0.0;
+        if (par >= 0) {
+            const NodeDev pd = nodes[par];
+            pp = pd.p, nslp = slices_of(pd.u), slotp = node_slot[par], c0p = pd.c0;
+            const double* Dp = dinv + pd.Doff;
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                const int m = gk + gpart + 4 * q;
+                if (gk < pp && m < pp) dreg[q] = Dp[gk + (long long)m * pp];
+            }
+            if (tid < pp) zp = zv[c0p + tid];
+        }
+        if (tid == 0) {
+            if (trace) trace[4 * (long long)itx] = gtime();
+            s_flag = (par < 0) ? 1 : (wait_counter_ge(&bdone[par], epoch * nslp, abort_flag) ? 1 : 0);
+            if (trace) trace[4 * (long long)itx + 1] = gtime();
+        }
+        __syncthreads();
+        if (!s_flag) return;
+        // ---- one batch of dependent loads: the parent's partials and the solution entries of older ancestors
+        const bool in_par = rr >= c0p && rr < c0p + pp; // (pp == 0 without a parent)
+        double xv = 0.0;
+        if (rr >= 0 && !in_par) xv = __ldcg(xp + rr);
+        if (par >= 0) {
+            if (tid < pp) {
+                double sacc = zp;
+                const double* base = scratch + (long long)slotp * B200_MAXP + tid;
+                for (int sl0 = 0; sl0 < nslp; sl0 += 8) { // eight loads in flight, subtracted in slice order
+                    double v[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) v[q] = sl0 + q < nslp ? __ldcg(base + (long long)(sl0 + q) * B200_MAXP) : 0.0;
+#pragma unroll
+                    for (int q = 0; q < 8; q++) sacc -= v[q];
+                }
+                t[tid] = sacc;
+            }
+            __syncthreads();
+            {   // x1(parent) = inv(U11) t, four threads per row, inv(U11) from registers (same order as the shared-memory GEMV)
+                double sacc = 0.0;
+#pragma unroll
+                for (int q = 0; q < 16; q++) {
+                    const int m = gk + gpart + 4 * q;
+                    if (gk < pp && m < pp) sacc += dreg[q] * t[m];
+                }
+                sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+                sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+                if (gk < pp && gpart == 0) {
+                    xpar[gk] = sacc;
+                    if (it.slice == 0) xp[c0p + gk] = sacc; // visible to deeper descendants through this front's release
+                }
+            }
+            __syncthreads();
+        }
+        if (rr >= 0) x2[tid] = in_par ? xpar[rr - c0p] : xv;
+        cp_async_wait_all();
+        __syncthreads();
+        double* part = scratch + ((long long)slot + it.slice) * B200_MAXP;
+        for (int k = warp; k < p; k += nwarps) {
+            const double* col = Ps + k * B200_SLICE;
+            double sacc = 0.0;
+            for (int j = lane; j < it.nrows; j += 32) sacc += col[j] * x2[j];
+            for (int off = 16; off > 0; off >>= 1) sacc += __shfl_down_sync(0xffffffffu, sacc, off);
+            if (lane == 0) part[k] = sacc;
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const int old = atomicAdd(&bdone[it.node], 1); // release: the children of this front may start
+            s_flag = (old + 1 == epoch * nsl);
+            if (trace) trace[4 * (long long)itx + 2] = gtime();
+        }
+        __syncthreads();
+        if (s_flag) { // last slice of this front: write its own x1 (off the critical path of the children)
+            __threadfence();
+            if (tid < p) {
+                double sacc = zv[nd.c0 + tid];
+                const double* base = scratch + (long long)slot * B200_MAXP + tid;
+                for (int sl0 = 0; sl0 < nsl; sl0 += 8) {
+                    double v[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) v[q] = sl0 + q < nsl ? __ldcg(base + (long long)(sl0 + q) * B200_MAXP) : 0.0;
+#pragma unroll
+                    for (int q = 0; q < 8; q++) sacc -= v[q];
+                }
+                t[tid] = sacc;
+            }
+            const double* Dv = dinv + nd.Doff;
+            double dv[16];
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                const int m = gk + gpart + 4 * q;
+                dv[q] = (gk < p && m < p) ? Dv[gk + (long long)m * p] : 0.0;
+            }
+            __syncthreads();
+            double sacc = 0.0;
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                const int m = gk + gpart + 4 * q;
+                if (gk < p && m < p) sacc += dv[q] * t[m];
+            }
+            sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+            sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+            if (gk < p && gpart == 0) xp[nd.c0 + gk] = sacc;
+        }
         __syncthreads(); // shared buffers are reused by the next item
     }
 }
