@@ -198,14 +198,16 @@ void nd_component(NdCtx& c, std::vector<int>& verts, int id, int* out, std::vect
         local_min_degree(c, verts, id, out);
         return;
     }
-    // choose the separator level: smallest level whose two sides both keep >= 1/4 of the vertices
+    // choose the separator level: smallest level whose two sides both keep >= 1/3 of the vertices (the numeric phases are
+    // bound by the length of the dependent chain of separator panels: at config 2 the 1/4 rule gives the same flops but 73
+    // instead of 62 levels; fully balanced bisection gives 62 levels but 23 % more flops)
     int ls = -1;
     {
         long bestsz = -1;
         long bestbal = 0;
         for (int l = 1; l <= nl - 2; l++) {
             long before = lptr[l], sep = lptr[l + 1] - lptr[l], after = m - lptr[l + 1];
-            if (std::min(before, after) * 4 < m - sep) continue;
+            if (std::min(before, after) * 3 < m - sep) continue; // >= 1/3 on each side: same flops as 1/4, 15 % fewer tree levels
             long bal = std::labs(before - after);
             if (ls < 0 || sep < bestsz || (sep == bestsz && bal < bestbal)) {
                 ls = l;
