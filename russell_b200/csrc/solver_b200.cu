@@ -73,9 +73,11 @@ struct InterfaceB200 {
     int verbose = 0;
 
     // options
-    int opt_panel_width = 64, opt_nd_leaf = 96;
+    int opt_panel_width = 64, opt_nd_leaf = 32; // (nd_leaf: measured at config 2 -- 96: 8.68 ms, 48: 8.46, 32: 8.27, 24: 8.29, 12: 8.20 ms per factorization)
     int use_graph = 1;
     int schur_variant = 1; // 0 = FMA, 1 = DMMA
+    int relax_small = -1;                                // supernode amalgamation knobs of the host analysis (plan.hpp); < 0: defaults
+    double relax_z1 = -1.0, relax_z2 = -1.0, relax_z3 = -1.0;
     int use_leaf_reg = 1;    // leaf fronts of order <= 32: k_leaf_reg (one warp per front, registers only)
     int panel_row_max = 160; // launches of at most this many 128-row panel items use k_panel_row (one warp per four rows)
     int panel_variant = 1; // 0 = k_panel (32-row tiles, barrier per column), 1 = k_panel_warp (thread per row, 128-row items)
@@ -729,6 +731,10 @@ int32_t solver_b200_set_option(struct InterfaceB200* s, const char* key, double 
     else if (k == "panel_variant") s->panel_variant = (int)value;
     else if (k == "panel_row_max") s->panel_row_max = (int)value;
     else if (k == "use_leaf_reg") s->use_leaf_reg = value != 0.0;
+    else if (k == "relax_small") s->relax_small = (int)value;
+    else if (k == "relax_z1") s->relax_z1 = value;
+    else if (k == "relax_z2") s->relax_z2 = value;
+    else if (k == "relax_z3") s->relax_z3 = value;
     else if (k == "overlap_invert") s->overlap_invert = (int)value;
     else if (k == "lookahead") s->lookahead = (int)value;
     else if (k == "invert_variant") s->invert_variant = (int)value;
@@ -783,6 +789,10 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     AnalyzeOptions opt;
     opt.panel_width = s->opt_panel_width;
     opt.nd_leaf = s->opt_nd_leaf;
+    if (s->relax_small >= 0) opt.relax_small = s->relax_small;
+    if (s->relax_z1 >= 0.0) opt.relax_z1 = s->relax_z1;
+    if (s->relax_z2 >= 0.0) opt.relax_z2 = s->relax_z2;
+    if (s->relax_z3 >= 0.0) opt.relax_z3 = s->relax_z3;
     opt.verbose = verbose;
     if (ordering == B200_ORDERING_NONE) opt.ordering = ORDERING_NATURAL;
     else if (ordering == B200_ORDERING_AMD) opt.ordering = ORDERING_MINDEG;
