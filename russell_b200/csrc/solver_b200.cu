@@ -37,6 +37,7 @@ using namespace b200;
     } while (0)
 
 // front-size classes of the fused kernel: upper bound on f and CTA size; class NFC = "big" (multi-kernel path)
+#define B200_ASM_SMEM_MAX (160 * 1024) // a one-column tile of a front of order 20,000 still fits
 static const int NFC = 6;
 static const int FC_MAXF[NFC] = {16, 32, 48, 64, 96, B200_FUSED_MAXF};
 static const int FC_THREADS[NFC] = {32, 64, 64, 128, 256, 256};
@@ -64,6 +65,7 @@ struct LevelLists {
     std::vector<int> inv_early; // NIC: per class, how many fronts (the first ones of the class) lie below level inv_split
     int inv_split = -1;         // first level of the "narrow" top of the tree (few fronts per level); -1: no overlap
     std::vector<size_t> fused_smem; // per (level, class): dynamic shared memory of the fused launch
+    std::vector<size_t> asm_smem;   // per level: largest tile (bytes) of k_assemble_tile
 };
 
 struct InterfaceB200 {
@@ -78,6 +80,7 @@ struct InterfaceB200 {
     int schur_variant = 1; // 0 = FMA, 1 = DMMA
     int relax_small = -1;                                // supernode amalgamation knobs of the host analysis (plan.hpp); < 0: defaults
     double relax_z1 = -1.0, relax_z2 = -1.0, relax_z3 = -1.0;
+    int asm_variant = 1;     // 0 = k_assemble (read-modify-write in global memory), 1 = k_assemble_tile (tile in shared memory)
     int use_leaf_reg = 1;    // leaf fronts of order <= 32: k_leaf_reg (one warp per front, registers only)
     int panel_row_max = 160; // launches of at most this many 128-row panel items use k_panel_row (one warp per four rows)
     int panel_variant = 1; // 0 = k_panel (32-row tiles, barrier per column), 1 = k_panel_warp (thread per row, 128-row items)
@@ -241,6 +244,7 @@ void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::ve
     lv.solve_threads.assign(P.nlevels, 32);
     lv.solve_pmax.assign(P.nlevels, 1);
     lv.fused_smem.assign((size_t)P.nlevels * NFC, 0);
+    lv.asm_smem.assign(P.nlevels, 0);
     auto fclass = [&](int f) {
         if (!s->use_fused || f > s->fused_maxf) return NFC;
         for (int c = 0; c < NFC; c++)
@@ -314,6 +318,8 @@ void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::ve
                 int ntiles = (int)std::ceil(total / 4096.0);
                 ntiles = std::max(1, std::min(ntiles, f));
                 int tw = (f + ntiles - 1) / ntiles;
+                if (s->asm_variant == 1) tw = std::max(1, std::min(tw, B200_ASM_TILE / f)); // the tile lives in shared memory
+                lv.asm_smem[l] = std::max(lv.asm_smem[l], (size_t)tw * f * sizeof(double));
                 for (int t0 = 0; t0 < f; t0 += tw) {
                     const int t1 = std::min(f, t0 + tw);
                     asm_items.push_back({v, t0, t1, (int)asm_ranges.size()});
@@ -408,7 +414,11 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
         if (nbig == 0) continue;
         int na = lv.asm_ptr[l + 1] - lv.asm_ptr[l];
         if (na > 0) {
-            k_assemble<<<na, 256, 0, s->stream>>>(s->d_asm + lv.asm_ptr[l], s->d_nodes, s->d_child_idx, s->d_rel, s->d_asm_ranges, s->d_fac, s->d_cb);
+            if (s->asm_variant == 1 && lv.asm_smem[l] <= (size_t)B200_ASM_SMEM_MAX) // tile in shared memory
+                k_assemble_tile<<<na, 256, lv.asm_smem[l], s->stream>>>(s->d_asm + lv.asm_ptr[l], s->d_nodes, s->d_child_idx, s->d_rel,
+                                                                      s->d_asm_ranges, s->d_fac, s->d_cb);
+            else
+                k_assemble<<<na, 256, 0, s->stream>>>(s->d_asm + lv.asm_ptr[l], s->d_nodes, s->d_child_idx, s->d_rel, s->d_asm_ranges, s->d_fac, s->d_cb);
             cnt++;
         }
         if (s->diag_variant == 4)
@@ -689,6 +699,7 @@ struct InterfaceB200* solver_b200_new(void) {
     if ((e = getenv("B200_PANEL_VARIANT"))) s->panel_variant = atoi(e);
     if ((e = getenv("B200_PANEL_ROW_MAX"))) s->panel_row_max = atoi(e);
     if ((e = getenv("B200_USE_LEAF_REG"))) s->use_leaf_reg = atoi(e);
+    if ((e = getenv("B200_ASM_VARIANT"))) s->asm_variant = atoi(e);
     if ((e = getenv("B200_OVERLAP_INVERT"))) s->overlap_invert = atoi(e);
     if ((e = getenv("B200_LOOKAHEAD"))) s->lookahead = atoi(e);
     if ((e = getenv("B200_INVERT_VARIANT"))) s->invert_variant = atoi(e);
@@ -731,6 +742,7 @@ int32_t solver_b200_set_option(struct InterfaceB200* s, const char* key, double 
     else if (k == "panel_variant") s->panel_variant = (int)value;
     else if (k == "panel_row_max") s->panel_row_max = (int)value;
     else if (k == "use_leaf_reg") s->use_leaf_reg = value != 0.0;
+    else if (k == "asm_variant") s->asm_variant = (int)value;
     else if (k == "relax_small") s->relax_small = (int)value;
     else if (k == "relax_z1") s->relax_z1 = value;
     else if (k == "relax_z2") s->relax_z2 = value;
@@ -1087,6 +1099,7 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     CUDA_TRY(cudaFuncSetAttribute(k_panel_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_PM_SMEM), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_schur_fma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_schur_fma(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_schur_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024), B200_ERROR_NOT_AVAILABLE);
+    CUDA_TRY(cudaFuncSetAttribute(k_assemble_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, B200_ASM_SMEM_MAX), B200_ERROR_NOT_AVAILABLE);
     (void)W;
     if (s->n_top_items > 0) {
         CUDA_TRY(cudaFuncSetAttribute(k_fwd_top, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_TOP_SMEM), B200_ERROR_NOT_AVAILABLE);
@@ -1153,7 +1166,9 @@ int32_t solver_b200_factorize_device(struct InterfaceB200* s, const double* d_va
     if (d_values != s->d_vals)
         CUDA_TRY(cudaMemcpyAsync(s->d_vals, d_values, (size_t)s->nnz_in * sizeof(double), cudaMemcpyDeviceToDevice, s->stream), B200_ERROR_CUDA_MEMCPY);
     cudaEventRecord(s->ev[0], s->stream);
-    if (!s->fac_cleared)
+    if (s->fac_cleared) // the host entry point cleared the arena on the side stream, under its H2D copy: join
+        CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_clr1, 0), B200_ERROR_NUM_FACTORIZATION + 1);
+    else
         CUDA_TRY(cudaMemsetAsync(s->d_fac, 0, (size_t)P.fac_size * sizeof(double), s->stream), B200_ERROR_NUM_FACTORIZATION + 1);
     s->fac_cleared = false;
     CUDA_TRY(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(int), s->stream), B200_ERROR_NUM_FACTORIZATION + 1);
@@ -1199,9 +1214,6 @@ static void clear_fac_under_h2d(InterfaceB200* s) {
     cudaEventRecord(s->ev_clr1, s->side);
     s->fac_cleared = true;
 }
-static void join_clear(InterfaceB200* s) {
-    if (s->fac_cleared) cudaStreamWaitEvent(s->stream, s->ev_clr1, 0);
-}
 
 int32_t solver_b200_factorize(struct InterfaceB200* s, int32_t* effective_matching, int32_t* effective_pivoting,
                               int32_t verbose, const double* values) {
@@ -1212,7 +1224,6 @@ int32_t solver_b200_factorize(struct InterfaceB200* s, int32_t* effective_matchi
     CUDA_TRY(cudaSetDevice(s->device), B200_ERROR_NOT_AVAILABLE);
     clear_fac_under_h2d(s);
     CUDA_TRY(cudaMemcpyAsync(s->d_vals, values, (size_t)s->nnz_in * sizeof(double), cudaMemcpyHostToDevice, s->stream), B200_ERROR_CUDA_MEMCPY);
-    join_clear(s);
     int32_t rc = solver_b200_factorize_device(s, s->d_vals);
     if (effective_matching) *effective_matching = s->effective_matching;
     if (effective_pivoting) *effective_pivoting = s->effective_pivoting;
@@ -1278,7 +1289,6 @@ int32_t solver_b200_factorize_coo(struct InterfaceB200* s, int32_t* effective_ma
     CUDA_TRY(cudaSetDevice(s->device), B200_ERROR_NOT_AVAILABLE);
     clear_fac_under_h2d(s);
     CUDA_TRY(cudaMemcpyAsync(s->d_coo_vals, coo_values, (size_t)s->nnz_coo * sizeof(double), cudaMemcpyHostToDevice, s->stream), B200_ERROR_CUDA_MEMCPY);
-    join_clear(s);
     int32_t rc = solver_b200_factorize_coo_device(s, s->d_coo_vals);
     if (effective_matching) *effective_matching = s->effective_matching;
     if (effective_pivoting) *effective_pivoting = s->effective_pivoting;

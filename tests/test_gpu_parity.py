@@ -267,7 +267,9 @@ def test_factor_panels_match_host_walk_lower_and_saddle():
                                   {"diag_variant": 4, "use_fused": 0, "panel_width": 37}, {"diag_variant": 4, "use_fused": 0, "panel_width": 5}, {"lookahead": 1, "overlap_invert": 1}, {"invert_variant": 0},
                                   {"invert_variant": 1, "use_fused": 0, "panel_width": 37}, {"invert_variant": 1, "use_fused": 0, "panel_width": 5},
                                   {"panel_variant": 2, "use_fused": 0, "panel_width": 37}, {"panel_variant": 2, "use_fused": 0, "panel_width": 5},
-                                  {"diag_variant": 3, "use_fused": 0, "panel_width": 37}, {"diag_variant": 3, "use_fused": 0, "panel_width": 5}])
+                                  {"diag_variant": 3, "use_fused": 0, "panel_width": 37}, {"diag_variant": 3, "use_fused": 0, "panel_width": 5},
+                                  {"asm_variant": 0}, {"asm_variant": 0, "use_fused": 0, "panel_width": 13}, {"asm_variant": 1, "use_fused": 0, "panel_width": 13},
+                                  {"relax_z1": 0.6, "nd_leaf": 96}, {"invert_all": 1}])
 def test_kernel_variants_match_host_walk(opts):
     # every alternative code path (shared-memory vs register-resident pivot-block LU, fused vs multi-kernel fronts,
     # persistent vs per-level sweeps) against the scalar walk, on a grid with fronts above the fused limit
@@ -336,11 +338,13 @@ def test_round1_kernels_are_bit_identical_to_the_ones_they_replace():
     ax = ax * (1.0 + 0.3 * rng.standard_normal(len(ax)))
     coo = rb.CooMatrix.from_triplets(n, n, ai, aj, ax)
     for extra in ({}, {"use_fused": 0, "panel_width": 29}, {"panel_width": 64, "nd_leaf": 300}):
-        f0, p0 = _raw_factors(coo, dict(extra, panel_row_max=0, use_leaf_reg=0))
+        f0, p0 = _raw_factors(coo, dict(extra, panel_row_max=0, use_leaf_reg=0, asm_variant=0))
         f1, p1 = _raw_factors(coo, dict(extra, panel_row_max=100000, use_leaf_reg=0))
         f2, p2 = _raw_factors(coo, dict(extra, panel_row_max=0, use_leaf_reg=1))
         assert np.array_equal(p0, p1) and np.array_equal(f0, f1)
         assert np.array_equal(p0, p2) and np.array_equal(f0, f2)
+        f3, p3 = _raw_factors(coo, dict(extra, panel_row_max=0, use_leaf_reg=0, asm_variant=1))  # shared-memory extend-add tile
+        assert np.array_equal(p0, p3) and np.array_equal(f0, f3)
 
 
 @pytest.mark.parametrize("k,lower", [(150, False), (400, True)])
