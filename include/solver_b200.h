@@ -178,6 +178,17 @@ int32_t complex_solver_b200_factorize(struct InterfaceComplexB200 *solver, int32
                                       int32_t *effective_pivoting, int32_t verbose, const double *values /* Complex64[nnz] */);
 int32_t complex_solver_b200_solve(struct InterfaceComplexB200 *solver, double *x /* Complex64[ndim] out */,
                                   const double *rhs /* Complex64[ndim] */, int32_t verbose);
+/* COO-level boundary for complex triplets (the complex twin of solver_b200_initialize_coo / _factorize_coo): the triplet
+ * structure is analysed once; every refactorization ships the raw Complex64 triplet values and the duplicates are summed
+ * per CSR slot on the device, in their order of appearance (ComplexCsrMatrix::update_from_coo, csr_matrix.rs:431-459) */
+int32_t complex_solver_b200_initialize_coo(struct InterfaceComplexB200 *solver,
+                                           int32_t ordering, int32_t matching, int32_t pivoting,
+                                           double pivot_epsilon, int32_t refinement_nstep, double hybrid_memory_factor,
+                                           int32_t verbose, int32_t general_symmetric, int32_t positive_definite,
+                                           int32_t ndim, int32_t nnz_coo, const int32_t *indices_i, const int32_t *indices_j,
+                                           const double *values /* Complex64[nnz_coo] */);
+int32_t complex_solver_b200_factorize_coo(struct InterfaceComplexB200 *solver, int32_t *effective_matching,
+                                          int32_t *effective_pivoting, int32_t verbose, const double *coo_values);
 /* extensions, as for the real solver: device-resident variants, A x and residual through the SpMV kernel, stats and
  * options of the underlying order-2n real handle */
 int32_t complex_solver_b200_factorize_device(struct InterfaceComplexB200 *solver, const double *d_values);

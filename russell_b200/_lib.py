@@ -49,6 +49,9 @@ SIGNATURES = {
                                                p_i32, p_i32, p_f64]),
     "complex_solver_b200_factorize": (c_i32, [p_void, p_i32, p_i32, c_i32, p_f64]),
     "complex_solver_b200_solve": (c_i32, [p_void, p_f64, p_f64, c_i32]),
+    "complex_solver_b200_initialize_coo": (c_i32, [p_void, c_i32, c_i32, c_i32, c_f64, c_i32, c_f64, c_i32, c_i32, c_i32, c_i32,
+                                                   c_i32, p_i32, p_i32, p_f64]),
+    "complex_solver_b200_factorize_coo": (c_i32, [p_void, p_i32, p_i32, c_i32, p_f64]),
     "complex_solver_b200_factorize_device": (c_i32, [p_void, p_void]),
     "complex_solver_b200_solve_device": (c_i32, [p_void, p_void, p_void]),
     "complex_solver_b200_spmv": (c_i32, [p_void, p_f64, p_f64]),

@@ -117,11 +117,15 @@ class ComplexSolverB200:
 
     STAT_NAMES = SolverB200.STAT_NAMES
 
-    def __init__(self):
+    def __init__(self, coo_boundary=True):
+        """coo_boundary=True: triplet structure analysed once (complex_solver_b200_initialize_coo), every later factorize
+        ships the raw triplet values and the duplicates are summed on the device; False: the reference's data flow, host
+        ComplexCsrMatrix::update_from_coo on every call (complex_solver_cudss.rs:221)."""
         self._lib = _lib.load()
         self.solver = self._lib.complex_solver_b200_new()
         if not self.solver:
             raise StrError("c-code failed to allocate the B200 solver")
+        self.coo_boundary = bool(coo_boundary)
         self.csr = None
         self.initialized = False
         self.factorized = False
@@ -157,7 +161,8 @@ class ComplexSolverB200:
                 raise StrError("subsequent factorizations must use the same matrix (nnz differs)")
             if params is not None:
                 raise StrError("subsequent factorizations must not change LinSolParams")
-            self.csr.update_from_coo(mat)
+            if not self.coo_boundary:
+                self.csr.update_from_coo(mat)
         else:
             if mat.nrow != mat.ncol:
                 raise StrError("the matrix must be square")
@@ -168,8 +173,13 @@ class ComplexSolverB200:
             self.initialized_sym = mat.symmetric
             self.initialized_ndim = mat.nrow
             self.initialized_nnz = mat.nnz
-            self.csr = ComplexCsrMatrix.from_coo(mat)
+            if not self.coo_boundary:
+                self.csr = ComplexCsrMatrix.from_coo(mat)
         csr = self.csr
+        if self.coo_boundary:
+            coo_i = np.ascontiguousarray(mat.indices_i[: mat.nnz], dtype=np.int32)
+            coo_j = np.ascontiguousarray(mat.indices_j[: mat.nnz], dtype=np.int32)
+            coo_v = np.ascontiguousarray(mat.values[: mat.nnz], dtype=np.complex128)
         par = params if params is not None else LinSolParams()
         pivot_epsilon = par.pivot_epsilon if par.pivot_epsilon is not None else -1.0
         refinement_nstep = par.refinement_nstep if par.refinement_nstep is not None else -1
@@ -185,18 +195,28 @@ class ComplexSolverB200:
         positive_definite = 1 if (par.positive_definite and mat.symmetric == Sym.YesLower) else 0
         if not self.initialized:
             t0 = time.perf_counter_ns()
-            status = self._lib.complex_solver_b200_initialize(
-                self.solver, b200_ordering(par.ordering), b200_matching(par.matching), b200_pivoting(par.pivoting),
-                pivot_epsilon, refinement_nstep, hybrid, verbose, general_symmetric, positive_definite,
-                _to_i32(csr.nrow), ptr(csr.pointers, p_i32), ptr(csr.indices, p_i32), ptr(csr.values, p_f64))
+            if self.coo_boundary:
+                status = self._lib.complex_solver_b200_initialize_coo(
+                    self.solver, b200_ordering(par.ordering), b200_matching(par.matching), b200_pivoting(par.pivoting),
+                    pivot_epsilon, refinement_nstep, hybrid, verbose, general_symmetric, positive_definite,
+                    _to_i32(mat.nrow), _to_i32(mat.nnz), ptr(coo_i, p_i32), ptr(coo_j, p_i32), ptr(coo_v, p_f64))
+            else:
+                status = self._lib.complex_solver_b200_initialize(
+                    self.solver, b200_ordering(par.ordering), b200_matching(par.matching), b200_pivoting(par.pivoting),
+                    pivot_epsilon, refinement_nstep, hybrid, verbose, general_symmetric, positive_definite,
+                    _to_i32(csr.nrow), ptr(csr.pointers, p_i32), ptr(csr.indices, p_i32), ptr(csr.values, p_f64))
             if status != 0:
                 raise StrError(handle_b200_error_code(status))
             self.time_initialize_ns = time.perf_counter_ns() - t0
             self.initialized = True
         em, ep = _lib.c_i32(0), _lib.c_i32(0)
         t0 = time.perf_counter_ns()
-        status = self._lib.complex_solver_b200_factorize(self.solver, ctypes.byref(em), ctypes.byref(ep), verbose,
-                                                         ptr(csr.values, p_f64))
+        if self.coo_boundary:
+            status = self._lib.complex_solver_b200_factorize_coo(self.solver, ctypes.byref(em), ctypes.byref(ep), verbose,
+                                                                 ptr(coo_v, p_f64))
+        else:
+            status = self._lib.complex_solver_b200_factorize(self.solver, ctypes.byref(em), ctypes.byref(ep), verbose,
+                                                             ptr(csr.values, p_f64))
         if status != 0:
             raise StrError(handle_b200_error_code(status))
         self.time_factorize_ns = time.perf_counter_ns() - t0

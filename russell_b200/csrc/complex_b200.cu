@@ -28,7 +28,9 @@
 
 #include "../../include/solver_b200.h"
 
-// host side of the embedding (host_formats.cpp)
+// host side of the COO conversion and of the embedding (host_formats.cpp)
+extern "C" int32_t b200_coo_to_csr_map(int32_t nrow, int32_t ncol, int32_t nnz, const int32_t* ai, const int32_t* aj, const double* ax,
+                                       int32_t* ptr, int32_t* idx, double* val, int32_t* seg_ptr, int32_t* seg_idx);
 extern "C" int32_t b200_complex_embed(int32_t n, const int32_t* rp, const int32_t* ci, const double* values, int32_t lower,
                                       int64_t* info, int32_t* rptr, int32_t* rcol, int32_t* code, double* rval);
 
@@ -46,6 +48,22 @@ __global__ void __launch_bounds__(256) k_complex_expand(long long nreal, const i
     }
 }
 
+// COO-level boundary: every CSR slot sums its triplets in their order of appearance (ComplexCsrMatrix::update_from_coo,
+// csr_matrix.rs:431-459 over Complex64), on the device
+__global__ void __launch_bounds__(256) k_complex_coo_to_csr_values(int nslots, const int* __restrict__ seg_ptr,
+                                                                   const int* __restrict__ seg_idx, const double2* __restrict__ coo,
+                                                                   double2* __restrict__ csr) {
+    for (int sl = blockIdx.x * blockDim.x + threadIdx.x; sl < nslots; sl += gridDim.x * blockDim.x) {
+        const int a = seg_ptr[sl], b = seg_ptr[sl + 1];
+        double2 acc = __ldg(coo + seg_idx[a]);
+        for (int e = a + 1; e < b; e++) {
+            const double2 v = __ldg(coo + seg_idx[e]);
+            acc.x += v.x, acc.y += v.y;
+        }
+        csr[sl] = acc;
+    }
+}
+
 } // namespace
 
 struct InterfaceComplexB200 {
@@ -57,6 +75,10 @@ struct InterfaceComplexB200 {
     int* d_code = nullptr;
     double2* d_cvals = nullptr;
     double* d_rvals = nullptr;
+    // COO-level boundary (complex_solver_b200_initialize_coo)
+    int nnz_coo = 0;
+    int *d_seg_ptr = nullptr, *d_seg_idx = nullptr;
+    double2* d_coo_cvals = nullptr;
 };
 
 #define CB_CUDA_TRY(call, code)             \
@@ -90,6 +112,9 @@ void complex_solver_b200_drop(struct InterfaceComplexB200* s) {
     if (s->d_code) cudaFree(s->d_code);
     if (s->d_cvals) cudaFree(s->d_cvals);
     if (s->d_rvals) cudaFree(s->d_rvals);
+    if (s->d_seg_ptr) cudaFree(s->d_seg_ptr);
+    if (s->d_seg_idx) cudaFree(s->d_seg_idx);
+    if (s->d_coo_cvals) cudaFree(s->d_coo_cvals);
     solver_b200_drop(s->real);
     delete s;
 }
@@ -167,6 +192,67 @@ int32_t complex_solver_b200_factorize(struct InterfaceComplexB200* s, int32_t* e
             printf("complex_solver_b200_factorize: numeric factorization completed in %.3f ms (device)\n", st8[B200_STAT_MS_FACTORIZE_DEVICE]);
     }
     if (effective_pivoting) *effective_pivoting = 5; // LocalBlock (solver_cudss.rs:393-466 numbering)
+    return rc;
+}
+
+// ---- COO-level boundary for complex triplets: structure analysed once, duplicates summed on the device per call ------
+int32_t complex_solver_b200_initialize_coo(struct InterfaceComplexB200* s, int32_t ordering, int32_t matching, int32_t pivoting,
+                                           double pivot_epsilon, int32_t refinement_nstep, double hybrid_memory_factor,
+                                           int32_t verbose, int32_t general_symmetric, int32_t positive_definite, int32_t ndim,
+                                           int32_t nnz_coo, const int32_t* indices_i, const int32_t* indices_j, const double* values) {
+    if (!s || !indices_i || !indices_j || !values) return B200_ERROR_NULL_POINTER;
+    if (s->initialized) return B200_ERROR_ALREADY_INITIALIZED;
+    if (ndim < 1 || nnz_coo < 1) return B200_ERROR_ANALYSIS + 3;
+    if (general_symmetric || positive_definite)
+        for (int32_t k = 0; k < nnz_coo; k++)
+            if (indices_j[k] > indices_i[k]) return B200_ERROR_ANALYSIS + 4; // Sym::YesLower promised: j <= i
+    std::vector<int32_t> ptr((size_t)ndim + 1), idx((size_t)nnz_coo), seg_ptr((size_t)nnz_coo + 1), seg_idx((size_t)nnz_coo);
+    std::vector<double> re((size_t)nnz_coo), dummy((size_t)nnz_coo);
+    for (int32_t k = 0; k < nnz_coo; k++) re[k] = values[2 * (size_t)k];
+    if (b200_coo_to_csr_map(ndim, ndim, nnz_coo, indices_i, indices_j, re.data(), ptr.data(), idx.data(), dummy.data(), seg_ptr.data(),
+                            seg_idx.data()) != 0)
+        return B200_ERROR_ANALYSIS + 3;
+    const int nslots = ptr[ndim];
+    std::vector<double> csr((size_t)2 * nslots);
+    for (int sl = 0; sl < nslots; sl++) { // the same sums the device kernel forms later (order of appearance)
+        double ar = values[2 * (size_t)seg_idx[seg_ptr[sl]]], ai = values[2 * (size_t)seg_idx[seg_ptr[sl]] + 1];
+        for (int e = seg_ptr[sl] + 1; e < seg_ptr[sl + 1]; e++) ar += values[2 * (size_t)seg_idx[e]], ai += values[2 * (size_t)seg_idx[e] + 1];
+        csr[2 * (size_t)sl] = ar, csr[2 * (size_t)sl + 1] = ai;
+    }
+    int32_t rc = complex_solver_b200_initialize(s, ordering, matching, pivoting, pivot_epsilon, refinement_nstep, hybrid_memory_factor,
+                                                verbose, general_symmetric, positive_definite, ndim, ptr.data(), idx.data(), csr.data());
+    if (rc != B200_SUCCESSFUL_EXIT) return rc;
+    cudaStream_t st = (cudaStream_t)solver_b200_get_stream(s->real);
+    s->nnz_coo = nnz_coo;
+    CB_CUDA_TRY(cudaMalloc(&s->d_seg_ptr, ((size_t)nslots + 1) * sizeof(int)), B200_ERROR_CUDA_MALLOC);
+    CB_CUDA_TRY(cudaMalloc(&s->d_seg_idx, (size_t)nnz_coo * sizeof(int)), B200_ERROR_CUDA_MALLOC);
+    CB_CUDA_TRY(cudaMalloc(&s->d_coo_cvals, (size_t)nnz_coo * sizeof(double2)), B200_ERROR_CUDA_MALLOC);
+    CB_CUDA_TRY(cudaMemcpyAsync(s->d_seg_ptr, seg_ptr.data(), ((size_t)nslots + 1) * sizeof(int), cudaMemcpyHostToDevice, st), B200_ERROR_CUDA_MEMCPY);
+    CB_CUDA_TRY(cudaMemcpyAsync(s->d_seg_idx, seg_idx.data(), (size_t)nnz_coo * sizeof(int), cudaMemcpyHostToDevice, st), B200_ERROR_CUDA_MEMCPY);
+    CB_CUDA_TRY(cudaStreamSynchronize(st), B200_ERROR_CUDA_SYNCHRONIZE);
+    return B200_SUCCESSFUL_EXIT;
+}
+
+int32_t complex_solver_b200_factorize_coo(struct InterfaceComplexB200* s, int32_t* effective_matching, int32_t* effective_pivoting,
+                                          int32_t verbose, const double* coo_values) {
+    if (!s) return B200_ERROR_NULL_POINTER;
+    if (!s->initialized || !s->d_seg_ptr) return B200_ERROR_NEED_INITIALIZATION;
+    if (!coo_values) return B200_ERROR_NULL_POINTER;
+    CB_CUDA_TRY(cudaSetDevice(solver_b200_get_device(s->real)), B200_ERROR_NOT_AVAILABLE);
+    cudaStream_t st = (cudaStream_t)solver_b200_get_stream(s->real);
+    CB_CUDA_TRY(cudaMemcpyAsync(s->d_coo_cvals, coo_values, (size_t)s->nnz_coo * sizeof(double2), cudaMemcpyHostToDevice, st), B200_ERROR_CUDA_MEMCPY);
+    int blocks = (s->nnz + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_complex_coo_to_csr_values<<<blocks, 256, 0, st>>>(s->nnz, s->d_seg_ptr, s->d_seg_idx, s->d_coo_cvals, s->d_cvals);
+    if (cudaGetLastError() != cudaSuccess) return B200_ERROR_NUM_FACTORIZATION + 1;
+    int32_t rc = complex_solver_b200_factorize_device(s, (const double*)s->d_cvals);
+    double st8[B200_STAT_COUNT];
+    if (solver_b200_get_stats(s->real, st8, B200_STAT_COUNT) == 0) {
+        if (effective_matching) *effective_matching = st8[B200_STAT_MATCHED] != 0.0 ? B200_MATCHING_MAX_DIAG_PRODUCT : B200_MATCHING_NONE;
+        if (rc == 0 && verbose)
+            printf("complex_solver_b200_factorize_coo: numeric factorization completed in %.3f ms (device)\n", st8[B200_STAT_MS_FACTORIZE_DEVICE]);
+    }
+    if (effective_pivoting) *effective_pivoting = 5;
     return rc;
 }
 

@@ -245,3 +245,50 @@ def test_radau5_brusselator_n200_properties():
     z2 = np.zeros(ndim, dtype=np.complex128)
     csol.solve(z2, (2.0 - 1.0j) * bz)  # linearity over the complex field
     assert np.max(np.abs(z2 - (2.0 - 1.0j) * z)) <= 1e-9
+
+
+def test_complex_coo_boundary_is_bit_identical_to_host_conversion():
+    # complex_solver_b200_factorize_coo (duplicates summed on the device) against complex_solver_b200_factorize fed by the
+    # host ComplexCsrMatrix::update_from_coo clone: identical CSR values => identical factors => identical solutions
+    ndim, ai, aj, _, kc = helpers.brusselator_radau5_triplets(30, h=2e-3)  # 16 triplets per grid point, with duplicates
+    coo = rb.ComplexCooMatrix.from_triplets(ndim, ndim, ai, aj, kc)
+    rng = np.random.default_rng(1)
+    b = rng.standard_normal(ndim) + 1j * rng.standard_normal(ndim)
+    xs = []
+    for flag in (True, False):
+        sol = rb.ComplexSolverB200(coo_boundary=flag)
+        sol.factorize(coo)
+        x = np.zeros(ndim, dtype=np.complex128)
+        sol.solve(x, b)
+        assert sol.residual(x, b) <= TOL_RESIDUAL
+        coo.values[: coo.nnz] = kc * (1.0 + 0.25j)  # refactorize with new values, same structure
+        sol.factorize(coo)
+        x2 = np.zeros(ndim, dtype=np.complex128)
+        sol.solve(x2, b)
+        assert sol.residual(x2, b) <= TOL_RESIDUAL
+        coo.values[: coo.nnz] = kc
+        xs.append((x, x2))
+    assert np.array_equal(xs[0][0], xs[1][0]) and np.array_equal(xs[0][1], xs[1][1])
+    assert np.max(np.abs(xs[0][0] - xs[0][1] * (1.0 + 0.25j))) <= 1e-12 * np.max(np.abs(xs[0][0]))  # (cA) x = b  =>  x scales by 1/c
+
+
+def test_complex_coo_boundary_errors():
+    from russell_b200 import _lib
+    from russell_b200._lib import p_f64, p_i32, ptr
+
+    lib = _lib.load()
+    h = lib.complex_solver_b200_new()
+    ii, jj = np.array([0, 1, 0], dtype=np.int32), np.array([0, 1, 1], dtype=np.int32)
+    vv = np.array([1.0, 0.0, 2.0, 0.5, 0.25, 0.0])
+    args = lambda sym, i, j, nnz: (0, 0, 0, -1.0, -1, -1.0, 0, sym, 0, 2, nnz, ptr(i, p_i32), ptr(j, p_i32), ptr(vv, p_f64))
+    assert lib.complex_solver_b200_factorize_coo(h, None, None, 0, ptr(vv, p_f64)) == 500000
+    assert lib.complex_solver_b200_initialize_coo(h, *args(1, ii, jj, 3)) == 704          # j > i with Sym::YesLower
+    bad = np.array([0, 2, 0], dtype=np.int32)
+    assert lib.complex_solver_b200_initialize_coo(h, *args(0, bad, jj, 3)) == 703         # index out of range
+    assert lib.complex_solver_b200_initialize_coo(h, *args(0, ii, jj, 3)) == 0
+    assert lib.complex_solver_b200_initialize_coo(h, *args(0, ii, jj, 3)) == 700000
+    assert lib.complex_solver_b200_factorize_coo(h, None, None, 0, ptr(vv, p_f64)) == 0
+    x, b = np.zeros(4), np.array([1.25, 0.0, 2.0, 0.5])  # A = [[1, 0.25], [0, 2+0.5i]], x = (1, 1)
+    assert lib.complex_solver_b200_solve(h, ptr(x, p_f64), ptr(b, p_f64), 0) == 0
+    assert np.allclose(x, [1.0, 0.0, 1.0, 0.0], atol=1e-14)
+    lib.complex_solver_b200_drop(h)
