@@ -156,3 +156,22 @@ def brusselator_radau5_triplets(npoint, h=1e-4, alpha=0.1):
     k_real = np.concatenate([jv, np.full(ndim, RADAU5_GAMMA / h)])
     k_comp = np.concatenate([jv.astype(np.complex128), np.full(ndim, complex(RADAU5_ALPHA / h, RADAU5_BETA / h))])
     return ndim, ai, aj, k_real, k_comp
+
+
+def laplacian_3d_triplets(k, skew=0.0):
+    """7-point Laplacian on a k^3 grid (Dirichlet), optionally with an index-seeded skew perturbation of the off-diagonal
+    entries (+-skew*sin(i*j)): the small-scale analogue of the stand-in SURVEY 8d proposes for af_shell10 (BASELINE.json
+    configs[2], which is not in the tree): large separator fronts (k^2 vertices), unsymmetric values."""
+    n = k * k * k
+    m = np.arange(n, dtype=np.int64)
+    i, j, l = m % k, (m // k) % k, m // (k * k)
+    cols = np.stack([m, m - 1, m + 1, m - k, m + k, m - k * k, m + k * k], axis=1)
+    ok = np.stack([np.ones(n, bool), i > 0, i < k - 1, j > 0, j < k - 1, l > 0, l < k - 1], axis=1)
+    vals = np.tile(np.array([6.0, -1.0, -1.0, -1.0, -1.0, -1.0, -1.0]), (n, 1))
+    rows = np.repeat(m[:, None], 7, axis=1)
+    sel = ok.ravel()
+    ai, aj, ax = rows.ravel()[sel], cols.ravel()[sel], vals.ravel()[sel].copy()
+    if skew != 0.0:
+        off = ai != aj
+        ax[off] += skew * np.sin((ai[off] + 1.0) * (aj[off] + 1.0))
+    return n, ai.astype(np.int32), aj.astype(np.int32), ax

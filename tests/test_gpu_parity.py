@@ -590,3 +590,72 @@ def test_two_handles_on_two_threads():
     [t.start() for t in ts]
     [t.join() for t in ts]
     assert len(results) == 4 and max(results.values()) <= TOL_RESIDUAL
+
+
+# ---- 3D problems: large separator fronts (the shape of BASELINE.json configs[2], whose file is not in the tree) -----------
+def test_laplacian_3d_vs_cpu_lu():
+    n, ai, aj, ax = helpers.laplacian_3d_triplets(22, skew=1e-3)  # 10,648 dof, unsymmetric values, top separator 22^2
+    coo = rb.CooMatrix.from_triplets(n, n, ai, aj, ax)
+    b = np.ones(n)
+    sol, x = solve_through_abi(coo, b)
+    a = oracle.full_scipy_matrix(n, n, ai, aj, ax)
+    xs = oracle.lu_solve(a, b)
+    assert np.linalg.norm(b - a @ x) / np.linalg.norm(b) <= TOL_RESIDUAL
+    assert np.max(np.abs(x - xs)) <= 1e-9 * np.max(np.abs(xs))
+    assert sol.device_stats()["max_front"] >= 22 * 22
+
+
+def test_laplacian_3d_60_properties():
+    # 216,000 dof, 1.5 M nonzeros, separator fronts of ~3600 columns (56 chain panels): held by properties
+    n, ai, aj, ax = helpers.laplacian_3d_triplets(60, skew=1e-3)
+    coo = rb.CooMatrix.from_triplets(n, n, ai, aj, ax)
+    sol = rb.SolverB200()
+    sol.factorize(coo)
+    st = sol.device_stats()
+    assert st["n_perturbed"] == 0 and st["max_front"] >= 3000
+    xstar = np.cos(0.01 * np.arange(n))
+    b = sol.mat_vec_mul(xstar)
+    x = np.zeros(n)
+    sol.solve(x, b)
+    assert sol.residual(x, b) <= TOL_RESIDUAL
+    assert np.max(np.abs(x - xstar)) <= 1e-8
+
+
+def test_radau5_real_and_complex_handles_on_two_threads():
+    # russell_ode/src/radau5.rs:270-296: with concurrency on, the real and the complex system are factorized (and solved)
+    # on two threads at the same time, each through its own handle (own stream, own buffers)
+    ndim, ai, aj, kr, kc = helpers.brusselator_radau5_triplets(40, h=1e-3)
+    rcoo = rb.CooMatrix.from_triplets(ndim, ndim, ai, aj, kr)
+    ccoo = rb.ComplexCooMatrix.from_triplets(ndim, ndim, ai, aj, kc)
+    rsol, csol = rb.SolverB200(), rb.ComplexSolverB200()
+    b = np.ones(ndim)
+    bz = np.ones(ndim, dtype=np.complex128) * (1.0 - 2.0j)
+    x, z = np.zeros(ndim), np.zeros(ndim, dtype=np.complex128)
+    errs = []
+
+    def run_real():
+        try:
+            for _ in range(3):
+                rsol.factorize(rcoo)
+                rsol.solve(x, b)
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    def run_complex():
+        try:
+            for _ in range(3):
+                csol.factorize(ccoo)
+                csol.solve(z, bz)
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    t1, t2 = threading.Thread(target=run_real), threading.Thread(target=run_complex)
+    t1.start(), t2.start()
+    t1.join(), t2.join()
+    assert not errs, errs
+    assert rsol.residual(x, b) <= TOL_RESIDUAL and csol.residual(z, bz) <= TOL_RESIDUAL
+    # same answers as a serial run
+    x2, z2 = np.zeros(ndim), np.zeros(ndim, dtype=np.complex128)
+    rsol.solve(x2, b)
+    csol.solve(z2, bz)
+    assert np.array_equal(x, x2) and np.array_equal(z, z2)
