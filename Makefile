@@ -14,7 +14,7 @@ $(LIB): $(OBJ)
 	mkdir -p russell_b200/lib
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -cudart static
 
-build/solver_b200.o: $(CSRC)/solver_b200.cu $(CSRC)/kernels.cuh $(CSRC)/plan.hpp include/solver_b200.h
+build/solver_b200.o: $(CSRC)/solver_b200.cu $(CSRC)/kernels.cuh $(CSRC)/sweep_top.cuh $(CSRC)/plan.hpp include/solver_b200.h
 	mkdir -p build
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> build/ptxas_solver_b200.log || (cat build/ptxas_solver_b200.log; false)
 

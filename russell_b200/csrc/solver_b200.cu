@@ -123,7 +123,7 @@ struct InterfaceB200 {
     int want_trace = 0;
     int *d_node_slot = nullptr, *d_bdone = nullptr; // k_bwd_top3: scratch slot base per front, partial-products-done counters
     int top_variant = 3;      // 1 = k_fwd_top/k_bwd_top, 2 = k_fwd_top2/k_bwd_top2 (descriptors and indices loaded before the dependency wait), 3 = k_fwd_top2/k_bwd_top3 (children finish their parent: one hop per level)
-    int use_top = 1, ltop = 0, n_top_items = 0, top_grid = 0, n_slots = 0;
+    int use_top = 1, ltop = 0, n_top_items = 0, top_grid = 0, top_grid_b = 0, n_slots = 0; // (the backward kernel needs less shared memory: its own, larger co-resident grid)
     bool sweep_dirty = false;          // a persistent sweep aborted: counters must be re-armed
     std::vector<int> cdone_init;       // host copy of the initial completion counters
     SolveItem* d_top_items = nullptr;
@@ -497,7 +497,7 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
 __global__ void k_bump_epoch(int* epoch) { *epoch += 1; }
 void k_fwd_top_launch(InterfaceB200* s) {
     if (s->top_variant >= 2) {
-        k_fwd_top2<<<s->top_grid, 256, B200_TOP_SMEM, s->stream>>>(s->d_top_items, s->n_top_items, s->d_nodes, s->d_rel, s->d_fac, s->d_dinv,
+        k_fwd_top2<<<s->top_grid, 256, B200_TOP3_SMEM, s->stream>>>(s->d_top_items, s->n_top_items, s->d_nodes, s->d_rel, s->d_fac, s->d_dinv,
                                                                  s->d_lperm, s->d_top_ranges, s->d_y, s->d_z, s->d_wv, s->d_cdone, s->d_epoch,
                                                                  s->d_abort, s->d_trace);
         return;
@@ -508,7 +508,7 @@ void k_fwd_top_launch(InterfaceB200* s) {
 }
 void k_bwd_top_launch(InterfaceB200* s) {
     if (s->top_variant >= 3) {
-        k_bwd_top3<<<s->top_grid, 256, B200_TOP3_SMEM, s->stream>>>(s->d_top_items, s->n_top_items, s->d_nodes, s->d_rows, s->d_fac, s->d_dinv,
+        k_bwd_top3<<<s->top_grid_b, 256, B200_TOP3_SMEM, s->stream>>>(s->d_top_items, s->n_top_items, s->d_nodes, s->d_rows, s->d_fac, s->d_dinv,
                                                                   s->d_z, s->d_xp, s->d_big_scratch, s->d_node_slot, s->d_bdone, s->d_epoch,
                                                                   s->d_abort, s->d_trace ? s->d_trace + 4 * (size_t)s->n_top_items : nullptr);
         return;
@@ -1104,7 +1104,7 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     if (s->n_top_items > 0) {
         CUDA_TRY(cudaFuncSetAttribute(k_fwd_top, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_TOP_SMEM), B200_ERROR_NOT_AVAILABLE);
         CUDA_TRY(cudaFuncSetAttribute(k_bwd_top, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_TOP_SMEM), B200_ERROR_NOT_AVAILABLE);
-        CUDA_TRY(cudaFuncSetAttribute(k_fwd_top2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_TOP_SMEM), B200_ERROR_NOT_AVAILABLE);
+        CUDA_TRY(cudaFuncSetAttribute(k_fwd_top2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_TOP3_SMEM), B200_ERROR_NOT_AVAILABLE);
         CUDA_TRY(cudaFuncSetAttribute(k_bwd_top2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_TOP_SMEM), B200_ERROR_NOT_AVAILABLE);
         CUDA_TRY(cudaFuncSetAttribute(k_bwd_top3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_TOP3_SMEM), B200_ERROR_NOT_AVAILABLE);
         int occ_f = 0, occ_b = 0, nsm = 0;
@@ -1112,7 +1112,7 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_bwd_top, 256, B200_TOP_SMEM), B200_ERROR_NOT_AVAILABLE);
         CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device), B200_ERROR_NOT_AVAILABLE);
         if (s->top_variant >= 2) {
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_fwd_top2, 256, B200_TOP_SMEM), B200_ERROR_NOT_AVAILABLE);
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_fwd_top2, 256, B200_TOP3_SMEM), B200_ERROR_NOT_AVAILABLE);
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_bwd_top2, 256, B200_TOP_SMEM), B200_ERROR_NOT_AVAILABLE);
         }
         if (s->top_variant >= 3)
@@ -1120,6 +1120,7 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
         int occ = std::min(occ_f, occ_b);
         if (occ < 1) s->n_top_items = 0; // cannot guarantee co-residency: fall back to per-level launches
         s->top_grid = std::max(1, std::min(s->n_top_items, occ * nsm));
+        s->top_grid_b = (s->top_variant >= 3) ? std::max(1, std::min(s->n_top_items, occ_b * nsm)) : s->top_grid;
     }
 
     // algorithmic bytes: SpTRSV streams every stored factor entry once (+ the pivot-block inverses)

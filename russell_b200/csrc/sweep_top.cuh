@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(256) k_bwd_top(const SolveItem* __restrict__ i
 // permutation and z come from host-built records or are loaded before the wait; the wait itself is one poll per child in
 // parallel; after it there is ONE batch of value loads (all children in flight together).  Fronts with a single row slice
 // skip the cross-CTA ticket reduction of the backward sweep.  Arithmetic and summation order are those of v1 (bit-identical).
-__global__ void __launch_bounds__(256) k_fwd_top2(const SolveItem* __restrict__ items, int nitems, const NodeDev* __restrict__ nodes,
+__global__ void __launch_bounds__(256, 3) k_fwd_top2(const SolveItem* __restrict__ items, int nitems, const NodeDev* __restrict__ nodes,
                                                   const int* __restrict__ rel_all, const double* __restrict__ fac,
                                                   const double* __restrict__ dinv, const int* __restrict__ lperm,
                                                   const int* __restrict__ ranges, const double* __restrict__ y, double* __restrict__ zv,
@@ -252,22 +252,29 @@ __global__ void __launch_bounds__(256) k_fwd_top2(const SolveItem* __restrict__ 
                                                   int* __restrict__ abort_flag, unsigned long long* __restrict__ trace) {
     const int epoch = *epoch_ptr;
     extern __shared__ double smt[];
-    double* Ds = smt;
-    double* Ps = smt + B200_MAXP * B200_MAXP; // Ps[k * SLICE + r]
+    double* Ps = smt; // this slice of L21: Ps[k * SLICE + r]  (inv(L11) is kept in registers: B200_TOP3_SMEM, 3 CTAs per SM)
     __shared__ double t1[B200_MAXP], z[B200_MAXP], wloc[B200_SLICE], wpart[B200_SLICE];
     const int tid = threadIdx.x, nt = blockDim.x;
+    const int gk = tid >> 2, gpart = tid & 3; // GEMV layout: four threads per row
     for (int itx = blockIdx.x; itx < nitems; itx += gridDim.x) {
         const SolveItem it = items[itx];
         const NodeDev nd = nodes[it.node];
         const int p = nd.p, u = nd.u, nchild = nd.nchild;
         const long long f = (long long)p + u;
         {
-            const double* D = dinv + nd.Doff;
-            for (int e = tid; e < p * p; e += nt) cp_async8(Ds + e, D + e);
             const int r = tid & (B200_SLICE - 1), g = tid >> 7;
             if (r < it.nrows) {
                 const double* src = fac + nd.Loff + p + it.r0 + r;
                 for (int k = g; k < p; k += 2) cp_async8(Ps + k * B200_SLICE + r, src + (long long)k * f);
+            }
+        }
+        double dreg[16]; // row gk of inv(L11), columns gpart, gpart+4, ... (< gk): loaded before the wait
+        {
+            const double* D = dinv + nd.Doff;
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                const int m = gpart + 4 * q;
+                dreg[q] = (gk < p && m < gk) ? D[gk + (long long)m * p] : 0.0;
             }
         }
         if (trace && tid == 0) trace[4 * (long long)itx] = gtime();
@@ -326,10 +333,13 @@ __global__ void __launch_bounds__(256) k_fwd_top2(const SolveItem* __restrict__ 
         if (tid < p) t1[tid] = tp;
         __syncthreads();
         {   // z = inv(L11) t1: four threads per row (fixed partition + fixed shuffle order: deterministic)
-            const int k = tid >> 2, part = tid & 3;
+            const int k = gk, part = gpart;
             double s = 0.0;
-            if (k < p)
-                for (int m = part; m < k; m += 4) s += Ds[k + m * p] * t1[m];
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                const int m = gpart + 4 * q;
+                if (gk < p && m < gk) s += dreg[q] * t1[m];
+            }
             s += __shfl_xor_sync(0xffffffffu, s, 1);
             s += __shfl_xor_sync(0xffffffffu, s, 2);
             if (k < p && part == 0) {
@@ -473,7 +483,7 @@ __global__ void __launch_bounds__(256) k_bwd_top2(const SolveItem* __restrict__ 
 // per level.  x1 is written to xp by slice 0 of each child before that child releases its own counter (so that deeper
 // descendants, which gather it from xp, see it) and by the front's own last slice (which covers fronts whose children
 // live outside the persistent region).
-__global__ void __launch_bounds__(256) k_bwd_top3(const SolveItem* __restrict__ items, int nitems, const NodeDev* __restrict__ nodes,
+__global__ void __launch_bounds__(256, 3) k_bwd_top3(const SolveItem* __restrict__ items, int nitems, const NodeDev* __restrict__ nodes,
                                                   const int* __restrict__ rows_all, const double* __restrict__ fac,
                                                   const double* __restrict__ dinv, const double* __restrict__ zv,
                                                   double* __restrict__ xp, double* __restrict__ scratch,
