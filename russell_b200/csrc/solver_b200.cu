@@ -80,6 +80,7 @@ struct InterfaceB200 {
     int schur_variant = 1; // 0 = FMA, 1 = DMMA
     int relax_small = -1;                                // supernode amalgamation knobs of the host analysis (plan.hpp); < 0: defaults
     double relax_z1 = -1.0, relax_z2 = -1.0, relax_z3 = -1.0;
+    int schur_occ3_min = 1 << 30; // launches with at least this many Schur tiles use the 3-CTAs-per-SM build of k_schur_dmma
     int asm_variant = 1;     // 0 = k_assemble (read-modify-write in global memory), 1 = k_assemble_tile (tile in shared memory)
     int use_leaf_reg = 1;    // leaf fronts of order <= 32: k_leaf_reg (one warp per front, registers only)
     int panel_row_max = 160; // launches of at most this many 128-row panel items use k_panel_row (one warp per four rows)
@@ -460,11 +461,14 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
                     cudaEventRecord(s->ev_la, s->stream);
                     cudaStreamWaitEvent(s->side, s->ev_la, 0);
                 }
-                k_schur_dmma<<<la ? ncrit : nsch, 256, smem_schur_dmma(), s->stream>>>(s->d_schur + lv.schur_ptr[l], s->d_nodes, s->d_fac, s->d_cb);
+                if ((la ? ncrit : nsch) >= s->schur_occ3_min) // many tiles: three CTAs per SM (80 registers) beat two (128 registers)
+                    k_schur_dmma<3><<<la ? ncrit : nsch, 256, smem_schur_dmma(), s->stream>>>(s->d_schur + lv.schur_ptr[l], s->d_nodes, s->d_fac, s->d_cb);
+                else
+                    k_schur_dmma<2><<<la ? ncrit : nsch, 256, smem_schur_dmma(), s->stream>>>(s->d_schur + lv.schur_ptr[l], s->d_nodes, s->d_fac, s->d_cb);
                 if (la) {
                     // lookahead == 2: the side launch asks for more shared memory than it needs, so only ONE of its CTAs fits
                     // on an SM and the next level's pivot-block / panel CTAs always find registers and a slot
-                    k_schur_dmma<<<nsch - ncrit, 256, s->lookahead == 2 ? (size_t)120 * 1024 : smem_schur_dmma(), s->side>>>(
+                    k_schur_dmma<2><<<nsch - ncrit, 256, s->lookahead == 2 ? (size_t)120 * 1024 : smem_schur_dmma(), s->side>>>(
                         s->d_schur + lv.schur_ptr[l] + ncrit, s->d_nodes, s->d_fac, s->d_cb);
                     cudaEventRecord(s->ev_rest, s->side);
                     pending_rest = true;
@@ -743,6 +747,7 @@ int32_t solver_b200_set_option(struct InterfaceB200* s, const char* key, double 
     else if (k == "panel_row_max") s->panel_row_max = (int)value;
     else if (k == "use_leaf_reg") s->use_leaf_reg = value != 0.0;
     else if (k == "asm_variant") s->asm_variant = (int)value;
+    else if (k == "schur_occ3_min") s->schur_occ3_min = (int)value;
     else if (k == "relax_small") s->relax_small = (int)value;
     else if (k == "relax_z1") s->relax_z1 = value;
     else if (k == "relax_z2") s->relax_z2 = value;
@@ -1098,7 +1103,8 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     CUDA_TRY(cudaFuncSetAttribute(k_panel_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_PW_SMEM), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_panel_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_PM_SMEM), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_schur_fma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_schur_fma(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
-    CUDA_TRY(cudaFuncSetAttribute(k_schur_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024), B200_ERROR_NOT_AVAILABLE);
+    CUDA_TRY(cudaFuncSetAttribute(k_schur_dmma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024), B200_ERROR_NOT_AVAILABLE);
+    CUDA_TRY(cudaFuncSetAttribute(k_schur_dmma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_assemble_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, B200_ASM_SMEM_MAX), B200_ERROR_NOT_AVAILABLE);
     (void)W;
     if (s->n_top_items > 0) {
