@@ -27,7 +27,7 @@ from ._lib import p_f64, p_i32, p_i64, ptr
 __all__ = [
     "StrError", "Sym", "Genie", "MMsym", "Ordering", "Scaling", "Matching", "Pivoting", "LinSolParams",
     "CooMatrix", "CsrMatrix", "CscMatrix", "SolverB200", "LinSolver", "VerifyLinSys", "StatsLinSol",
-    "read_matrix_market", "handle_b200_error_code",
+    "read_matrix_market", "read_matrix_market_pair", "handle_b200_error_code",
 ]
 
 
@@ -293,29 +293,45 @@ _MM_ERRORS = {  # read_matrix_market.rs messages, keyed by the codes of host_for
     28: "MatrixMarket data is invalid: the number of rows must equal the number of columns for symmetric matrices",
     29: "complex MatrixMarket files are not supported by the B200 backend yet",
     30: "cannot find the dimensions line",
+    31: "cannot read bij",
+    32: "cannot parse bij",
 }
 
 
 def read_matrix_market(full_path, symmetric_handling=MMsym.LeaveAsLower):
-    """read_matrix_market.rs:346-475 (real coordinate files); returns a CooMatrix"""
+    """read_matrix_market.rs:346-475: coordinate files, real or complex, general / symmetric (/ Hermitian read as general).
+    Returns a CooMatrix for a real file and a ComplexCooMatrix for a complex one (read_matrix_market_pair gives the
+    reference's `(Option<CooMatrix>, Option<ComplexCooMatrix>)` shape)."""
     lib = _lib.load()
-    info = np.zeros(6, dtype=np.int64)
+    info = np.zeros(8, dtype=np.int64)
     path = str(full_path).encode()
     rc = lib.b200_mm_read(path, symmetric_handling.value, ptr(info, p_i64), None, None, None, 0)
     if rc != 0:
         raise StrError(_MM_ERRORS.get(rc, "MatrixMarket error %d" % rc))
     m, n, _, is_sym, cap = (int(v) for v in info[:5])
+    is_complex = bool(info[6])
     if is_sym:
         sym = {MMsym.LeaveAsLower: Sym.YesLower, MMsym.SwapToUpper: Sym.YesUpper, MMsym.MakeItFull: Sym.YesFull}[symmetric_handling]
     else:
         sym = Sym.No
-    coo = CooMatrix(m, n, cap, sym)
+    if is_complex:
+        from .complex import ComplexCooMatrix
+
+        coo = ComplexCooMatrix(m, n, cap, sym)
+    else:
+        coo = CooMatrix(m, n, cap, sym)
     rc = lib.b200_mm_read(path, symmetric_handling.value, ptr(info, p_i64), ptr(coo.indices_i, p_i32),
                           ptr(coo.indices_j, p_i32), ptr(coo.values, p_f64), cap)
     if rc != 0:
         raise StrError(_MM_ERRORS.get(rc, "MatrixMarket error %d" % rc))
     coo.nnz = int(info[5])
     return coo
+
+
+def read_matrix_market_pair(full_path, symmetric_handling=MMsym.LeaveAsLower):
+    """the reference's return shape: (coo_real or None, coo_complex or None)"""
+    coo = read_matrix_market(full_path, symmetric_handling)
+    return (None, coo) if coo.values.dtype == np.complex128 else (coo, None)
 
 
 _B200_ERRORS = {  # same spirit as handle_cudss_error_code (solver_cudss.rs:501-558); OOM wording kept for

@@ -207,8 +207,10 @@ enum {
     MM_VAL_INDEX = 26,     // found an invalid index
     MM_VAL_MISSING = 27,   // not all values have been found
     MM_SYM_RECT = 28,      // symmetric matrices must be square
-    MM_COMPLEX = 29,       // complex files are handled by the complex twin (not in this backend yet)
+    MM_COMPLEX = 29,       // (unused since complex files are read: kept so that the numbering stays stable)
     MM_NO_DIMS = 30,
+    MM_VAL_NO_B = 31,      // cannot read bij
+    MM_VAL_B = 32,         // cannot parse bij
 };
 
 static bool parse_i64(const std::string& s, long long& out) {
@@ -253,9 +255,10 @@ static int parse_header(const std::string& line, bool& is_complex, bool& is_sym)
     return MM_OK;
 }
 
-// Reads a coordinate/real file.  handling: 0 LeaveAsLower, 1 SwapToUpper, 2 MakeItFull (enums.rs:45-67).
-// Pass ai=aj=NULL to query: info[0..4] = nrow, ncol, nnz_file, symmetric(0/1), max_entries (capacity to allocate).
-// With arrays: fills triplets, info[5] = number of triplets written.
+// Reads a coordinate file, real or complex.  handling: 0 LeaveAsLower, 1 SwapToUpper, 2 MakeItFull (enums.rs:45-67).
+// Pass ai=aj=NULL to query: info[0..4] = nrow, ncol, nnz_file, symmetric(0/1), max_entries (capacity to allocate),
+// info[6] = 1 for a complex file (values are then interleaved (re, im) pairs: ax needs 2 * capacity doubles).
+// With arrays: fills triplets, info[5] = number of triplets written.  info must hold 8 entries.
 int32_t b200_mm_read(const char* path, int32_t handling, int64_t* info, int32_t* ai, int32_t* aj, double* ax, int64_t cap) {
     std::ifstream in(path);
     if (!in.good()) return MM_CANNOT_OPEN;
@@ -280,9 +283,9 @@ int32_t b200_mm_read(const char* path, int32_t handling, int64_t* info, int32_t*
     }
     if (!have_dims) return MM_NO_DIMS;
     if (is_sym && m != n) return MM_SYM_RECT;
-    if (is_complex) return MM_COMPLEX;
+    const int W = is_complex ? 2 : 1;
     long long maxent = (is_sym && handling == 2) ? 2 * nnz : nnz;
-    info[0] = m, info[1] = n, info[2] = nnz, info[3] = is_sym ? 1 : 0, info[4] = maxent;
+    info[0] = m, info[1] = n, info[2] = nnz, info[3] = is_sym ? 1 : 0, info[4] = maxent, info[6] = is_complex ? 1 : 0;
     if (!ai || !aj || !ax) return MM_OK;
     long long pos = 0, w = 0;
     while (std::getline(in, line)) {
@@ -290,21 +293,30 @@ int32_t b200_mm_read(const char* path, int32_t handling, int64_t* info, int32_t*
         if (t.empty() || t[0][0] == '%') continue;
         if (pos == nnz) return MM_VAL_TOO_MANY;
         long long i, j;
-        double a;
+        double a, bim = 0.0;
         if (!parse_i64(t[0], i)) return MM_VAL_I;
         if (t.size() < 2) return MM_VAL_NO_J;
         if (!parse_i64(t[1], j)) return MM_VAL_J;
         if (t.size() < 3) return MM_VAL_NO_A;
         if (!parse_f64(t[2], a)) return MM_VAL_A;
+        if (is_complex) {
+            if (t.size() < 4) return MM_VAL_NO_B;
+            if (!parse_f64(t[3], bim)) return MM_VAL_B;
+        }
         i -= 1, j -= 1;
         if (i < 0 || i >= m || j < 0 || j >= n) return MM_VAL_INDEX;
         pos++;
         if (w + 2 > cap && w + 1 > cap) return MM_VAL_TOO_MANY;
+        auto put = [&](long long r, long long c) {
+            ai[w] = (int32_t)r, aj[w] = (int32_t)c, ax[W * w] = a;
+            if (W == 2) ax[W * w + 1] = bim;
+            w++;
+        };
         if (is_sym && handling == 1) {
-            ai[w] = (int32_t)j, aj[w] = (int32_t)i, ax[w] = a, w++;
+            put(j, i);
         } else {
-            ai[w] = (int32_t)i, aj[w] = (int32_t)j, ax[w] = a, w++;
-            if (is_sym && handling == 2 && i != j) ai[w] = (int32_t)j, aj[w] = (int32_t)i, ax[w] = a, w++;
+            put(i, j);
+            if (is_sym && handling == 2 && i != j) put(j, i);
         }
     }
     if (pos != nnz) return MM_VAL_MISSING;

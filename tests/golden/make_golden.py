@@ -194,7 +194,7 @@ def main():
     mm = os.path.join(OUT, "matrix_market")
     os.makedirs(mm, exist_ok=True)
     for fn in sorted(os.listdir(os.path.join(REF, "data/matrix_market"))):
-        if fn.endswith(".mtx") and "complex" not in fn and "hermitian" not in fn:
+        if fn.endswith(".mtx"):
             shutil.copy(os.path.join(REF, "data/matrix_market", fn), os.path.join(mm, fn))
     print("samples:", len(samples), sorted(samples)[:5], "...")
 

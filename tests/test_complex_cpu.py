@@ -188,3 +188,60 @@ def test_brusselator_radau5_matrices():
     b = np.ones(ndim)
     rc, x, st = oracle.mf_solve(ndim, bp, bj, bx, b)
     assert rc == 0 and np.linalg.norm(b - a @ x) / np.linalg.norm(b) <= 1e-10
+
+
+# ---- complex Matrix Market files (read_matrix_market.rs:401-437; tests :613-660, :684-816) ----------------------------------
+def test_read_matrix_market_complex_general():
+    coo_real, coo = rb.read_matrix_market_pair(helpers.mm_path("ok_complex_general.mtx"), rb.MMsym.LeaveAsLower)
+    assert coo_real is None and coo.symmetric == rb.Sym.No
+    assert (coo.nrow, coo.ncol, coo.nnz, coo.max_nnz) == (5, 5, 12, 12)
+    assert list(coo.indices_i) == [0, 1, 0, 2, 4, 1, 2, 3, 4, 2, 1, 4]
+    assert list(coo.indices_j) == [0, 0, 1, 1, 1, 2, 2, 2, 2, 3, 4, 4]
+    want = [2 - 1j, 3 - 8j, 3 + 80j, -1 + 30j, 4 + 33j, 4 + 60j, -3 + 6j, 1 + 8j, 2 + 3j, 2 + 1j, 6 + 9j, 1 - 2j]
+    assert np.array_equal(coo.values, np.array(want))
+    real, cpx = rb.read_matrix_market_pair(helpers.mm_path("ok_general.mtx"), rb.MMsym.LeaveAsLower)
+    assert cpx is None and real.nnz == 12
+
+
+@pytest.mark.parametrize("handling,sym,ii,jj", [
+    (rb.MMsym.LeaveAsLower, rb.Sym.YesLower, [0, 1, 2, 3, 3, 4, 4], [0, 0, 1, 2, 3, 1, 4]),
+    (rb.MMsym.SwapToUpper, rb.Sym.YesUpper, [0, 0, 1, 2, 3, 1, 4], [0, 1, 2, 3, 3, 4, 4]),
+])
+def test_read_matrix_market_complex_symmetric(handling, sym, ii, jj):
+    coo = rb.read_matrix_market(helpers.mm_path("ok_complex_symmetric_small.mtx"), handling)
+    assert coo.symmetric == sym and (coo.nrow, coo.ncol, coo.nnz, coo.max_nnz) == (5, 5, 7, 7)
+    assert list(coo.indices_i) == ii and list(coo.indices_j) == jj
+    assert np.array_equal(coo.values, np.array([2 + 1j, 3 + 2j, -1 + 3j, 2 + 4j, 3 + 5j, 6 + 6j, 1 + 7j]))
+
+
+def test_read_matrix_market_complex_make_it_full_and_hermitian():
+    coo = rb.read_matrix_market(helpers.mm_path("ok_complex_symmetric_small.mtx"), rb.MMsym.MakeItFull)
+    assert coo.symmetric == rb.Sym.YesFull and coo.max_nnz == 14 and coo.nnz == 11  # 3 diagonal + 2 * 4 off-diagonal entries
+    a = coo.as_dense()
+    assert np.array_equal(a, a.T) and a[1, 0] == 3 + 2j
+    # "Hermitian" files are read like general ones (read_matrix_market.rs:86-93): the stored entries, no mirroring
+    h = rb.read_matrix_market(helpers.mm_path("ok_complex_hermitian.mtx"), rb.MMsym.LeaveAsLower)
+    assert h.symmetric == rb.Sym.No and h.values.dtype == np.complex128 and h.nnz >= 1
+
+
+@pytest.mark.parametrize("name,msg", [
+    ("bad_wrong_dims_complex.mtx", "found invalid (zero or negative) dimensions"),
+    ("bad_missing_data_complex.mtx", "not all values have been found"),
+    ("bad_many_lines_complex.mtx", "there are more values than specified"),
+    ("bad_symmetric_rectangular_complex.mtx",
+     "MatrixMarket data is invalid: the number of rows must equal the number of columns for symmetric matrices"),
+    ("bad_not_complex_hermitian.mtx", '"Hermitian" keyword can only be used with the "complex" type'),
+])
+def test_read_matrix_market_complex_bad_files(name, msg):
+    with pytest.raises(rb.StrError) as e:
+        rb.read_matrix_market(helpers.mm_path(name), rb.MMsym.LeaveAsLower)
+    assert str(e.value) == msg or msg in str(e.value)
+
+
+def test_read_matrix_market_complex_value_errors(tmp_path):
+    # parse_values (read_matrix_market.rs:166-171, tests :598-607): "cannot read bij" / "cannot parse bij"
+    for body, msg in (("1 1 1.0\n", "cannot read bij"), ("1 1 1.0 wrong\n", "cannot parse bij")):
+        f = tmp_path / "c.mtx"
+        f.write_text("%%MatrixMarket matrix coordinate complex general\n2 2 1\n" + body)
+        with pytest.raises(rb.StrError, match=msg):
+            rb.read_matrix_market(str(f), rb.MMsym.LeaveAsLower)
