@@ -82,6 +82,8 @@ struct InterfaceB200 {
     double relax_z1 = -1.0, relax_z2 = -1.0, relax_z3 = -1.0;
     int schur_occ3_min = 1 << 30; // launches with at least this many Schur tiles use the 3-CTAs-per-SM build of k_schur_dmma
     int asm_variant = 1;     // 0 = k_assemble (read-modify-write in global memory), 1 = k_assemble_tile (tile in shared memory)
+    int small_reg_maxf = 0;  // fronts WITH children of order <= this (16 or 32) may use the register kernel too; measured slower than
+                             // the shared-memory kernel (7.50 -> 7.58 / 7.67 ms per factorization): off
     int use_leaf_reg = 1;    // leaf fronts of order <= 32: k_leaf_reg (one warp per front, registers only)
     int panel_row_max = 160; // launches of at most this many 128-row panel items use k_panel_row (one warp per four rows)
     int panel_variant = 1; // 0 = k_panel (32-row tiles, barrier per column), 1 = k_panel_warp (thread per row, 128-row items)
@@ -396,10 +398,18 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
             if (nn > 0) {
                 // register-resident LU (one warp per 8 front columns): wins when the launch is latency bound (few fronts),
                 // loses to the leaner shared-memory kernel when tens of thousands of fronts compete for thread slots
-                if (l == 0 && s->use_leaf_reg && FC_MAXF[c] <= 32) // leaves (level 0 = no children), whole front in one warp's registers
-                    k_leaf_reg<<<(nn + B200_LEAF_WARPS - 1) / B200_LEAF_WARPS, 32 * B200_LEAF_WARPS, 0, s->stream>>>(
-                        s->d_fact_nodes + fp[c], nn, s->d_nodes, s->d_fac, s->d_cb, s->d_lperm, s->d_upiv, s->d_amax, s->pivot_eps,
-                        s->d_counters);
+                if (FC_MAXF[c] <= 32 && ((l == 0 && s->use_leaf_reg) || (l > 0 && FC_MAXF[c] <= s->small_reg_maxf))) {
+                    // leaves (level 0) and small fronts with children: the whole front in one warp's registers
+                    const int gridw = (nn + B200_LEAF_WARPS - 1) / B200_LEAF_WARPS;
+                    if (FC_MAXF[c] <= 16)
+                        k_small_reg<16><<<gridw, 32 * B200_LEAF_WARPS, 0, s->stream>>>(s->d_fact_nodes + fp[c], nn, s->d_nodes, s->d_child_idx,
+                                                                                      s->d_rel, s->d_fac, s->d_cb, s->d_lperm, s->d_upiv,
+                                                                                      s->d_amax, s->pivot_eps, s->d_counters);
+                    else
+                        k_small_reg<32><<<gridw, 32 * B200_LEAF_WARPS, 0, s->stream>>>(s->d_fact_nodes + fp[c], nn, s->d_nodes, s->d_child_idx,
+                                                                                      s->d_rel, s->d_fac, s->d_cb, s->d_lperm, s->d_upiv,
+                                                                                      s->d_amax, s->pivot_eps, s->d_counters);
+                }
                 else if (FC_MAXF[c] <= 64 && (s->fused_variant == 1 || (s->fused_variant == 2 && nn <= s->fused_w8_max)))
                     k_front_fused_w8<<<nn, 32 * ((FC_MAXF[c] + 7) / 8), lv.fused_smem[(size_t)l * NFC + c], s->stream>>>(
                         s->d_fact_nodes + fp[c], s->d_nodes, s->d_child_idx, s->d_rel, s->d_fac, s->d_cb, s->d_lperm,
@@ -746,6 +756,7 @@ int32_t solver_b200_set_option(struct InterfaceB200* s, const char* key, double 
     else if (k == "panel_variant") s->panel_variant = (int)value;
     else if (k == "panel_row_max") s->panel_row_max = (int)value;
     else if (k == "use_leaf_reg") s->use_leaf_reg = value != 0.0;
+    else if (k == "small_reg_maxf") s->small_reg_maxf = (int)value;
     else if (k == "asm_variant") s->asm_variant = (int)value;
     else if (k == "schur_occ3_min") s->schur_occ3_min = (int)value;
     else if (k == "relax_small") s->relax_small = (int)value;

@@ -345,6 +345,8 @@ def test_round1_kernels_are_bit_identical_to_the_ones_they_replace():
         assert np.array_equal(p0, p2) and np.array_equal(f0, f2)
         f3, p3 = _raw_factors(coo, dict(extra, panel_row_max=0, use_leaf_reg=0, asm_variant=1))  # shared-memory extend-add tile
         assert np.array_equal(p0, p3) and np.array_equal(f0, f3)
+        f4, p4 = _raw_factors(coo, dict(extra, panel_row_max=0, use_leaf_reg=1, small_reg_maxf=32))  # register kernel with children
+        assert np.array_equal(p0, p4) and np.array_equal(f0, f4)
 
 
 @pytest.mark.parametrize("k,lower", [(150, False), (400, True)])
