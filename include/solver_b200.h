@@ -138,8 +138,13 @@ int32_t solver_b200_determinant(struct InterfaceB200 *solver, double *coefficien
 #define B200_STAT_COUNT 24
 int32_t solver_b200_get_stats(struct InterfaceB200 *solver, double *out, int32_t n_out);
 
-/* tuning knobs, must be called before initialize: key in {"panel_width","nd_leaf","use_graph","ir_tol",
- * "schur_variant","device"} */
+/* tuning knobs, to be set before initialize ("ir_tol" and "refinement_nstep" also later).  Host analysis: "panel_width",
+ * "nd_leaf", "relax_small", "relax_z1", "relax_z2", "relax_z3", "force_no_matching".  Execution: "device", "use_graph",
+ * "ir_tol", "refinement_nstep", "trace".  Kernel variants kept for A/B measurements (defaults = the measured optimum, see
+ * DESIGN.md): "schur_variant", "schur_occ3_min", "panel_variant", "panel_row_max", "diag_variant", "invert_variant",
+ * "invert_all", "use_fused", "fused_variant", "fused_maxf", "fused_w8_max", "use_leaf_reg", "small_reg_maxf", "asm_variant",
+ * "fuse_chain", "lookahead", "overlap_invert", "use_top", "top_variant", "top_max_nodes", "use_subtree", "subtree_maxf",
+ * "subtree_budget".  Unknown keys return B200_ERROR_NOT_AVAILABLE. */
 int32_t solver_b200_set_option(struct InterfaceB200 *solver, const char *key, double value);
 
 /* debug/parity: copies factor panels (fac), pivot-block inverses (dinv) and local pivots to host buffers
