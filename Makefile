@@ -3,7 +3,7 @@ NVCC ?= /usr/local/cuda/bin/nvcc
 CXX ?= g++
 ARCH = -gencode arch=compute_100a,code=sm_100a
 NVFLAGS = -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-unused-function
-CXXFLAGS = -O2 -std=c++17 -fPIC -Wall
+CXXFLAGS = -O2 -std=c++17 -fPIC -Wall -pthread
 CSRC = russell_b200/csrc
 LIB = russell_b200/lib/libsolver_b200.so
 OBJ = build/solver_b200.o build/complex_b200.o build/symbolic.o build/ordering.o build/matching.o build/host_formats.o
@@ -12,7 +12,7 @@ all: $(LIB) oracle
 
 $(LIB): $(OBJ)
 	mkdir -p russell_b200/lib
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -cudart static
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -cudart static -lpthread
 
 build/solver_b200.o: $(CSRC)/solver_b200.cu $(CSRC)/kernels.cuh $(CSRC)/sweep_top.cuh $(CSRC)/plan.hpp include/solver_b200.h
 	mkdir -p build

@@ -8,8 +8,11 @@
 #include "plan.hpp"
 
 #include <algorithm>
+#include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <thread>
 
 namespace b200 {
 
@@ -21,7 +24,7 @@ struct NdCtx {
     std::vector<int> label; // partition id of every vertex
     std::vector<int> lvl;   // BFS level scratch, -1 = not visited
     std::vector<int> loc;   // local index scratch
-    int next_id = 1;
+    std::atomic<int> next_id{1}; // (the two halves of a dissection may be ordered by two threads)
     int* out = nullptr;     // perm (new -> old)
     explicit NdCtx(const Graph& gg, int lf) : g(gg), leaf(lf), label(gg.n, 0), lvl(gg.n, -1), loc(gg.n, -1) {}
 };
@@ -129,10 +132,10 @@ void local_min_degree(NdCtx& c, const std::vector<int>& verts, int id, int* out)
     }
 }
 
-void nd_component(NdCtx& c, std::vector<int>& verts, int id, int* out, std::vector<int>& order, std::vector<int>& lptr);
+void nd_component(NdCtx& c, std::vector<int>& verts, int id, int* out, std::vector<int>& order, std::vector<int>& lptr, int depth);
 
 // `verts` all carry label `id`; writes verts.size() entries at out
-void nd_rec(NdCtx& c, std::vector<int>& verts, int id, int* out) {
+void nd_rec(NdCtx& c, std::vector<int>& verts, int id, int* out, int depth = 0) {
     const int m = (int)verts.size();
     if (m == 0) return;
     if (m <= c.leaf) {
@@ -143,7 +146,7 @@ void nd_rec(NdCtx& c, std::vector<int>& verts, int id, int* out) {
     std::vector<int> order, lptr;
     bfs_levels(c, id, verts[0], order, lptr);
     if ((int)order.size() == m) {
-        nd_component(c, verts, id, out, order, lptr);
+        nd_component(c, verts, id, out, order, lptr, depth);
         return;
     }
     clear_levels(c, order);
@@ -162,14 +165,14 @@ void nd_rec(NdCtx& c, std::vector<int>& verts, int id, int* out) {
             local_min_degree(c, comp, cid, out + pos);
         } else {
             comp = order;
-            nd_rec(c, comp, cid, out + pos);
+            nd_rec(c, comp, cid, out + pos, depth);
         }
         pos += (int)order.size();
     }
 }
 
 // connected subgraph; `order`/`lptr` hold a BFS from verts[0] (levels still set in c.lvl)
-void nd_component(NdCtx& c, std::vector<int>& verts, int id, int* out, std::vector<int>& order, std::vector<int>& lptr) {
+void nd_component(NdCtx& c, std::vector<int>& verts, int id, int* out, std::vector<int>& order, std::vector<int>& lptr, int depth) {
     const int m = (int)verts.size();
     // pseudo-peripheral start: walk to the far end a few times
     int nl = (int)lptr.size() - 1;
@@ -299,8 +302,19 @@ void nd_component(NdCtx& c, std::vector<int>& verts, int id, int* out, std::vect
     }
     S.clear();
     S.shrink_to_fit();
-    nd_rec(c, A, idA, out);
-    nd_rec(c, B, idB, out + sa);
+    // The two halves are independent: the separator (already relabelled) keeps every vertex of A away from every vertex
+    // of B, so the per-vertex scratch arrays (label, lvl, loc) are touched at disjoint indices and the halves write
+    // disjoint slices of `out`.  The first three dissection levels of a large graph are ordered by two threads each
+    // (up to 8 concurrent); the resulting permutation does not depend on the schedule (labels are only compared for equality).
+    static const bool serial = getenv("B200_ND_SERIAL") != nullptr; // (tests compare the threaded and the serial ordering)
+    if (!serial && depth < 3 && sa + sb > 40000 && std::thread::hardware_concurrency() > 1) {
+        std::thread other([&c, &A, idA, out, depth]() { nd_rec(c, A, idA, out, depth + 1); });
+        nd_rec(c, B, idB, out + sa, depth + 1);
+        other.join();
+    } else {
+        nd_rec(c, A, idA, out, depth + 1);
+        nd_rec(c, B, idB, out + sa, depth + 1);
+    }
 }
 
 } // namespace

@@ -417,3 +417,27 @@ def test_analysis_stats_are_sane_at_scale():
     assert rc == 0
     assert st["nnz_l"] + st["nnz_u"] < 6.0e6
     assert st["max_front"] < 600
+
+
+def test_threaded_nested_dissection_equals_serial():
+    # ordering.cpp orders the two halves of the first three dissection levels on separate threads; the permutation must
+    # not depend on the schedule.  The serial run happens in a child process (the switch is read once per process).
+    import os
+    import subprocess
+    import sys
+
+    HERE = os.path.dirname(os.path.abspath(__file__))
+    ROOT = os.path.dirname(HERE)
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import numpy as np, helpers\nfrom oracle import oracle\n"
+            "n, ai, aj, ax = helpers.convection_diffusion_triplets(260)\n"
+            "bp, bj, bx = oracle.coo_to_csr(n, n, ai, aj, ax)\n"
+            "rc, x, st = oracle.mf_solve(n, bp, bj, bx, np.ones(n))\n"
+            "print(rc, float(x.sum()).hex(), float(np.abs(x).max()).hex(), int(st['nnz_l']), int(st['nlevels']))\n"
+            % (ROOT, HERE))
+    outs = []
+    for env_extra in ({}, {"B200_ND_SERIAL": "1"}, {}):
+        env = dict(os.environ, **env_extra)
+        outs.append(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout.strip())
+    assert outs[0] == outs[1] == outs[2], outs
+    assert outs[0].startswith("0 ")
