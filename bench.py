@@ -319,7 +319,7 @@ def main():
                     "rel_residual": res_e2e, "api": "solver_b200_factorize + solver_b200_solve (pinned host buffers)"},
             "gpu_launches": int(K * (st["launches_factorize"] + st["launches_solve"])),
             "clocks": clocks,
-            "roofline": {"kernel": "SpTRSV sweep (k_fwd + k_bwd over all tree levels, one forward+backward solve)",
+            "roofline": {"kernel": "SpTRSV sweep = k_fwd_subtree + k_fwd_top2 + k_bwd_top3 + k_bwd_subtree (one forward+backward solve over the whole front tree; algorithmic bytes = 8 B per stored factor entry + 16 B per unknown)",
                          "bound": "hbm", "achieved": sptrsv_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": sptrsv_gbs / hbm_peak,
                          "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes": st["sptrsv_bytes"], "ms": parts["sptrsv"]},
