@@ -171,6 +171,110 @@ void nd_rec(NdCtx& c, std::vector<int>& verts, int id, int* out, int depth = 0) 
     }
 }
 
+// Minimum-vertex-cover refinement of a separator `sep` (label `id`) between sides idA and idB.
+// X = separator vertices with a neighbour in B, Y = B vertices with a neighbour in the separator.  A maximum matching of
+// the bipartite graph (X, Y) is found by augmenting paths; with Z = everything reachable from the unmatched X vertices by
+// alternating paths, (X \ Z) + (Y & Z) covers every X-Y edge.  The new separator is that cover; X & Z and the separator
+// vertices without B neighbours go to A.
+void shrink_separator_by_cover(NdCtx& c, std::vector<int>& sep, int id, int idA, int idB, long& na, long& nb) {
+    std::vector<int> X, Y;
+    for (int v : sep) {
+        bool touches_b = false;
+        for (int e = c.g.ptr[v]; e < c.g.ptr[v + 1] && !touches_b; e++) touches_b = c.label[c.g.adj[e]] == idB;
+        if (touches_b) X.push_back(v);
+    }
+    if (X.size() < 8) return;
+    for (size_t i = 0; i < X.size(); i++) c.loc[X[i]] = (int)i;
+    for (int v : X)
+        for (int e = c.g.ptr[v]; e < c.g.ptr[v + 1]; e++) {
+            const int w = c.g.adj[e];
+            if (c.label[w] == idB && c.loc[w] < 0) c.loc[w] = (int)Y.size(), Y.push_back(w);
+        }
+    const int nx = (int)X.size(), ny = (int)Y.size();
+    std::vector<int> mx(nx, -1), my(ny, -1), seen(ny, -1);
+    // iterative augmenting-path search from every X vertex
+    std::vector<int> stack_x, stack_e, parent_y(ny, -1);
+    int matched = 0;
+    for (int s0 = 0; s0 < nx; s0++) {
+        stack_x.assign(1, s0);
+        stack_e.assign(1, c.g.ptr[X[s0]]);
+        int found = -1;
+        while (!stack_x.empty() && found < 0) {
+            const int x = stack_x.back();
+            int& e = stack_e.back();
+            bool pushed = false;
+            for (; e < c.g.ptr[X[x] + 1]; e++) {
+                const int w = c.g.adj[e];
+                if (c.label[w] != idB) continue;
+                const int y = c.loc[w];
+                if (seen[y] == s0) continue;
+                seen[y] = s0;
+                parent_y[y] = x;
+                if (my[y] < 0) {
+                    found = y;
+                    break;
+                }
+                e++;
+                stack_x.push_back(my[y]);
+                stack_e.push_back(c.g.ptr[X[my[y]]]);
+                pushed = true;
+                break;
+            }
+            if (found >= 0 || pushed) continue;
+            stack_x.pop_back();
+            stack_e.pop_back();
+        }
+        if (found >= 0) { // flip the path
+            int y = found;
+            while (y >= 0) {
+                const int x = parent_y[y];
+                const int prev = mx[x];
+                mx[x] = y, my[y] = x;
+                y = prev;
+            }
+            matched++;
+        }
+    }
+    if (matched < nx) { // the cover is smaller than X: apply it
+        std::vector<char> zx(nx, 0), zy(ny, 0);
+        std::vector<int> q;
+        for (int x = 0; x < nx; x++)
+            if (mx[x] < 0) zx[x] = 1, q.push_back(x);
+        while (!q.empty()) {
+            const int x = q.back();
+            q.pop_back();
+            for (int e = c.g.ptr[X[x]]; e < c.g.ptr[X[x] + 1]; e++) {
+                const int w = c.g.adj[e];
+                if (c.label[w] != idB) continue;
+                const int y = c.loc[w];
+                if (zy[y]) continue;
+                zy[y] = 1; // reached through a non-matching edge
+                const int x2 = my[y];
+                if (x2 >= 0 && !zx[x2]) zx[x2] = 1, q.push_back(x2); // and back along the matching edge
+            }
+        }
+        long pulled = 0;
+        for (int y = 0; y < ny; y++) pulled += zy[y] ? 1 : 0;
+        if (nb - pulled < 1 || 2 * (nb - pulled) < nb) { // side B must survive (and keep at least half of its vertices)
+            for (int v : X) c.loc[v] = -1;
+            for (int w : Y) c.loc[w] = -1;
+            return;
+        }
+        for (int x = 0; x < nx; x++)
+            if (zx[x]) c.label[X[x]] = idA, na++; // covered by its B neighbours, which join the separator
+        for (int y = 0; y < ny; y++)
+            if (zy[y]) c.label[Y[y]] = id, nb--;
+        std::vector<int> nsep;
+        for (int v : sep)
+            if (c.label[v] == id) nsep.push_back(v);
+        for (int y = 0; y < ny; y++)
+            if (zy[y]) nsep.push_back(Y[y]);
+        sep.swap(nsep);
+    }
+    for (int v : X) c.loc[v] = -1;
+    for (int w : Y) c.loc[w] = -1;
+}
+
 // connected subgraph; `order`/`lptr` hold a BFS from verts[0] (levels still set in c.lvl)
 void nd_component(NdCtx& c, std::vector<int>& verts, int id, int* out, std::vector<int>& order, std::vector<int>& lptr, int depth) {
     const int m = (int)verts.size();
@@ -238,6 +342,11 @@ void nd_component(NdCtx& c, std::vector<int>& verts, int id, int* out, std::vect
     clear_levels(c, order);
     order.clear();
     order.shrink_to_fit();
+    // A BFS level is a wide separator on irregular graphs: shrink it to a minimum vertex cover of the edges that join it
+    // to side B (Koenig: |cover| = |maximum matching| of the bipartite boundary graph).  Separator vertices that are
+    // not needed move to A, covering B vertices join the separator.  Applied only when it strictly shrinks the
+    // separator (on regular grids every level-set vertex is matched: nothing changes there).
+    shrink_separator_by_cover(c, sep, id, idA, idB, na, nb);
 
     // refinement: trim vertices that touch only one side, then zero-gain balancing moves
     for (int pass = 0; pass < 3; pass++) {
