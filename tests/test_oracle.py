@@ -441,3 +441,27 @@ def test_threaded_nested_dissection_equals_serial():
         outs.append(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout.strip())
     assert outs[0] == outs[1] == outs[2], outs
     assert outs[0].startswith("0 ")
+
+
+def test_host_walk_unstructured_graphs():
+    # irregular graphs (k-nearest-neighbour meshes in 2D and 3D): the level-set separators are shrunk by the
+    # minimum-vertex-cover refinement (ordering.cpp: shrink_separator_by_cover); the walk must still solve the system
+    import scipy.sparse as sp
+    from scipy.spatial import cKDTree
+
+    rng = np.random.default_rng(1)
+    for npts, dim in ((6000, 2), (4000, 3)):
+        pts = rng.random((npts, dim))
+        _, idx = cKDTree(pts).query(pts, k=7)
+        rows, cols = np.repeat(np.arange(npts), 6), idx[:, 1:].ravel()
+        g = sp.coo_matrix((np.ones(len(rows)), (rows, cols)), shape=(npts, npts))
+        g = (g + g.T).tocsr()
+        g.data[:] = -1.0
+        a = (g + sp.diags(np.asarray(-g.sum(axis=1)).ravel() + 1.0)).tocsr()
+        a.sort_indices()
+        b = np.ones(npts)
+        rc, x, st = oracle.mf_solve(npts, a.indptr.astype(np.int32), a.indices.astype(np.int32), a.data, b)
+        assert rc == 0
+        assert np.linalg.norm(b - a @ x) / np.linalg.norm(b) <= 1e-10
+        xs = oracle.lu_solve(a.tocsc(), b)
+        assert np.max(np.abs(x - xs)) <= 1e-9 * np.max(np.abs(xs))
