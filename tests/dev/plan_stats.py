@@ -1,18 +1,18 @@
 #!/usr/bin/env python3
 """CPU-only view of the front tree the host analysis builds (no GPU needed): per level the number of fronts, pivot and
 update-row statistics and stored entries; the separator chains (supernodes split into panels); the subtree partition the
-solve phase would use.  Usage: python tools/plan_stats.py [grid=1000]  (5-point Laplacian)  |  --brusselator N"""
+solve phase would use.  Usage: python tests/dev/plan_stats.py [grid=1000]  (5-point Laplacian)  |  --brusselator N"""
 import ctypes
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import helpers  # noqa: E402
-from oracle import oracle  # noqa: E402  (tools/ are development aids, not product code)
+from oracle import oracle  # noqa: E402  (lives under tests/: only test infrastructure may use oracle/)
 
 oracle.build()
 lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_build", "liboracle_mf.so"))
