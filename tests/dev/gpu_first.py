@@ -2,7 +2,7 @@
 """First-contact GPU diagnostics: runs the C-ABI solver on small and large systems and compares every stage
 with the CPU checkers.  Prints one line per check; never raises, so that one gpurun call reports everything."""
 import os, sys, time, traceback
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import russell_b200 as rb
