@@ -121,10 +121,11 @@ def test_no_device_means_no_solver_not_a_cpu_fallback():
 
 def test_product_does_not_import_the_oracle():
     # the oracle is test infrastructure: nothing under russell_b200/ may reference it
-    pkg = os.path.join(ROOT, "russell_b200")
-    for dirpath, _, files in os.walk(pkg):
-        for fn in files:
-            if fn.endswith((".py", ".cpp", ".cu", ".cuh", ".hpp", ".h")):
-                with open(os.path.join(dirpath, fn)) as f:
-                    txt = f.read()
-                assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt.replace("// ", ""), fn
+    for top in ("russell_b200", "tools", "bindings", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for fn in files:
+                if fn.endswith((".py", ".cpp", ".cu", ".cuh", ".hpp", ".h", ".rs")):
+                    with open(os.path.join(dirpath, fn)) as f:
+                        txt = f.read()
+                    assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt.replace("// ", ""), fn
+                    assert "liboracle" not in txt, fn
