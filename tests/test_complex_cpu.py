@@ -245,3 +245,66 @@ def test_read_matrix_market_complex_value_errors(tmp_path):
         f.write_text("%%MatrixMarket matrix coordinate complex general\n2 2 1\n" + body)
         with pytest.raises(rb.StrError, match=msg):
             rb.read_matrix_market(str(f), rb.MMsym.LeaveAsLower)
+
+
+# ---- randomized checks ----------------------------------------------------------------------------------------------
+def test_complex_converter_random_with_duplicates_bit_exact():
+    # product (C++ stable sort + in-order sums) vs the oracle's restatement on random triplets with many duplicates
+    rng = np.random.default_rng(11)
+    for nrow, ncol, nnz in ((7, 5, 60), (40, 40, 900), (1, 9, 30), (300, 300, 5000)):
+        ai = rng.integers(0, nrow, nnz).astype(np.int32)
+        aj = rng.integers(0, ncol, nnz).astype(np.int32)
+        av = rng.standard_normal(nnz) + 1j * rng.standard_normal(nnz)
+        coo = rb.ComplexCooMatrix.from_triplets(nrow, ncol, ai, aj, av)
+        csr = rb.ComplexCsrMatrix.from_coo(coo)
+        bp, bj, bx = oracle.complex_coo_to_csr(nrow, ncol, ai, aj, av)
+        k = csr.nnz
+        assert np.array_equal(csr.pointers, bp) and np.array_equal(csr.indices[:k], bj) and np.array_equal(csr.values[:k], bx)
+        csc = rb.ComplexCscMatrix.from_coo(coo)
+        cp, cj, cx = oracle.complex_coo_to_csr(ncol, nrow, aj, ai, av)  # columns of A = rows of A^T
+        assert np.array_equal(csc.pointers, cp) and np.array_equal(csc.indices[:k], cj) and np.array_equal(csc.values[:k], cx)
+        # and the mat-vec of the oracle agrees with the dense product
+        u = rng.standard_normal(ncol) + 1j * rng.standard_normal(ncol)
+        dense = np.zeros((nrow, ncol), dtype=np.complex128)
+        np.add.at(dense, (ai, aj), av)
+        assert np.allclose(oracle.complex_coo_matvec(nrow, ai, aj, av, u), dense @ u, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("seed,lower", [(0, False), (1, True), (2, False)])
+def test_scalar_walk_of_random_complex_systems(seed, lower):
+    # random sparse complex matrices (unsymmetric with an empty diagonal, or complex symmetric in lower storage): embedding
+    # + host analysis + scalar walk against the complex CPU LU
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(seed)
+    n = 120
+    a = sp.random(n, n, density=0.04, random_state=seed, format="coo")
+    ai, aj = a.row.astype(np.int32), a.col.astype(np.int32)
+    av = a.data + 1j * rng.standard_normal(len(a.data))
+    if lower:
+        keep = aj < ai
+        ai, aj, av = ai[keep], aj[keep], av[keep]
+        ai = np.concatenate([ai, np.arange(n, dtype=np.int32)])
+        aj = np.concatenate([aj, np.arange(n, dtype=np.int32)])
+        av = np.concatenate([av, 4.0 + 2.0j + rng.standard_normal(n)])
+        sym = rb.Sym.YesLower
+    else:
+        perm = rng.permutation(n).astype(np.int32)  # the heavy entries sit on a hidden permutation, not on the diagonal
+        keep = ai != aj
+        ai = np.concatenate([ai[keep], np.arange(n, dtype=np.int32)])
+        aj = np.concatenate([aj[keep], perm])
+        av = np.concatenate([av[keep], (8.0 + rng.random(n)) * np.exp(1j * rng.random(n))])
+        keep = ai != aj
+        ai, aj, av = ai[keep], aj[keep], av[keep]
+        sym = rb.Sym.No
+    coo = rb.ComplexCooMatrix.from_triplets(n, n, ai, aj, av, sym)
+    csr = rb.ComplexCsrMatrix.from_coo(coo)
+    rptr, rcol, _, rval, _ = embed(csr, lower)
+    b = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    rc, x, st = oracle.mf_solve(2 * n, rptr, rcol, rval, b.view(np.float64))
+    assert rc == 0
+    dense = coo.as_dense()
+    z = x.view(np.complex128)
+    assert np.linalg.norm(b - dense @ z) / np.linalg.norm(b) <= 1e-10
+    zs = oracle.lu_solve(sp.csc_matrix(dense), b)
+    assert np.max(np.abs(z - zs)) <= 1e-8 * np.max(np.abs(zs))
