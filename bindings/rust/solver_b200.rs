@@ -34,22 +34,30 @@ unsafe extern "C" {
     fn solver_b200_solve(solver: *mut InterfaceB200, x: *mut f64, rhs: *const f64, verbose: CcBool) -> i32;
 }
 
-/// Integers the C side understands (include/solver_b200.h): 0 default (nested dissection), 3 minimum degree, 5 natural
+/// Same integers as `cudss_ordering` (russell_sparse/src/solver_cudss.rs:425-441) and as the tested Python twin: the C side
+/// maps 3 to minimum degree, 5 to the natural order and everything else to nested dissection (include/solver_b200.h)
 pub(crate) fn b200_ordering(ordering: Ordering) -> i32 {
     match ordering {
-        Ordering::Amd | Ordering::Qamd | Ordering::Amf => 3,
-        Ordering::Metis | Ordering::Scotch | Ordering::Pord => 4,
+        Ordering::BtfColamd => 1,
+        Ordering::Colamd => 2,
+        Ordering::Amd => 3,
+        Ordering::Metis => 4,
         Ordering::No => 5,
         _ => 0,
     }
 }
 
-/// 0 none (upgraded to "auto" by the library: zero diagonals get a max-product matching), 5 max-product, 6 auto
+/// Same integers as `cudss_matching` (solver_cudss.rs:459-469): 0 none (upgraded to "auto" by the library: zero diagonals get a
+/// max-product matching + scaling), 6 auto, 1..5 force the matching
 pub(crate) fn b200_matching(matching: Matching) -> i32 {
     match matching {
         Matching::None => 0,
+        Matching::MaxDiagCount => 1,
+        Matching::MaxMinDiag => 2,
+        Matching::MaxMinDiagAlt => 3,
+        Matching::MaxDiagSum => 4,
+        Matching::MaxDiagProduct => 5,
         Matching::Auto => 6,
-        _ => 5,
     }
 }
 
