@@ -298,10 +298,17 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
         for (int k = 0; k < n; k++) q2[k] = q[post[k]];
         q.swap(q2);
         relabel_graph(g0, q, g);
-        etree_symmetric(g, parent);
-        std::vector<int> ident(n);
-        std::iota(ident.begin(), ident.end(), 0);
-        column_counts_post(g, parent, ident, cc);
+        // A postorder only renames the vertices of the elimination tree: parents and column counts of the final
+        // labelling follow from the first pass by renaming (no second etree / column-count computation).
+        std::vector<int> newid(n);
+        for (int k = 0; k < n; k++) newid[post[k]] = k;
+        parent.assign(n, -1);
+        cc.assign(n, 0);
+        for (int k = 0; k < n; k++) {
+            const int old = post[k];
+            parent[k] = par1[old] < 0 ? -1 : newid[par1[old]];
+            cc[k] = cc1[old];
+        }
     }
     g0 = Graph();
     std::vector<int> invq(n);
