@@ -36,9 +36,9 @@ extern "C" {
 #define B200_ERROR_CUDA_MALLOC 100               /* constants.h:22 */
 #define B200_ERROR_CUDA_MEMCPY 200               /* constants.h:23 */
 #define B200_ERROR_CUDA_SYNCHRONIZE 300          /* constants.h:24 */
-#define B200_ERROR_ANALYSIS 700                  /* phase offset like ERROR_CUDSS_SYM_FACTORIZATION; +1 structurally singular, +2 invalid CSR, +3 invalid COO, +4 COO not lower */
+#define B200_ERROR_ANALYSIS 700                  /* phase offset like ERROR_CUDSS_SYM_FACTORIZATION; +1 structurally singular, +2 invalid CSR, +3 invalid COO, +4 COO not lower, +5 COO structure differs from the analysed one */
 #define B200_ERROR_NUM_FACTORIZATION 800         /* phase offset like ERROR_CUDSS_NUM_FACTORIZATION; +1 kernel launch failure, +2 non-finite values */
-#define B200_ERROR_SOLVE 900                     /* phase offset like ERROR_CUDSS_SOLVE; +1 kernel launch failure, +7 refinement failed */
+#define B200_ERROR_SOLVE 900                     /* phase offset like ERROR_CUDSS_SOLVE; +1 kernel launch failure, +7 refinement failed (residual NaN, or above 10 x ir_tol with a backward error above rounding level) */
 
 /* ---- option values (same integers the Rust maps for cuDSS send, solver_cudss.rs:393-466) ------------------- */
 #define B200_ORDERING_DEFAULT 0  /* nested dissection */
@@ -99,6 +99,13 @@ int32_t solver_b200_initialize_coo(struct InterfaceB200 *solver,
 int32_t solver_b200_factorize_coo(struct InterfaceB200 *solver, int32_t *effective_matching,
                                   int32_t *effective_pivoting, int32_t verbose, const double *coo_values);
 int32_t solver_b200_factorize_coo_device(struct InterfaceB200 *solver, const double *d_coo_values);
+/* factorize_coo that also receives the triplet indices, like CsrMatrix::update_from_coo does on every call in the reference
+ * (solver_cudss.rs:209): identical indices -> same as factorize_coo (the comparison runs on a helper thread underneath the
+ * copy and the kernels); same pattern, triplets in another order -> the slot map is rebuilt; another pattern or nnz ->
+ * B200_ERROR_ANALYSIS+5 (the structure is frozen after the first call, solver_cudss.rs:196-208) */
+int32_t solver_b200_factorize_coo_checked(struct InterfaceB200 *solver, int32_t *effective_matching,
+                                          int32_t *effective_pivoting, int32_t verbose, int32_t nnz_coo,
+                                          const int32_t *indices_i, const int32_t *indices_j, const double *coo_values);
 
 /* residual r = rhs - A x with the CSR SpMV kernel; returns ||r||_2 / ||rhs||_2 through *rel_residual
  * (russell's VerifyLinSys / the north-star accuracy metric).  Host pointers. */
@@ -106,6 +113,10 @@ int32_t solver_b200_residual(struct InterfaceB200 *solver, const double *x, cons
 
 /* y <- A x on the device (host pointers; SpMV kernel parity tests) */
 int32_t solver_b200_spmv(struct InterfaceB200 *solver, double *y, const double *x);
+
+/* reciprocal condition number estimate, UMFPACK's definition: min|U_kk| / max|U_kk| (Info[UMFPACK_RCOND],
+ * interface_umfpack.c:179-184 -> StatsLinSol.output.umfpack_rcond_estimate) */
+int32_t solver_b200_rcond(struct InterfaceB200 *solver, double *rcond);
 
 /* determinant as mantissa * 10^exponent (StatsLinSol / solver_umfpack.rs:141-152 convention) */
 int32_t solver_b200_determinant(struct InterfaceB200 *solver, double *coefficient, double *exponent);
@@ -135,10 +146,14 @@ int32_t solver_b200_determinant(struct InterfaceB200 *solver, double *coefficien
 #define B200_STAT_MATCHED 21
 #define B200_STAT_T_MATCH_S 22
 #define B200_STAT_LAST_BACKWARD_ERROR 23 /* max_i |r_i| / (|A||x|+|b|)_i of the last solve */
-#define B200_STAT_COUNT 24
+#define B200_STAT_EFFECTIVE_ORDERING 24   /* B200_ORDERING_ND / _AMD / _NONE: what the analysis actually ran (UMFPACK_ORDERING_USED, interface_umfpack.c:180) */
+#define B200_STAT_EFFECTIVE_SCALING 25    /* 0 = none, 1 = row/column scaling from the max-product matching (UMFPACK_SCALE, interface_umfpack.c:181) */
+#define B200_STAT_RCOND 26                /* last solver_b200_rcond value, -1 when not computed for the current factors */
+#define B200_STAT_T_INITIALIZE_HOST_S 27  /* wall time of the host analysis (matching + ordering + symbolic + plan) */
+#define B200_STAT_COUNT 28
 int32_t solver_b200_get_stats(struct InterfaceB200 *solver, double *out, int32_t n_out);
 
-/* tuning knobs, to be set before initialize ("ir_tol" and "refinement_nstep" also later).  Host analysis: "panel_width",
+/* tuning knobs, to be set before initialize ("ir_tol", "refinement_nstep" and "strict_residual" also later).  Host analysis: "panel_width",
  * "nd_leaf", "relax_small", "relax_z1", "relax_z2", "relax_z3", "force_no_matching".  Execution: "device", "use_graph",
  * "ir_tol", "refinement_nstep", "trace".  Kernel variants kept for A/B measurements (defaults = the measured optimum, see
  * DESIGN.md): "schur_variant", "schur_occ3_min", "panel_variant", "panel_row_max", "diag_variant", "invert_variant",
@@ -194,6 +209,9 @@ int32_t complex_solver_b200_initialize_coo(struct InterfaceComplexB200 *solver,
                                            const double *values /* Complex64[nnz_coo] */);
 int32_t complex_solver_b200_factorize_coo(struct InterfaceComplexB200 *solver, int32_t *effective_matching,
                                           int32_t *effective_pivoting, int32_t verbose, const double *coo_values);
+int32_t complex_solver_b200_factorize_coo_checked(struct InterfaceComplexB200 *solver, int32_t *effective_matching,
+                                                  int32_t *effective_pivoting, int32_t verbose, int32_t nnz_coo,
+                                                  const int32_t *indices_i, const int32_t *indices_j, const double *coo_values);
 /* extensions, as for the real solver: device-resident variants, A x and residual through the SpMV kernel, stats and
  * options of the underlying order-2n real handle */
 int32_t complex_solver_b200_factorize_device(struct InterfaceComplexB200 *solver, const double *d_values);

@@ -344,6 +344,7 @@ _B200_ERRORS = {  # same spirit as handle_cudss_error_code (solver_cudss.rs:501-
     702: "B200 analysis failed: invalid CSR structure",
     703: "B200 analysis failed: invalid COO structure (index out of range or empty)",
     704: "B200 analysis failed: Sym::YesLower requires triplets with j <= i",
+    705: "subsequent factorizations must use the same matrix (the COO structure differs from the analysed one)",
     801: "B200 numeric factorization failed: kernel launch failure",
     802: "B200 numeric factorization failed: matrix values are not finite",
     901: "B200 solve failed: kernel launch failure",
@@ -369,6 +370,12 @@ class StatsLinSol:
         self.solver = "Unknown"
         self.effective_matching = "Unknown"
         self.effective_pivoting = "Unknown"
+        self.effective_ordering = "Unknown"  # stats_lin_sol.rs:50-60 (StatsLinSolOutput)
+        self.effective_scaling = "Unknown"
+        self.rcond_estimate = 0.0
+        self.determinant = (0.0, 0.0)  # (mantissa, exponent), base 10
+        self.n_perturbed = 0
+        self.rel_residual = -1.0
         self.initialize_array, self.factorize_array, self.solve_array = [], [], []
         self.device = {}
 
@@ -379,7 +386,8 @@ class SolverB200:
     STAT_NAMES = ["nnodes", "nlevels", "nnz_l", "nnz_u", "flops", "fac_bytes", "cb_bytes", "max_front", "t_order_s",
                   "t_symbolic_s", "n_perturbed", "last_rel_residual", "last_refine_steps", "ms_factorize_device",
                   "ms_solve_device", "ms_sptrsv_device", "ms_spmv_device", "launches_factorize", "launches_solve",
-                  "sptrsv_bytes", "spmv_bytes", "matched", "t_match_s", "last_backward_error"]
+                  "sptrsv_bytes", "spmv_bytes", "matched", "t_match_s", "last_backward_error", "effective_ordering",
+                  "effective_scaling", "rcond", "t_initialize_host_s"]
 
     def __init__(self, coo_boundary=True):
         """coo_boundary=True: the triplet structure is analysed once (solver_b200_initialize_coo) and every later
@@ -478,7 +486,10 @@ class SolverB200:
         em, ep = _lib.c_i32(0), _lib.c_i32(0)
         t0 = time.perf_counter_ns()
         if self.coo_boundary:
-            status = self._lib.solver_b200_factorize_coo(self.solver, ctypes.byref(em), ctypes.byref(ep), verbose, ptr(coo_v, p_f64))
+            # the triplet indices travel with the values, like CsrMatrix::update_from_coo sees them on every call
+            # (solver_cudss.rs:209): a CooMatrix refilled in another triplet order must not land in the wrong slots
+            status = self._lib.solver_b200_factorize_coo_checked(self.solver, ctypes.byref(em), ctypes.byref(ep), verbose,
+                                                                 _to_i32(mat.nnz), ptr(coo_i, p_i32), ptr(coo_j, p_i32), ptr(coo_v, p_f64))
         else:
             status = self._lib.solver_b200_factorize(self.solver, ctypes.byref(em), ctypes.byref(ep), verbose, ptr(csr.values, p_f64))
         if status != 0:
@@ -551,8 +562,20 @@ class SolverB200:
             raise StrError(handle_b200_error_code(rc))
         return c.value, e.value
 
-    def update_stats(self, stats):  # solver_cudss.rs:362-390
+    def rcond(self):
+        """UMFPACK's reciprocal condition number estimate min|U_kk| / max|U_kk| (interface_umfpack.c:179-184)"""
+        import ctypes
+        out = ctypes.c_double(0.0)
+        rc = self._lib.solver_b200_rcond(self.solver, ctypes.byref(out))
+        if rc != 0:
+            raise StrError(handle_b200_error_code(rc))
+        return out.value
+
+    def update_stats(self, stats):  # solver_cudss.rs:362-390 + the UMFPACK output fields (solver_umfpack.rs:392-422)
         stats.solver = "B200"
+        if self.factorized:
+            stats.rcond_estimate = self.rcond()
+            stats.determinant = self.determinant()
         stats.initialize_array.append(self.time_initialize_ns)
         stats.factorize_array.append(self.time_factorize_ns)
         stats.solve_array.append(self.time_solve_ns)
@@ -562,6 +585,10 @@ class SolverB200:
         stats.effective_pivoting = piv.get(self.effective_pivoting, "Unknown")
         if self.initialized:
             stats.device = self.device_stats()
+            stats.effective_ordering = {0: "Metis", 4: "Metis", 3: "Amd", 5: "No"}.get(int(stats.device["effective_ordering"]), "Unknown")
+            stats.effective_scaling = "Max" if stats.device["effective_scaling"] else "No"
+            stats.n_perturbed = int(stats.device["n_perturbed"])
+            stats.rel_residual = stats.device["last_rel_residual"]
 
     def get_ns_init(self):
         return self.time_initialize_ns

@@ -31,6 +31,8 @@ SIGNATURES = {
                                            c_i32, p_i32, p_i32, p_f64]),
     "solver_b200_factorize_coo": (c_i32, [p_void, p_i32, p_i32, c_i32, p_f64]),
     "solver_b200_factorize_coo_device": (c_i32, [p_void, p_void]),
+    "solver_b200_factorize_coo_checked": (c_i32, [p_void, p_i32, p_i32, c_i32, c_i32, p_i32, p_i32, p_f64]),
+    "solver_b200_rcond": (c_i32, [p_void, p_f64]),
     "solver_b200_solve_device": (c_i32, [p_void, p_void, p_void]),
     "solver_b200_residual": (c_i32, [p_void, p_f64, p_f64, p_f64]),
     "solver_b200_spmv": (c_i32, [p_void, p_f64, p_f64]),
@@ -52,6 +54,7 @@ SIGNATURES = {
     "complex_solver_b200_initialize_coo": (c_i32, [p_void, c_i32, c_i32, c_i32, c_f64, c_i32, c_f64, c_i32, c_i32, c_i32, c_i32,
                                                    c_i32, p_i32, p_i32, p_f64]),
     "complex_solver_b200_factorize_coo": (c_i32, [p_void, p_i32, p_i32, c_i32, p_f64]),
+    "complex_solver_b200_factorize_coo_checked": (c_i32, [p_void, p_i32, p_i32, c_i32, c_i32, p_i32, p_i32, p_f64]),
     "complex_solver_b200_factorize_device": (c_i32, [p_void, p_void]),
     "complex_solver_b200_solve_device": (c_i32, [p_void, p_void, p_void]),
     "complex_solver_b200_spmv": (c_i32, [p_void, p_f64, p_f64]),

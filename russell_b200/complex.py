@@ -212,8 +212,9 @@ class ComplexSolverB200:
         em, ep = _lib.c_i32(0), _lib.c_i32(0)
         t0 = time.perf_counter_ns()
         if self.coo_boundary:
-            status = self._lib.complex_solver_b200_factorize_coo(self.solver, ctypes.byref(em), ctypes.byref(ep), verbose,
-                                                                 ptr(coo_v, p_f64))
+            status = self._lib.complex_solver_b200_factorize_coo_checked(self.solver, ctypes.byref(em), ctypes.byref(ep), verbose,
+                                                                         _to_i32(mat.nnz), ptr(coo_i, p_i32), ptr(coo_j, p_i32),
+                                                                         ptr(coo_v, p_f64))
         else:
             status = self._lib.complex_solver_b200_factorize(self.solver, ctypes.byref(em), ctypes.byref(ep), verbose,
                                                              ptr(csr.values, p_f64))

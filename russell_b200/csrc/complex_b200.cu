@@ -28,9 +28,11 @@
 
 #include "../../include/solver_b200.h"
 
+#include "coo_guard.hpp"
+#include <atomic>
+#include <thread>
+
 // host side of the COO conversion and of the embedding (host_formats.cpp)
-extern "C" int32_t b200_coo_to_csr_map(int32_t nrow, int32_t ncol, int32_t nnz, const int32_t* ai, const int32_t* aj, const double* ax,
-                                       int32_t* ptr, int32_t* idx, double* val, int32_t* seg_ptr, int32_t* seg_idx);
 extern "C" int32_t b200_complex_embed(int32_t n, const int32_t* rp, const int32_t* ci, const double* values, int32_t lower,
                                       int64_t* info, int32_t* rptr, int32_t* rcol, int32_t* code, double* rval);
 
@@ -79,6 +81,7 @@ struct InterfaceComplexB200 {
     int nnz_coo = 0;
     int *d_seg_ptr = nullptr, *d_seg_idx = nullptr;
     double2* d_coo_cvals = nullptr;
+    b200::CooGuard coo_guard;
 };
 
 #define CB_CUDA_TRY(call, code)             \
@@ -230,6 +233,7 @@ int32_t complex_solver_b200_initialize_coo(struct InterfaceComplexB200* s, int32
     CB_CUDA_TRY(cudaMemcpyAsync(s->d_seg_ptr, seg_ptr.data(), ((size_t)nslots + 1) * sizeof(int), cudaMemcpyHostToDevice, st), B200_ERROR_CUDA_MEMCPY);
     CB_CUDA_TRY(cudaMemcpyAsync(s->d_seg_idx, seg_idx.data(), (size_t)nnz_coo * sizeof(int), cudaMemcpyHostToDevice, st), B200_ERROR_CUDA_MEMCPY);
     CB_CUDA_TRY(cudaStreamSynchronize(st), B200_ERROR_CUDA_SYNCHRONIZE);
+    s->coo_guard.remember(ndim, nnz_coo, indices_i, indices_j, ptr, idx);
     return B200_SUCCESSFUL_EXIT;
 }
 
@@ -254,6 +258,28 @@ int32_t complex_solver_b200_factorize_coo(struct InterfaceComplexB200* s, int32_
     }
     if (effective_pivoting) *effective_pivoting = 5;
     return rc;
+}
+
+int32_t complex_solver_b200_factorize_coo_checked(struct InterfaceComplexB200* s, int32_t* effective_matching, int32_t* effective_pivoting,
+                                                  int32_t verbose, int32_t nnz_coo, const int32_t* indices_i, const int32_t* indices_j,
+                                                  const double* coo_values) {
+    if (!s) return B200_ERROR_NULL_POINTER;
+    if (!s->initialized || !s->d_seg_ptr || !s->coo_guard.armed()) return B200_ERROR_NEED_INITIALIZATION;
+    if (!indices_i || !indices_j || !coo_values) return B200_ERROR_NULL_POINTER;
+    if (nnz_coo != s->nnz_coo) return B200_ERROR_ANALYSIS + 5;
+    std::atomic<int> same{1};
+    std::thread checker([&] { same.store(s->coo_guard.same(indices_i, indices_j) ? 1 : 0); });
+    int32_t rc = complex_solver_b200_factorize_coo(s, effective_matching, effective_pivoting, verbose, coo_values);
+    checker.join();
+    if (same.load()) return rc;
+    std::vector<int32_t> seg_ptr, seg_idx;
+    if (s->coo_guard.remap(indices_i, indices_j, seg_ptr, seg_idx) != 0) return B200_ERROR_ANALYSIS + 5;
+    CB_CUDA_TRY(cudaSetDevice(solver_b200_get_device(s->real)), B200_ERROR_NOT_AVAILABLE);
+    cudaStream_t st = (cudaStream_t)solver_b200_get_stream(s->real);
+    CB_CUDA_TRY(cudaMemcpyAsync(s->d_seg_ptr, seg_ptr.data(), ((size_t)s->nnz + 1) * sizeof(int), cudaMemcpyHostToDevice, st), B200_ERROR_CUDA_MEMCPY);
+    CB_CUDA_TRY(cudaMemcpyAsync(s->d_seg_idx, seg_idx.data(), (size_t)nnz_coo * sizeof(int), cudaMemcpyHostToDevice, st), B200_ERROR_CUDA_MEMCPY);
+    CB_CUDA_TRY(cudaStreamSynchronize(st), B200_ERROR_CUDA_SYNCHRONIZE);
+    return complex_solver_b200_factorize_coo(s, effective_matching, effective_pivoting, verbose, coo_values);
 }
 
 int32_t complex_solver_b200_solve(struct InterfaceComplexB200* s, double* x, const double* rhs, int32_t verbose) {

@@ -24,6 +24,10 @@
 #include "kernels.cuh"
 #include "sweep_top.cuh"
 #include "plan.hpp"
+#include "coo_guard.hpp"
+#include <atomic>
+#include <chrono>
+#include <thread>
 
 using namespace b200;
 
@@ -95,6 +99,7 @@ struct InterfaceB200 {
     double ir_tol = 1e-11;
     double pivot_eps = 1e-13;
     int force_no_matching = 0;
+    int strict_residual = 0; // 1: solve returns B200_ERROR_SOLVE+7 whenever ||b-Ax||/||b|| > 10 ir_tol after refinement
 
     Plan plan;
     LevelLists lv;
@@ -125,7 +130,6 @@ struct InterfaceB200 {
     unsigned long long* d_trace = nullptr; // optional per-item timestamps of the persistent sweeps (option "trace")
     int want_trace = 0;
     int *d_node_slot = nullptr, *d_bdone = nullptr; // k_bwd_top3: scratch slot base per front, partial-products-done counters
-    int top_variant = 3;      // 1 = k_fwd_top/k_bwd_top, 2 = k_fwd_top2/k_bwd_top2 (descriptors and indices loaded before the dependency wait), 3 = k_fwd_top2/k_bwd_top3 (children finish their parent: one hop per level)
     int use_top = 1, ltop = 0, n_top_items = 0, top_grid = 0, top_grid_b = 0, n_slots = 0; // (the backward kernel needs less shared memory: its own, larger co-resident grid)
     bool sweep_dirty = false;          // a persistent sweep aborted: counters must be re-armed
     std::vector<int> cdone_init;       // host copy of the initial completion counters
@@ -147,6 +151,7 @@ struct InterfaceB200 {
     int nnz_coo = 0;
     int *d_seg_ptr = nullptr, *d_seg_idx = nullptr;
     double* d_coo_vals = nullptr;
+    CooGuard coo_guard; // host copy of the triplet indices the slot map was built from (solver_b200_factorize_coo_checked)
     const double* spmv_vals = nullptr; // mirrored values (symmetric input) or d_vals (general input)
     double *d_fac = nullptr, *d_cb = nullptr, *d_dinv = nullptr, *d_upiv = nullptr;
     int* d_lperm = nullptr;
@@ -173,6 +178,8 @@ struct InterfaceB200 {
 
     // stats
     int n_perturbed = 0;
+    double rcond = -1.0;      // last value computed by solver_b200_rcond (-1: not computed for these factors)
+    double t_init_host = 0.0; // wall time of the host analysis inside initialize
     double last_rel_residual = -1.0, last_backward_error = -1.0;
     int last_refine_steps = 0;
     float ms_factorize = 0, ms_solve = 0, ms_sptrsv = 0, ms_spmv = 0;
@@ -508,34 +515,30 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
-__global__ void k_bump_epoch(int* epoch) { *epoch += 1; }
-void k_fwd_top_launch(InterfaceB200* s) {
-    if (s->top_variant >= 2) {
-        k_fwd_top2<<<s->top_grid, 256, B200_TOP3_SMEM, s->stream>>>(s->d_top_items, s->n_top_items, s->d_nodes, s->d_rel, s->d_fac, s->d_dinv,
-                                                                 s->d_lperm, s->d_top_ranges, s->d_y, s->d_z, s->d_wv, s->d_cdone, s->d_epoch,
-                                                                 s->d_abort, s->d_trace);
-        return;
+// one sweep = one epoch of the completion counters; the item tickets of both persistent kernels restart at zero
+__global__ void k_bump_epoch(int* epoch) { epoch[0] += 1, epoch[1] = 0, epoch[2] = 0; }
+// min and max of |U_kk| (IEEE bit patterns of non-negative doubles order like unsigned integers): UMFPACK's rcond estimate
+__global__ void __launch_bounds__(256) k_minmax_abs(int n, const double* __restrict__ v, unsigned long long* __restrict__ mm) {
+    unsigned long long lo = ~0ull, hi = 0ull;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const unsigned long long b = (unsigned long long)__double_as_longlong(fabs(v[k]));
+        lo = b < lo ? b : lo, hi = b > hi ? b : hi;
     }
-    k_fwd_top<<<s->top_grid, 256, B200_TOP_SMEM, s->stream>>>(s->d_top_items, s->n_top_items, s->d_nodes, s->d_child_idx, s->d_rel, s->d_fac,
-                                                            s->d_dinv, s->d_lperm, s->d_top_ranges, s->d_y, s->d_z, s->d_wv, s->d_cdone,
-                                                            s->d_epoch, s->d_abort);
+    for (int off = 16; off > 0; off >>= 1) {
+        const unsigned long long l2 = __shfl_down_sync(0xffffffffu, lo, off), h2 = __shfl_down_sync(0xffffffffu, hi, off);
+        lo = l2 < lo ? l2 : lo, hi = h2 > hi ? h2 : hi;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMin(mm, lo), atomicMax(mm + 1, hi);
+}
+void k_fwd_top_launch(InterfaceB200* s) {
+    k_fwd_top2<<<s->top_grid, 256, B200_TOP3_SMEM, s->stream>>>(s->d_top_items, s->n_top_items, s->d_nodes, s->d_rel, s->d_fac, s->d_dinv,
+                                                             s->d_lperm, s->d_top_ranges, s->d_y, s->d_z, s->d_wv, s->d_cdone, s->d_epoch,
+                                                             s->d_abort, s->d_trace);
 }
 void k_bwd_top_launch(InterfaceB200* s) {
-    if (s->top_variant >= 3) {
-        k_bwd_top3<<<s->top_grid_b, 256, B200_TOP3_SMEM, s->stream>>>(s->d_top_items, s->n_top_items, s->d_nodes, s->d_rows, s->d_fac, s->d_dinv,
-                                                                  s->d_z, s->d_xp, s->d_big_scratch, s->d_node_slot, s->d_bdone, s->d_epoch,
-                                                                  s->d_abort, s->d_trace ? s->d_trace + 4 * (size_t)s->n_top_items : nullptr);
-        return;
-    }
-    if (s->top_variant >= 2) {
-        k_bwd_top2<<<s->top_grid, 256, B200_TOP_SMEM, s->stream>>>(s->d_top_items, s->n_top_items, s->d_nodes, s->d_rows, s->d_fac, s->d_dinv,
-                                                                 s->d_z, s->d_xp, s->d_big_scratch, s->d_big_tickets, s->d_top_slot,
-                                                                 s->d_xdone, s->d_epoch, s->d_abort, s->d_trace ? s->d_trace + 4 * (size_t)s->n_top_items : nullptr);
-        return;
-    }
-    k_bwd_top<<<s->top_grid, 256, B200_TOP_SMEM, s->stream>>>(s->d_top_items, s->n_top_items, s->d_nodes, s->d_rows, s->d_fac, s->d_dinv,
-                                                            s->d_z, s->d_xp, s->d_big_scratch, s->d_big_tickets, s->d_top_slot, s->d_xdone,
-                                                            s->d_epoch, s->d_abort);
+    k_bwd_top3<<<s->top_grid_b, 256, B200_TOP3_SMEM, s->stream>>>(s->d_top_items, s->n_top_items, s->d_nodes, s->d_rows, s->d_fac, s->d_dinv,
+                                                              s->d_z, s->d_xp, s->d_big_scratch, s->d_node_slot, s->d_bdone, s->d_epoch,
+                                                              s->d_abort, s->d_trace ? s->d_trace + 4 * (size_t)s->n_top_items : nullptr);
 }
 
 int enqueue_sweep_levels(InterfaceB200* s, int* launches) {
@@ -720,7 +723,6 @@ struct InterfaceB200* solver_b200_new(void) {
     if ((e = getenv("B200_FUSED_VARIANT"))) s->fused_variant = atoi(e);
     if ((e = getenv("B200_USE_FUSED"))) s->use_fused = atoi(e);
     if ((e = getenv("B200_USE_TOP"))) s->use_top = atoi(e);
-    if ((e = getenv("B200_TOP_VARIANT"))) s->top_variant = atoi(e);
     if ((e = getenv("B200_USE_SUBTREE"))) s->use_subtree = atoi(e);
     if ((e = getenv("B200_SUBTREE_MAXF"))) s->subtree_maxf = atoi(e);
     if ((e = getenv("B200_SUBTREE_BUDGET"))) s->subtree_budget = atoi(e);
@@ -748,6 +750,7 @@ int32_t solver_b200_set_option(struct InterfaceB200* s, const char* key, double 
     std::string k(key);
     if (k == "ir_tol") { s->ir_tol = value; return 0; }
     if (k == "refinement_nstep") { s->nrefine = (int)value; return 0; }
+    if (k == "strict_residual") { s->strict_residual = value != 0.0; return 0; }
     if (s->initialized) return B200_ERROR_ALREADY_INITIALIZED;
     if (k == "panel_width") s->opt_panel_width = std::max(4, std::min((int)value, B200_MAXP));
     else if (k == "nd_leaf") s->opt_nd_leaf = std::max(4, (int)value);
@@ -770,7 +773,6 @@ int32_t solver_b200_set_option(struct InterfaceB200* s, const char* key, double 
     else if (k == "fused_w8_max") s->fused_w8_max = (int)value;
     else if (k == "use_fused") s->use_fused = value != 0.0;
     else if (k == "use_top") s->use_top = value != 0.0;
-    else if (k == "top_variant") s->top_variant = (int)value;
     else if (k == "trace") s->want_trace = value != 0.0;
     else if (k == "use_subtree") s->use_subtree = value != 0.0;
     else if (k == "invert_all") s->invert_all = value != 0.0;
@@ -831,6 +833,7 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     else if (matching == B200_MATCHING_NONE || matching == B200_MATCHING_AUTO) opt.matching = 2;
     else opt.matching = 1;
 
+    const auto t_host0 = std::chrono::steady_clock::now();
     int rc = analyze(ndim, row_pointers, col_indices, values, general_symmetric != 0 || positive_definite != 0, opt, s->plan);
     if (rc == -1) return B200_ERROR_SINGULAR;
     if (rc != 0) return B200_ERROR_ANALYSIS + 2;
@@ -1090,10 +1093,10 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     DM(d_xdone, P.nnodes, int);
     DM(d_bdone, P.nnodes, int);
     CUDA_TRY(cudaMemset(s->d_bdone, 0, (size_t)std::max(P.nnodes, 1) * sizeof(int)), B200_ERROR_CUDA_MALLOC);
-    DM(d_epoch, 1, int);
+    DM(d_epoch, 4, int); // [0] sweep epoch, [1] / [2] item tickets of the forward / backward persistent kernels
     DM(d_abort, 1, int);
     CUDA_TRY(cudaMemset(s->d_xdone, 0, (size_t)std::max(P.nnodes, 1) * sizeof(int)), B200_ERROR_CUDA_MALLOC);
-    CUDA_TRY(cudaMemset(s->d_epoch, 0, sizeof(int)), B200_ERROR_CUDA_MALLOC);
+    CUDA_TRY(cudaMemset(s->d_epoch, 0, 4 * sizeof(int)), B200_ERROR_CUDA_MALLOC);
     CUDA_TRY(cudaMemset(s->d_abort, 0, sizeof(int)), B200_ERROR_CUDA_MALLOC);
 #undef DM
     if (s->want_trace && s->n_top_items > 0) { // must precede the first graph capture of the sweep (the pointer is a kernel argument)
@@ -1119,25 +1122,16 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     CUDA_TRY(cudaFuncSetAttribute(k_assemble_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, B200_ASM_SMEM_MAX), B200_ERROR_NOT_AVAILABLE);
     (void)W;
     if (s->n_top_items > 0) {
-        CUDA_TRY(cudaFuncSetAttribute(k_fwd_top, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_TOP_SMEM), B200_ERROR_NOT_AVAILABLE);
-        CUDA_TRY(cudaFuncSetAttribute(k_bwd_top, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_TOP_SMEM), B200_ERROR_NOT_AVAILABLE);
         CUDA_TRY(cudaFuncSetAttribute(k_fwd_top2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_TOP3_SMEM), B200_ERROR_NOT_AVAILABLE);
-        CUDA_TRY(cudaFuncSetAttribute(k_bwd_top2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_TOP_SMEM), B200_ERROR_NOT_AVAILABLE);
         CUDA_TRY(cudaFuncSetAttribute(k_bwd_top3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_TOP3_SMEM), B200_ERROR_NOT_AVAILABLE);
         int occ_f = 0, occ_b = 0, nsm = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_fwd_top, 256, B200_TOP_SMEM), B200_ERROR_NOT_AVAILABLE);
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_bwd_top, 256, B200_TOP_SMEM), B200_ERROR_NOT_AVAILABLE);
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_fwd_top2, 256, B200_TOP3_SMEM), B200_ERROR_NOT_AVAILABLE);
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_bwd_top3, 256, B200_TOP3_SMEM), B200_ERROR_NOT_AVAILABLE);
         CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device), B200_ERROR_NOT_AVAILABLE);
-        if (s->top_variant >= 2) {
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_fwd_top2, 256, B200_TOP3_SMEM), B200_ERROR_NOT_AVAILABLE);
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_bwd_top2, 256, B200_TOP_SMEM), B200_ERROR_NOT_AVAILABLE);
-        }
-        if (s->top_variant >= 3)
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_bwd_top3, 256, B200_TOP3_SMEM), B200_ERROR_NOT_AVAILABLE);
         int occ = std::min(occ_f, occ_b);
-        if (occ < 1) s->n_top_items = 0; // cannot guarantee co-residency: fall back to per-level launches
-        s->top_grid = std::max(1, std::min(s->n_top_items, occ * nsm));
-        s->top_grid_b = (s->top_variant >= 3) ? std::max(1, std::min(s->n_top_items, occ_b * nsm)) : s->top_grid;
+        if (occ < 1) s->n_top_items = 0; // the kernels cannot run at all: fall back to per-level launches
+        s->top_grid = std::max(1, std::min(s->n_top_items, occ_f * nsm)); // (a performance choice only: items are handed out by ticket)
+        s->top_grid_b = std::max(1, std::min(s->n_top_items, occ_b * nsm));
     }
 
     // algorithmic bytes: SpTRSV streams every stored factor entry once (+ the pivot-block inverses)
@@ -1160,6 +1154,7 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
         printf("solver_b200_initialize: analysis done: %d fronts, %d levels, nnz(L+U)=%lld, %.3e flops, device memory used %.2f GB\n",
                P.nnodes, P.nlevels, (long long)(P.nnz_L + P.nnz_U), P.flops, (tot - fr) / 1e9);
     }
+    s->t_init_host = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_host0).count();
     s->initialized = true;
     return B200_SUCCESSFUL_EXIT;
 }
@@ -1171,11 +1166,12 @@ int32_t solver_b200_factorize_device(struct InterfaceB200* s, const double* d_va
     CUDA_TRY(cudaSetDevice(s->device), B200_ERROR_NOT_AVAILABLE);
     const Plan& P = s->plan;
     s->factorized = false;
+    s->rcond = -1.0;
     if (s->sweep_dirty) { // re-arm the dependency counters of the persistent sweep after an aborted solve
         CUDA_TRY(cudaMemcpyAsync(s->d_cdone, s->cdone_init.data(), s->cdone_init.size() * sizeof(int), cudaMemcpyHostToDevice, s->stream), B200_ERROR_CUDA_MEMCPY);
         CUDA_TRY(cudaMemsetAsync(s->d_xdone, 0, (size_t)std::max(P.nnodes, 1) * sizeof(int), s->stream), B200_ERROR_CUDA_MEMCPY);
         CUDA_TRY(cudaMemsetAsync(s->d_bdone, 0, (size_t)std::max(P.nnodes, 1) * sizeof(int), s->stream), B200_ERROR_CUDA_MEMCPY);
-        CUDA_TRY(cudaMemsetAsync(s->d_epoch, 0, sizeof(int), s->stream), B200_ERROR_CUDA_MEMCPY);
+        CUDA_TRY(cudaMemsetAsync(s->d_epoch, 0, 4 * sizeof(int), s->stream), B200_ERROR_CUDA_MEMCPY);
         CUDA_TRY(cudaMemsetAsync(s->d_abort, 0, sizeof(int), s->stream), B200_ERROR_CUDA_MEMCPY);
         CUDA_TRY(cudaMemsetAsync(s->d_big_tickets, 0, (size_t)std::max(s->n_slots, 1) * sizeof(int), s->stream), B200_ERROR_CUDA_MEMCPY);
         CUDA_TRY(cudaStreamSynchronize(s->stream), B200_ERROR_CUDA_SYNCHRONIZE);
@@ -1239,6 +1235,7 @@ int32_t solver_b200_factorize(struct InterfaceB200* s, int32_t* effective_matchi
     if (!s->initialized) return B200_ERROR_NEED_INITIALIZATION;
     if (!values) return B200_ERROR_NULL_POINTER;
     s->verbose = verbose;
+    s->factorized = false; // the factor arena is about to be cleared: a failed copy must not leave a "factorized" handle
     CUDA_TRY(cudaSetDevice(s->device), B200_ERROR_NOT_AVAILABLE);
     clear_fac_under_h2d(s);
     CUDA_TRY(cudaMemcpyAsync(s->d_vals, values, (size_t)s->nnz_in * sizeof(double), cudaMemcpyHostToDevice, s->stream), B200_ERROR_CUDA_MEMCPY);
@@ -1255,10 +1252,6 @@ int32_t solver_b200_factorize(struct InterfaceB200* s, int32_t* effective_matchi
 
 // ---- COO-level boundary: what CsrMatrix::update_from_coo + solver_cudss_factorize do together
 // (russell_sparse/src/solver_cudss.rs:195-290), with the per-factorize conversion moved to the device.
-extern "C" int32_t b200_coo_to_csr_map(int32_t nrow, int32_t ncol, int32_t nnz, const int32_t* ai, const int32_t* aj,
-                                       const double* ax, int32_t* ptr, int32_t* idx, double* val, int32_t* seg_ptr,
-                                       int32_t* seg_idx);
-
 int32_t solver_b200_initialize_coo(struct InterfaceB200* s, int32_t ordering, int32_t matching, int32_t pivoting,
                                    double pivot_epsilon, int32_t refinement_nstep, double hybrid_memory_factor,
                                    int32_t verbose, int32_t general_symmetric, int32_t positive_definite, int32_t ndim,
@@ -1286,6 +1279,7 @@ int32_t solver_b200_initialize_coo(struct InterfaceB200* s, int32_t ordering, in
     CUDA_TRY(cudaMemcpyAsync(s->d_seg_ptr, seg_ptr.data(), ((size_t)nslots + 1) * sizeof(int), cudaMemcpyHostToDevice, s->stream), B200_ERROR_CUDA_MEMCPY);
     CUDA_TRY(cudaMemcpyAsync(s->d_seg_idx, seg_idx.data(), (size_t)nnz_coo * sizeof(int), cudaMemcpyHostToDevice, s->stream), B200_ERROR_CUDA_MEMCPY);
     CUDA_TRY(cudaStreamSynchronize(s->stream), B200_ERROR_CUDA_SYNCHRONIZE);
+    s->coo_guard.remember(ndim, nnz_coo, indices_i, indices_j, ptr, idx);
     return B200_SUCCESSFUL_EXIT;
 }
 
@@ -1304,6 +1298,7 @@ int32_t solver_b200_factorize_coo(struct InterfaceB200* s, int32_t* effective_ma
     if (!s->initialized || !s->d_seg_ptr) return B200_ERROR_NEED_INITIALIZATION;
     if (!coo_values) return B200_ERROR_NULL_POINTER;
     s->verbose = verbose;
+    s->factorized = false;
     CUDA_TRY(cudaSetDevice(s->device), B200_ERROR_NOT_AVAILABLE);
     clear_fac_under_h2d(s);
     CUDA_TRY(cudaMemcpyAsync(s->d_coo_vals, coo_values, (size_t)s->nnz_coo * sizeof(double), cudaMemcpyHostToDevice, s->stream), B200_ERROR_CUDA_MEMCPY);
@@ -1312,6 +1307,32 @@ int32_t solver_b200_factorize_coo(struct InterfaceB200* s, int32_t* effective_ma
     if (effective_pivoting) *effective_pivoting = s->effective_pivoting;
     if (rc == 0 && verbose) printf("solver_b200_factorize_coo: numeric factorization completed in %.3f ms (device)\n", s->ms_factorize);
     return rc;
+}
+
+// what SolverCUDSS::factorize does on every call (update_from_coo over the caller's indices, solver_cudss.rs:209), at the
+// price of two memcmp that run on a helper thread underneath the copy and the kernels
+int32_t solver_b200_factorize_coo_checked(struct InterfaceB200* s, int32_t* effective_matching, int32_t* effective_pivoting,
+                                          int32_t verbose, int32_t nnz_coo, const int32_t* indices_i, const int32_t* indices_j,
+                                          const double* coo_values) {
+    if (!s) return B200_ERROR_NULL_POINTER;
+    if (!s->initialized || !s->d_seg_ptr || !s->coo_guard.armed()) return B200_ERROR_NEED_INITIALIZATION;
+    if (!indices_i || !indices_j || !coo_values) return B200_ERROR_NULL_POINTER;
+    if (nnz_coo != s->nnz_coo) return B200_ERROR_ANALYSIS + 5;
+    std::atomic<int> same{1};
+    std::thread checker([&] { same.store(s->coo_guard.same(indices_i, indices_j) ? 1 : 0); });
+    int32_t rc = solver_b200_factorize_coo(s, effective_matching, effective_pivoting, verbose, coo_values);
+    checker.join();
+    if (same.load()) return rc;
+    // the triplets were refilled in another order: rebuild the slot map (or refuse a different pattern) and redo the work
+    s->factorized = false;
+    std::vector<int32_t> seg_ptr, seg_idx;
+    if (s->coo_guard.remap(indices_i, indices_j, seg_ptr, seg_idx) != 0) return B200_ERROR_ANALYSIS + 5;
+    CUDA_TRY(cudaSetDevice(s->device), B200_ERROR_NOT_AVAILABLE);
+    CUDA_TRY(cudaMemcpyAsync(s->d_seg_ptr, seg_ptr.data(), ((size_t)s->nnz_in + 1) * sizeof(int), cudaMemcpyHostToDevice, s->stream), B200_ERROR_CUDA_MEMCPY);
+    CUDA_TRY(cudaMemcpyAsync(s->d_seg_idx, seg_idx.data(), (size_t)nnz_coo * sizeof(int), cudaMemcpyHostToDevice, s->stream), B200_ERROR_CUDA_MEMCPY);
+    CUDA_TRY(cudaStreamSynchronize(s->stream), B200_ERROR_CUDA_SYNCHRONIZE);
+    if (verbose) printf("solver_b200_factorize_coo_checked: triplet order changed, slot map rebuilt\n");
+    return solver_b200_factorize_coo(s, effective_matching, effective_pivoting, verbose, coo_values);
 }
 
 int32_t solver_b200_solve_device(struct InterfaceB200* s, double* d_xout, const double* d_rhs) {
@@ -1361,6 +1382,23 @@ int32_t solver_b200_solve_device(struct InterfaceB200* s, double* d_xout, const 
     cudaEventElapsedTime(&s->ms_solve, s->ev[2], s->ev[3]);
     cudaEventElapsedTime(&s->ms_sptrsv, s->ev[4], s->ev[5]);
     cudaEventElapsedTime(&s->ms_spmv, s->ev[6], s->ev[7]);
+    // accuracy gate (UMFPACK reports a failed solve through its status, solver_umfpack.rs:380-387; cuDSS does not): the
+    // refinement loop above may stop on stagnation or on the step limit, so the answer is checked here.  A solve FAILED
+    // when the residual is not a number, or when it stays above 10 x ir_tol although the componentwise backward error is
+    // not at rounding level either (a backward-stable solve of an ill-conditioned system is not a failure); with
+    // "strict_residual" the first condition alone decides.
+    {
+        const double rel = s->last_rel_residual, omega = s->last_backward_error;
+        const double bar = 10.0 * s->ir_tol;
+        const bool nan = !(rel == rel) || !(omega == omega);
+        const bool unstable = rel > bar && (s->strict_residual || omega > 1e3 * 2.220446049250313e-16);
+        if (nan || unstable) {
+            if (s->verbose)
+                fprintf(stderr, "solver_b200_solve: refinement failed: ||b-Ax||/||b|| = %.3e, backward error %.3e, %d perturbed pivot(s)\n",
+                        rel, omega, s->n_perturbed);
+            return B200_ERROR_SOLVE + 7;
+        }
+    }
     return B200_SUCCESSFUL_EXIT;
 }
 
@@ -1463,6 +1501,26 @@ int32_t solver_b200_determinant(struct InterfaceB200* s, double* coefficient, do
     return B200_SUCCESSFUL_EXIT;
 }
 
+// reciprocal condition number estimate with UMFPACK's definition (Info[UMFPACK_RCOND] = min|U_kk| / max|U_kk|, the number
+// interface_umfpack.c:179-184 hands to StatsLinSol.output.umfpack_rcond_estimate), taken over the scaled, permuted factors
+int32_t solver_b200_rcond(struct InterfaceB200* s, double* rcond) {
+    if (!s || !rcond) return B200_ERROR_NULL_POINTER;
+    if (!s->factorized) return B200_ERROR_NEED_FACTORIZATION;
+    CUDA_TRY(cudaSetDevice(s->device), B200_ERROR_NOT_AVAILABLE);
+    unsigned long long* mm = (unsigned long long*)s->d_norms; // 4 doubles of scratch
+    const unsigned long long init[2] = {~0ull, 0ull};
+    CUDA_TRY(cudaMemcpyAsync(mm, init, sizeof(init), cudaMemcpyHostToDevice, s->stream), B200_ERROR_CUDA_MEMCPY);
+    k_minmax_abs<<<grid_for(s->n), 256, 0, s->stream>>>(s->n, s->d_upiv, mm);
+    unsigned long long out[2];
+    CUDA_TRY(cudaMemcpyAsync(out, mm, sizeof(out), cudaMemcpyDeviceToHost, s->stream), B200_ERROR_CUDA_MEMCPY);
+    CUDA_TRY(cudaStreamSynchronize(s->stream), B200_ERROR_CUDA_SYNCHRONIZE);
+    double lo, hi;
+    memcpy(&lo, &out[0], 8), memcpy(&hi, &out[1], 8);
+    s->rcond = (hi > 0.0 && hi == hi && lo == lo) ? lo / hi : 0.0;
+    *rcond = s->rcond;
+    return B200_SUCCESSFUL_EXIT;
+}
+
 int32_t solver_b200_get_stats(struct InterfaceB200* s, double* out, int32_t n_out) {
     if (!s || !out) return B200_ERROR_NULL_POINTER;
     if (!s->initialized) return B200_ERROR_NEED_INITIALIZATION;
@@ -1492,6 +1550,10 @@ int32_t solver_b200_get_stats(struct InterfaceB200* s, double* out, int32_t n_ou
     v[B200_STAT_MATCHED] = P.matched ? 1.0 : 0.0;
     v[B200_STAT_T_MATCH_S] = P.t_match;
     v[B200_STAT_LAST_BACKWARD_ERROR] = s->last_backward_error;
+    v[B200_STAT_EFFECTIVE_ORDERING] = P.opt.ordering == ORDERING_NATURAL ? B200_ORDERING_NONE : P.opt.ordering == ORDERING_MINDEG ? B200_ORDERING_AMD : B200_ORDERING_ND;
+    v[B200_STAT_EFFECTIVE_SCALING] = P.rscale.empty() ? 0.0 : 1.0;
+    v[B200_STAT_RCOND] = s->rcond;
+    v[B200_STAT_T_INITIALIZE_HOST_S] = s->t_init_host;
     for (int i = 0; i < n_out && i < B200_STAT_COUNT; i++) out[i] = v[i];
     return B200_SUCCESSFUL_EXIT;
 }

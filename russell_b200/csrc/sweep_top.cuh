@@ -7,10 +7,12 @@
 // front's panel slice and pivot-block inverse are staged into shared memory with cp.async BEFORE the wait, so the
 // HBM stream runs ahead of the dependency wave.
 //
-// Progress guarantee: items are sorted so that every dependency has a smaller index; CTA b processes items
-// b, b+G, b+2G, ... in increasing order and all G CTAs are co-resident (G <= occupancy * #SMs), hence the
-// unfinished item with the smallest index can always run.  Spins are bounded: on timeout an abort flag makes every
-// CTA leave, and the host reports B200_ERROR_SOLVE+1 instead of hanging the device.
+// Progress guarantee: items are sorted so that every dependency has a smaller index, and CTAs take items from an ATOMIC
+// TICKET counter in increasing order (backward sweep: decreasing).  The unfinished item with the smallest ticket was
+// therefore handed to a CTA that is running (it executed the atomic), and all of its dependencies are finished or owned by
+// running CTAs as well: the wave always advances, whatever part of the grid is resident -- two handles sweeping at the same
+// time, or a sweep next to another handle's factorization (Radau5's real + complex systems), cannot starve each other.
+// Spins are bounded all the same: on timeout an abort flag makes every CTA leave, and the host reports B200_ERROR_SOLVE+1.
 //
 // Role in the reference: the inside of umfpack_di_solve / cudssExecute(SOLVE)
 // (russell_sparse/c_code/interface_umfpack.c:229, interface_cudss.cu:530).
@@ -43,8 +45,7 @@ __device__ __forceinline__ bool wait_counter_ge(const int* counter, int target, 
     return false;
 }
 
-// dynamic shared memory: D (MAXP*MAXP) | panel slice (SLICE*MAXP) doubles
-#define B200_TOP_SMEM ((size_t)(B200_MAXP * B200_MAXP + B200_SLICE * B200_MAXP) * sizeof(double))
+// dynamic shared memory: one panel slice (SLICE x MAXP doubles); the pivot-block inverses live in registers
 #define B200_TOP3_SMEM ((size_t)(B200_SLICE * B200_MAXP) * sizeof(double)) // k_bwd_top3 stages the U slice only
 
 // per (item, child) record of the forward sweep, built on the host: head count, slice begin, slice end (positions in the
@@ -62,188 +63,12 @@ __device__ __forceinline__ unsigned long long gtime() {
 
 __device__ __forceinline__ int slices_of(int u) { return u > 0 ? (u + B200_SLICE - 1) / B200_SLICE : 1; }
 
-__global__ void __launch_bounds__(256) k_fwd_top(const SolveItem* __restrict__ items, int nitems, const NodeDev* __restrict__ nodes,
-                                                 const int* __restrict__ child_idx, const int* __restrict__ rel_all,
-                                                 const double* __restrict__ fac, const double* __restrict__ dinv,
-                                                 const int* __restrict__ lperm, const int* __restrict__ ranges,
-                                                 const double* __restrict__ y, double* __restrict__ zv, double* __restrict__ wv,
-                                                 int* __restrict__ cdone, const int* __restrict__ epoch_ptr, int* __restrict__ abort_flag) {
-    const int epoch = *epoch_ptr;
-    extern __shared__ double smt[];
-    double* Ds = smt;
-    double* Ps = smt + B200_MAXP * B200_MAXP; // Ps[k * SLICE + r]
-    __shared__ double t1[B200_MAXP], z[B200_MAXP], wloc[B200_SLICE], wpart[B200_SLICE];
-    __shared__ int s_ok;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    for (int itx = blockIdx.x; itx < nitems; itx += gridDim.x) {
-        const SolveItem it = items[itx];
-        const NodeDev nd = nodes[it.node];
-        const int p = nd.p, u = nd.u;
-        const long long f = (long long)p + u;
-        // ---- stage the pivot-block inverse and this slice of L21 (independent of the dependency wait)
-        {
-            const double* D = dinv + nd.Doff;
-            for (int e = tid; e < p * p; e += nt) cp_async8(Ds + e, D + e);
-            const int r = tid & (B200_SLICE - 1), g = tid >> 7;
-            if (r < it.nrows) {
-                const double* src = fac + nd.Loff + p + it.r0 + r;
-                for (int k = g; k < p; k += 2) cp_async8(Ps + k * B200_SLICE + r, src + (long long)k * f);
-            }
-        }
-        if (tid < p) t1[tid] = y[nd.c0 + tid];
-        if (tid < B200_SLICE) wloc[tid] = 0.0;
-        // ---- wait for the children (fronts below the top region are complete before this kernel starts:
-        //      their counters are pre-set to a huge value)
-        if (tid == 0) {
-            int ok = 1;
-            for (int e = 0; e < nd.nchild && ok; e++) {
-                const int c = child_idx[nd.child_ptr + e];
-                ok = wait_counter_ge(&cdone[c], epoch * slices_of(nodes[c].u), abort_flag) ? 1 : 0;
-            }
-            s_ok = ok;
-        }
-        __syncthreads();
-        if (!s_ok) return;
-        const int lo = p + it.r0;
-        for (int e = 0; e < nd.nchild; e++) {
-            const int c = child_idx[nd.child_ptr + e];
-            const NodeDev cd = nodes[c];
-            const int* rel = rel_all + cd.rows_ptr;
-            const double* wc = wv + cd.rows_ptr;
-            const int nhead = ranges[it.rng + B200_TOP_REC * e], a = ranges[it.rng + B200_TOP_REC * e + 1], b = ranges[it.rng + B200_TOP_REC * e + 2];
-            for (int i = tid; i < nhead; i += nt) t1[rel[i]] += __ldcg(wc + i); // written by other SMs: read through L2
-            for (int i = a + tid; i < b; i += nt) wloc[rel[i] - lo] += __ldcg(wc + i);
-            __syncthreads();
-        }
-        double tp = 0.0;
-        if (tid < p) tp = t1[lperm[nd.c0 + tid]];
-        cp_async_wait_all();
-        __syncthreads();
-        if (tid < p) t1[tid] = tp;
-        __syncthreads();
-        {   // z = inv(L11) t1: four threads per row (fixed partition + fixed shuffle order: deterministic)
-            const int k = tid >> 2, part = tid & 3;
-            double s = 0.0;
-            if (k < p)
-                for (int m = part; m < k; m += 4) s += Ds[k + m * p] * t1[m];
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            if (k < p && part == 0) {
-                s += t1[k];
-                z[k] = s;
-                if (it.slice == 0) zv[nd.c0 + k] = s;
-            }
-        }
-        __syncthreads();
-        {
-            const int r = tid & (B200_SLICE - 1), h = tid >> 7;
-            const int kh = (p + 1) >> 1;
-            const int kbeg = h * kh, kend = min(p, kbeg + kh);
-            double s = 0.0;
-            if (r < it.nrows)
-                for (int k = kbeg; k < kend; k++) s += Ps[k * B200_SLICE + r] * z[k];
-            if (h == 1) wpart[r] = s;
-            __syncthreads();
-            if (h == 0 && r < it.nrows) wv[nd.rows_ptr + it.r0 + r] = wloc[r] - (s + wpart[r]);
-        }
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            atomicAdd(&cdone[it.node], 1);
-        }
-    }
-}
-
-__global__ void __launch_bounds__(256) k_bwd_top(const SolveItem* __restrict__ items, int nitems, const NodeDev* __restrict__ nodes,
-                                                 const int* __restrict__ rows_all, const double* __restrict__ fac,
-                                                 const double* __restrict__ dinv, const double* __restrict__ zv,
-                                                 double* __restrict__ xp, double* __restrict__ scratch, int* __restrict__ tickets,
-                                                 const int* __restrict__ slot_of_item, int* __restrict__ xdone,
-                                                 const int* __restrict__ epoch_ptr, int* __restrict__ abort_flag) {
-    const int epoch = *epoch_ptr;
-    extern __shared__ double smt[];
-    double* Ds = smt;
-    double* Ps = smt + B200_MAXP * B200_MAXP;
-    __shared__ double t[B200_MAXP], x2[B200_SLICE];
-    __shared__ int s_flag;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
-    // items are stored in forward (level-ascending) order: walk them backwards
-    for (int itx = nitems - 1 - (int)blockIdx.x; itx >= 0; itx -= gridDim.x) {
-        const SolveItem it = items[itx];
-        const NodeDev nd = nodes[it.node];
-        const int p = nd.p, u = nd.u;
-        const int nsl = slices_of(u);
-        {
-            const double* D = dinv + nd.Doff;
-            for (int e = tid; e < p * p; e += nt) cp_async8(Ds + e, D + e);
-            const int r = tid & (B200_SLICE - 1), g = tid >> 7;
-            if (r < it.nrows) {
-                const double* src = fac + nd.Uoff + it.r0 + r;
-                for (int k = g; k < p; k += 2) cp_async8(Ps + k * B200_SLICE + r, src + (long long)k * u);
-            }
-        }
-        if (tid == 0) {
-            const int par = nd.pad; // parent front (or -1)
-            s_flag = (par < 0) ? 1 : (wait_counter_ge(&xdone[par], epoch, abort_flag) ? 1 : 0);
-        }
-        __syncthreads();
-        if (!s_flag) return;
-        const int* rows = rows_all + nd.rows_ptr + it.r0;
-        if (tid < it.nrows) x2[tid] = __ldcg(xp + rows[tid]);
-        cp_async_wait_all();
-        __syncthreads();
-        const int slot = slot_of_item[itx];
-        double* part = scratch + ((long long)slot + it.slice) * B200_MAXP;
-        for (int k = warp; k < p; k += nwarps) {
-            const double* col = Ps + k * B200_SLICE;
-            double s = 0.0;
-            for (int j = lane; j < it.nrows; j += 32) s += col[j] * x2[j];
-            for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
-            if (lane == 0) part[k] = s;
-        }
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) {
-            int ticket = atomicAdd(&tickets[slot], 1);
-            s_flag = (ticket == nsl - 1);
-        }
-        __syncthreads();
-        if (s_flag) { // last slice of this front: reduce the partials in slice order and finish the pivot block
-            __threadfence();
-            if (tid < p) {
-                double s = zv[nd.c0 + tid];
-                const double* base = scratch + (long long)slot * B200_MAXP;
-                for (int sl = 0; sl < nsl; sl++) s -= __ldcg(base + (long long)sl * B200_MAXP + tid);
-                t[tid] = s;
-            }
-            if (tid == 0) tickets[slot] = 0;
-            __syncthreads();
-            {   // x1 = inv(U11) t: four threads per row
-                const int k = tid >> 2, part = tid & 3;
-                double s = 0.0;
-                if (k < p)
-                    for (int m = k + part; m < p; m += 4) s += Ds[k + m * p] * t[m];
-                s += __shfl_xor_sync(0xffffffffu, s, 1);
-                s += __shfl_xor_sync(0xffffffffu, s, 2);
-                if (k < p && part == 0) xp[nd.c0 + k] = s;
-            }
-            __syncthreads();
-            if (tid == 0) {
-                __threadfence();
-                atomicExch(&xdone[it.node], epoch);
-            }
-        }
-        __syncthreads(); // shared buffers are reused by the next item
-    }
-}
-
-// ---- v2 (default): nothing but the dependent data itself is loaded after the dependency wait -------------------------
-// The v1 kernels above paid 4-5 serialized L2 round trips per chain link AFTER the wait (child descriptor -> relative
+// ---- forward sweep: nothing but the dependent data itself is loaded after the dependency wait -------------------------
+// The first version of these kernels paid 4-5 serialized L2 round trips per chain link AFTER the wait (child descriptor -> relative
 // indices -> values -> local permutation; children polled one after the other).  Here every descriptor, index, the local
 // permutation and z come from host-built records or are loaded before the wait; the wait itself is one poll per child in
 // parallel; after it there is ONE batch of value loads (all children in flight together).  Fronts with a single row slice
-// skip the cross-CTA ticket reduction of the backward sweep.  Arithmetic and summation order are those of v1 (bit-identical).
+// skip the cross-CTA ticket reduction of the backward sweep.  Items are handed out through an atomic ticket counter (see the progress guarantee above).
 __global__ void __launch_bounds__(256, 3) k_fwd_top2(const SolveItem* __restrict__ items, int nitems, const NodeDev* __restrict__ nodes,
                                                   const int* __restrict__ rel_all, const double* __restrict__ fac,
                                                   const double* __restrict__ dinv, const int* __restrict__ lperm,
@@ -256,7 +81,13 @@ __global__ void __launch_bounds__(256, 3) k_fwd_top2(const SolveItem* __restrict
     __shared__ double t1[B200_MAXP], z[B200_MAXP], wloc[B200_SLICE], wpart[B200_SLICE];
     const int tid = threadIdx.x, nt = blockDim.x;
     const int gk = tid >> 2, gpart = tid & 3; // GEMV layout: four threads per row
-    for (int itx = blockIdx.x; itx < nitems; itx += gridDim.x) {
+    __shared__ int s_next;
+    int* ticket = const_cast<int*>(epoch_ptr) + 1;
+    if (tid == 0) s_next = atomicAdd(ticket, 1);
+    __syncthreads();
+    for (int itx = s_next; itx < nitems; itx = s_next) {
+        int nxt = 0;
+        if (tid == 0) nxt = atomicAdd(ticket, 1); // the next item's ticket is fetched underneath this item's work
         const SolveItem it = items[itx];
         const NodeDev nd = nodes[it.node];
         const int p = nd.p, u = nd.u, nchild = nd.nchild;
@@ -360,116 +191,13 @@ __global__ void __launch_bounds__(256, 3) k_fwd_top2(const SolveItem* __restrict
             __syncthreads();
             if (h == 0 && r < it.nrows) wv[nd.rows_ptr + it.r0 + r] = wloc[r] - (s + wpart[r]);
         }
+        if (tid == 0) s_next = nxt; // (every thread read the previous value before this item's first barrier)
         __syncthreads();
         if (tid == 0) {
             __threadfence();
             atomicAdd(&cdone[it.node], 1);
             if (trace) trace[4 * (long long)itx + 2] = gtime();
         }
-    }
-}
-
-__global__ void __launch_bounds__(256) k_bwd_top2(const SolveItem* __restrict__ items, int nitems, const NodeDev* __restrict__ nodes,
-                                                  const int* __restrict__ rows_all, const double* __restrict__ fac,
-                                                  const double* __restrict__ dinv, const double* __restrict__ zv,
-                                                  double* __restrict__ xp, double* __restrict__ scratch, int* __restrict__ tickets,
-                                                  const int* __restrict__ slot_of_item, int* __restrict__ xdone,
-                                                  const int* __restrict__ epoch_ptr, int* __restrict__ abort_flag,
-                                                  unsigned long long* __restrict__ trace) {
-    const int epoch = *epoch_ptr;
-    extern __shared__ double smt[];
-    double* Ds = smt;
-    double* Ps = smt + B200_MAXP * B200_MAXP;
-    __shared__ double t[B200_MAXP], zs[B200_MAXP], x2[B200_SLICE];
-    __shared__ int s_flag;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
-    for (int itx = nitems - 1 - (int)blockIdx.x; itx >= 0; itx -= gridDim.x) {
-        const SolveItem it = items[itx];
-        const NodeDev nd = nodes[it.node];
-        const int p = nd.p, u = nd.u;
-        const int nsl = slices_of(u);
-        {
-            const double* D = dinv + nd.Doff;
-            for (int e = tid; e < p * p; e += nt) cp_async8(Ds + e, D + e);
-            const int r = tid & (B200_SLICE - 1), g = tid >> 7;
-            if (r < it.nrows) {
-                const double* src = fac + nd.Uoff + it.r0 + r;
-                for (int k = g; k < p; k += 2) cp_async8(Ps + k * B200_SLICE + r, src + (long long)k * u);
-            }
-        }
-        // everything that does not depend on the parent's solution is loaded before the wait
-        const int rr = tid < it.nrows ? rows_all[nd.rows_ptr + it.r0 + tid] : -1;
-        if (tid < p) zs[tid] = zv[nd.c0 + tid]; // complete: the forward kernel is an earlier launch
-        const int slot = slot_of_item[itx];
-        if (tid == 0) {
-            if (trace) trace[4 * (long long)itx] = gtime();
-            const int par = nd.pad; // parent front (or -1)
-            s_flag = (par < 0) ? 1 : (wait_counter_ge(&xdone[par], epoch, abort_flag) ? 1 : 0);
-            if (trace) trace[4 * (long long)itx + 1] = gtime();
-        }
-        __syncthreads();
-        if (!s_flag) return;
-        if (rr >= 0) x2[tid] = __ldcg(xp + rr);
-        cp_async_wait_all();
-        __syncthreads();
-        double* part = scratch + ((long long)slot + it.slice) * B200_MAXP;
-        for (int k = warp; k < p; k += nwarps) {
-            const double* col = Ps + k * B200_SLICE;
-            double s = 0.0;
-            for (int j = lane; j < it.nrows; j += 32) s += col[j] * x2[j];
-            for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
-            if (lane == 0) {
-                if (nsl == 1) t[k] = zs[k] - s; // single slice: no cross-CTA reduction
-                else part[k] = s;
-            }
-        }
-        int last = 1;
-        if (nsl > 1) {
-            __threadfence();
-            __syncthreads();
-            if (tid == 0) {
-                int ticket = atomicAdd(&tickets[slot], 1);
-                s_flag = (ticket == nsl - 1);
-            }
-            __syncthreads();
-            last = s_flag;
-            if (last) { // last slice of this front: reduce the partials in slice order
-                __threadfence();
-                if (tid < p) {
-                    double s = zs[tid];
-                    const double* base = scratch + (long long)slot * B200_MAXP + tid;
-                    for (int sl0 = 0; sl0 < nsl; sl0 += 8) { // eight loads in flight, subtracted in slice order (deterministic)
-                        double v[8];
-#pragma unroll
-                        for (int q = 0; q < 8; q++) v[q] = sl0 + q < nsl ? __ldcg(base + (long long)(sl0 + q) * B200_MAXP) : 0.0;
-#pragma unroll
-                        for (int q = 0; q < 8; q++) s -= v[q];
-                    }
-                    t[tid] = s;
-                }
-                if (tid == 0) tickets[slot] = 0;
-            }
-        }
-        if (last) {
-            __syncthreads();
-            {   // x1 = inv(U11) t: four threads per row
-                const int k = tid >> 2, part4 = tid & 3;
-                double s = 0.0;
-                if (k < p)
-                    for (int m = k + part4; m < p; m += 4) s += Ds[k + m * p] * t[m];
-                s += __shfl_xor_sync(0xffffffffu, s, 1);
-                s += __shfl_xor_sync(0xffffffffu, s, 2);
-                if (k < p && part4 == 0) xp[nd.c0 + k] = s;
-            }
-            __syncthreads();
-            if (tid == 0) {
-                __threadfence();
-                atomicExch(&xdone[it.node], epoch);
-            }
-        }
-        if (trace && tid == 0) trace[4 * (long long)itx + 2] = gtime();
-        __syncthreads(); // shared buffers are reused by the next item
     }
 }
 
@@ -498,7 +226,13 @@ __global__ void __launch_bounds__(256, 3) k_bwd_top3(const SolveItem* __restrict
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
     const int gk = tid >> 2, gpart = tid & 3; // GEMV layout: four threads per row
-    for (int itx = nitems - 1 - (int)blockIdx.x; itx >= 0; itx -= gridDim.x) {
+    __shared__ int s_next;
+    int* ticket = const_cast<int*>(epoch_ptr) + 2;
+    if (tid == 0) s_next = nitems - 1 - atomicAdd(ticket, 1);
+    __syncthreads();
+    for (int itx = s_next; itx >= 0; itx = s_next) {
+        int nxt = 0;
+        if (tid == 0) nxt = nitems - 1 - atomicAdd(ticket, 1);
         const SolveItem it = items[itx];
         const NodeDev nd = nodes[it.node];
         const int p = nd.p, u = nd.u;
@@ -621,6 +355,7 @@ __global__ void __launch_bounds__(256, 3) k_bwd_top3(const SolveItem* __restrict
             sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
             if (gk < p && gpart == 0) xp[nd.c0 + gk] = sacc;
         }
+        if (tid == 0) s_next = nxt;
         __syncthreads(); // shared buffers are reused by the next item
     }
 }

@@ -156,6 +156,9 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
             int j = colidx[k];
             if (j < 0 || j >= n) return -2;
             if (sym_lower && j > i) return -2;
+            // the CSR contract (csr_matrix.rs:359-480): columns ascending, duplicates already summed.  A duplicate would make
+            // the value scatter last-writer-wins while the SpMV sums it, so it is rejected rather than tolerated.
+            if (!sym_lower && k > rowptr[i] && j <= colidx[k - 1]) return -2;
         }
     }
     const int W = std::max(4, std::min(opt.panel_width, 128));
@@ -197,6 +200,8 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
                 std::sort(tmp.begin(), tmp.end());
                 for (int k = a; k < b; k++) fcol[k] = tmp[k - a].first, fsrc[k] = tmp[k - a].second;
             }
+            for (int k = a + 1; k < b; k++)
+                if (fcol[k] == fcol[k - 1]) return -2; // duplicate entry
         }
     } else {
         fptr.assign(rowptr, rowptr + n + 1);

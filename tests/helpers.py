@@ -175,3 +175,37 @@ def laplacian_3d_triplets(k, skew=0.0):
         off = ai != aj
         ax[off] += skew * np.sin((ai[off] + 1.0) * (aj[off] + 1.0))
     return n, ai.astype(np.int32), aj.astype(np.int32), ax
+
+
+def laplacian_3d_27pt_triplets(k, skew=1e-3):
+    """SURVEY 8d's named stand-in for BASELINE.json configs[2] (af_shell10 is not in the tree and there is no network):
+    27-point Laplacian on a k^3 grid (centre 26, every one of the 26 neighbours -1, Dirichlet neighbours dropped) plus the
+    index-seeded skew perturbation +-skew*sin((i+1)(j+1)) of the off-diagonal entries, so the VALUES are unsymmetric like
+    the general (MakeItFull) path af_shell10 is run through.  k = 115: n = 1,520,875, nnz = 40.4 M."""
+    n = k * k * k
+    m = np.arange(n, dtype=np.int64)
+    i, j, l = m % k, (m // k) % k, m // (k * k)
+    ai, aj, ax = [], [], []
+    for dl in (-1, 0, 1):
+        for dj in (-1, 0, 1):
+            for di in (-1, 0, 1):
+                ok = (i + di >= 0) & (i + di < k) & (j + dj >= 0) & (j + dj < k) & (l + dl >= 0) & (l + dl < k)
+                r = m[ok]
+                c = r + di + dj * k + dl * k * k
+                v = np.full(len(r), 26.0 if (di == 0 and dj == 0 and dl == 0) else -1.0)
+                if skew != 0.0 and not (di == 0 and dj == 0 and dl == 0):
+                    v += skew * np.sin((r + 1.0) * (c + 1.0))
+                ai.append(r), aj.append(c), ax.append(v)
+    ai, aj, ax = np.concatenate(ai), np.concatenate(aj), np.concatenate(ax)
+    order = np.argsort(ai, kind="stable")  # row-major triplets, the 27 stencil entries of a row in (dl, dj, di) order
+    return n, ai[order].astype(np.int32), aj[order].astype(np.int32), ax[order]
+
+
+def host_rel_residual(n, ai, aj, ax, x, b):
+    """||b - A x||_2 / ||b||_2 evaluated on the HOST with scipy (duplicates summed): the independent check of the
+    product's own SpMV-based residual"""
+    import scipy.sparse as sp
+
+    a = sp.coo_matrix((ax, (ai, aj)), shape=(n, n)).tocsr()
+    r = b - a @ x
+    return float(np.linalg.norm(r) / np.linalg.norm(b))

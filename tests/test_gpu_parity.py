@@ -351,16 +351,15 @@ def test_round1_kernels_are_bit_identical_to_the_ones_they_replace():
 
 @pytest.mark.parametrize("k,lower", [(150, False), (400, True)])
 def test_sweep_variants_agree(k, lower):
-    # per-level launches, persistent top-of-tree kernels v1/v2/v3, with and without the one-CTA-per-subtree kernels.
-    # The three persistent variants perform the same operations in the same order (bit-identical x); the per-level and
+    # per-level launches, persistent top-of-tree kernels, with and without the one-CTA-per-subtree kernels.
+    # The persistent kernels give the same bits with and without graph replay; the per-level and
     # subtree kernels sum the pivot-block GEMV in a different (also fixed) order, so they agree to rounding only.
     coo = helpers.laplacian_2d_coo(k, lower=lower)
     b = np.sin(0.1 * np.arange(coo.nrow)) + 1.0
     ref, ref_top = None, None
-    for opts in ({"use_top": 0, "use_subtree": 0}, {"top_variant": 1, "use_subtree": 0}, {"top_variant": 2, "use_subtree": 0},
-                 {"top_variant": 3, "use_subtree": 0}, {"top_variant": 3, "use_subtree": 1}, {"use_top": 0, "use_subtree": 1},
-                 {"top_variant": 3, "use_subtree": 1, "subtree_budget": 2000, "subtree_maxf": 40}, {"top_variant": 3, "top_max_nodes": 8},
-                 {"top_variant": 2, "use_subtree": 1, "use_graph": 0}):
+    for opts in ({"use_top": 0, "use_subtree": 0}, {"use_subtree": 0}, {"use_subtree": 1}, {"use_top": 0, "use_subtree": 1},
+                 {"use_subtree": 1, "subtree_budget": 2000, "subtree_maxf": 40}, {"top_max_nodes": 8},
+                 {"use_subtree": 0, "use_graph": 0}):
         sol, x = solve_through_abi(coo, b, opts=opts)
         assert sol.residual(x, b) <= TOL_RESIDUAL, opts
         x2 = np.zeros_like(x)
@@ -369,7 +368,7 @@ def test_sweep_variants_agree(k, lower):
         if ref is None:
             ref = x
         assert np.max(np.abs(x - ref)) <= 1e-12 * np.max(np.abs(ref)), opts
-        if opts.get("use_subtree") == 0 and "top_variant" in opts:
+        if opts.get("use_subtree") == 0 and "use_top" not in opts:
             if ref_top is None:
                 ref_top = x
             assert np.array_equal(x, ref_top), opts
