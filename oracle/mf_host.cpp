@@ -263,6 +263,7 @@ int oracle_mf_solve(int n, const int* rowptr, const int* colidx, const double* v
     if (panel_width > 0) opt.panel_width = panel_width;
     if (nd_leaf > 0) opt.nd_leaf = nd_leaf;
     opt.verbose = verbose;
+    opt.cb_reuse = false; // this walk runs in postorder and accumulates into zero-initialised private blocks
     int rc = analyze(n, rowptr, colidx, vals, sym_lower != 0, opt, S.P);
     if (rc != 0) return rc;
     host_factorize(S, vals, pivot_eps > 0 ? pivot_eps : 1e-13);
@@ -303,6 +304,7 @@ void* oracle_mf_create(int n, const int* rowptr, const int* colidx, const double
     opt.matching = matching;
     if (panel_width > 0) opt.panel_width = panel_width;
     if (nd_leaf > 0) opt.nd_leaf = nd_leaf;
+    opt.cb_reuse = false;
     int rc = analyze(n, rowptr, colidx, vals, sym_lower != 0, opt, S->P);
     if (rc != 0) {
         *status = rc;

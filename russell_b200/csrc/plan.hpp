@@ -34,6 +34,17 @@ struct AnalyzeOptions {
                                // kernels small fronts are cheap, 0.3 stores 12 % fewer entries: 9.37 -> 8.84 ms per step at config 2)
     double relax_z2 = 0.25;    // merged width <= panel_width : allowed fraction of explicit zeros
     double relax_z3 = 0.05;    // wider
+    // solve phase, bottom of the tree: maximal subtrees made of small fronts are walked by ONE CTA each with the subtree's
+    // segment of the solution vector in shared memory (sweep_sub.cuh).  Their L panels, U panels and pivot-block copies are
+    // laid out contiguously per subtree so that one bulk copy (TMA, cp.async.bulk) stages everything a CTA needs.
+    int st_enable = 1;
+    int st_maxf = 96;          // largest front order inside a subtree
+    int st_pmax = 32;          // most pivots per front inside a subtree
+    int st_budget = 5632;      // stored L entries (padded) per subtree: 44 KB of shared memory for the panels
+    int st_maxcols = 2560;     // columns of a subtree + update rows of its root (shared-memory solution segment)
+    int st_min_count = 64;     // fewer subtrees than this are not worth a launch of their own
+    bool cb_reuse = true;      // contribution blocks with disjoint lifetimes (tree levels) share storage; a walk in
+                               // postorder (the test suite's scalar host walk) needs private, zero-initialised blocks: false
     int verbose = 0;
 };
 
@@ -69,6 +80,12 @@ struct Plan {
     std::vector<int> level_ptr, level_nodes; // nodes grouped by level (level 0 = leaves)
 
     int64_t fac_size = 0, cb_size = 0, dinv_size = 0;
+
+    // subtree region of the solve phase: in_sub[v] = front v is walked by a subtree CTA; st_first/st_root = node ranges
+    // (a subtree is the contiguous postorder range [first, root]); within a subtree the L panels are contiguous in `fac`
+    // (first..root), then the U panels; Doff is contiguous in node order anyway
+    std::vector<char> in_sub;
+    std::vector<int> st_first, st_root;
 
     // value scatter map (user CSR slot -> fac offset); symmetric-lower input contributes two entries
     std::vector<int> a_src;

@@ -23,6 +23,7 @@
 #include "../../include/solver_b200.h"
 #include "kernels.cuh"
 #include "sweep_top.cuh"
+#include "sweep_sub.cuh"
 #include "plan.hpp"
 #include "coo_guard.hpp"
 #include <atomic>
@@ -118,10 +119,13 @@ struct InterfaceB200 {
     // persistent top-of-tree sweep (sweep_top.cuh)
     int top_max_nodes = 1600; // (measured optimum at config 2) levels with at most this many fronts belong to the persistent sweep region
     // bottom of the tree: one CTA per small subtree (k_fwd_subtree / k_bwd_subtree)
-    int use_subtree = 1, subtree_maxf = 96, subtree_budget = 16384; // eligibility: every front f <= maxf, p <= B200_ST_PMAX, stored entries <= budget
+    int use_subtree = 1, subtree_maxf = 96, subtree_budget = 5632; // eligibility: every front f <= maxf, p <= 32, stored L entries of the subtree <= budget
     std::vector<char> in_sub;   // per front: handled by a subtree CTA in the solve phase
     int n_subtrees = 0;
-    int2* d_subtrees = nullptr; // (first, root) node ranges, largest first
+    SubtreeDev* d_subtrees = nullptr; // descriptors, largest first (sweep_sub.cuh)
+    unsigned short* d_st_tgt = nullptr;
+    uchar2* d_st_pu = nullptr;
+    size_t sub_smem = 0;
     ChildRec* d_child_rec = nullptr;
     bool fac_cleared = false;      // the host entry points clear the factor arena on the side stream, under their H2D copy
     int invert_all = 0;            // 1: explicit pivot-block inverses for every front (the subtree kernels do not need them)
@@ -211,7 +215,7 @@ void release_device(InterfaceB200* s) {
     dfree(s->d_nodes), dfree(s->d_rows), dfree(s->d_rel), dfree(s->d_child_idx), dfree(s->d_fact_nodes), dfree(s->d_solve_nodes), dfree(s->d_inv_nodes);
     dfree(s->d_asm), dfree(s->d_panel), dfree(s->d_schur);
     dfree(s->d_trace);
-    dfree(s->d_subtrees);
+    dfree(s->d_subtrees), dfree(s->d_st_tgt), dfree(s->d_st_pu);
     dfree(s->d_node_slot), dfree(s->d_bdone);
     dfree(s->d_child_rec);
     dfree(s->d_inv_skip);
@@ -547,8 +551,8 @@ int enqueue_sweep_levels(InterfaceB200* s, int* launches) {
     int cnt = 0;
     const int lsplit = s->n_top_items > 0 ? s->ltop : P.nlevels; // levels >= lsplit run in the persistent kernels
     if (s->n_subtrees > 0) {
-        k_fwd_subtree<<<s->n_subtrees, B200_ST_THREADS, 0, s->stream>>>(s->d_subtrees, s->d_nodes, s->d_child_rec, s->d_rel, s->d_fac, s->d_dinv,
-                                                                         s->d_lperm, s->d_y, s->d_z, s->d_wv);
+        k_fwd_stree<<<s->n_subtrees, B200_SUB_THREADS, s->sub_smem, s->stream>>>(s->d_subtrees, s->d_fac, s->d_st_tgt, s->d_st_pu, s->d_lperm,
+                                                                                 s->d_y, s->d_z, s->d_wv);
         cnt++;
     }
     for (int l = 0; l < lsplit; l++) {
@@ -589,7 +593,8 @@ int enqueue_sweep_levels(InterfaceB200* s, int* launches) {
         }
     }
     if (s->n_subtrees > 0) {
-        k_bwd_subtree<<<s->n_subtrees, B200_ST_THREADS, 0, s->stream>>>(s->d_subtrees, s->d_nodes, s->d_rows, s->d_fac, s->d_dinv, s->d_z, s->d_xp);
+        k_bwd_stree<<<s->n_subtrees, B200_SUB_THREADS, s->sub_smem, s->stream>>>(s->d_subtrees, s->d_fac, s->d_dinv, s->d_st_tgt, s->d_st_pu,
+                                                                                 s->d_rows, s->d_z, s->d_xp);
         cnt++;
     }
     if (launches) *launches = cnt;
@@ -824,6 +829,9 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     if (s->relax_z2 >= 0.0) opt.relax_z2 = s->relax_z2;
     if (s->relax_z3 >= 0.0) opt.relax_z3 = s->relax_z3;
     opt.verbose = verbose;
+    opt.st_enable = s->use_subtree;
+    opt.st_maxf = std::max(1, std::min(s->subtree_maxf, 200));
+    opt.st_budget = std::max(16, s->subtree_budget);
     if (ordering == B200_ORDERING_NONE) opt.ordering = ORDERING_NATURAL;
     else if (ordering == B200_ORDERING_AMD) opt.ordering = ORDERING_MINDEG;
     else opt.ordering = ORDERING_ND;
@@ -854,35 +862,59 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
         d.Loff = P.Loff[v], d.Uoff = P.Uoff[v], d.Coff = P.Coff[v], d.Doff = P.Doff[v], d.rows_ptr = P.rows_ptr[v];
         d.pad = P.parent[v]; // parent front (used by the persistent backward sweep)
     }
-    // solve phase, bottom of the tree: maximal subtrees made of small fronts only.  Nodes are in postorder, so the
-    // subtree rooted at v is the contiguous range [v - size + 1, v].
-    std::vector<int2> subtrees;
-    s->in_sub.assign(P.nnodes, 0);
-    if (s->use_subtree) {
-        std::vector<int64_t> ent(P.nnodes);
-        std::vector<int> size(P.nnodes, 1);
-        std::vector<char> elig(P.nnodes, 1);
-        for (int v = 0; v < P.nnodes; v++) { // children precede parents: ent/size/elig of v are final when v is visited
-            ent[v] += (int64_t)P.p[v] * (P.p[v] + 2 * (int64_t)P.u[v]);
-            if (P.p[v] + P.u[v] > std::min(s->subtree_maxf, B200_ST_FMAX) || P.p[v] > B200_ST_PMAX || ent[v] > s->subtree_budget) elig[v] = 0;
-            const int par = P.parent[v];
-            if (par >= 0) {
-                ent[par] += ent[v], size[par] += size[v];
-                if (!elig[v]) elig[par] = 0;
-            }
+    // solve phase, bottom of the tree: the subtrees found (and laid out contiguously) by the analysis, largest first.
+    // Per subtree: a descriptor, the 16-bit target index of every update row of every front (its place in the CTA's
+    // shared-memory solution segment), and the (p, u) pairs of its fronts.
+    std::vector<SubtreeDev> subtrees;
+    std::vector<unsigned short> st_tgt;
+    std::vector<uchar2> st_pu;
+    s->in_sub = P.in_sub;
+    size_t sub_smem = 0;
+    {
+        std::vector<std::pair<int64_t, int>> order;
+        for (size_t i = 0; i < P.st_first.size(); i++) {
+            int64_t ent = 0;
+            for (int w = P.st_first[i]; w <= P.st_root[i]; w++) ent += (int64_t)P.p[w] * (P.p[w] + P.u[w]);
+            order.push_back({-ent, (int)i});
         }
-        std::vector<std::pair<int64_t, int>> roots;
-        for (int v = 0; v < P.nnodes; v++)
-            if (elig[v] && (P.parent[v] < 0 || !elig[P.parent[v]])) roots.push_back({-ent[v], v});
-        if ((int)roots.size() >= 64) { // worth a launch of its own
-            std::sort(roots.begin(), roots.end()); // largest first: the long subtrees start early
-            for (auto& r : roots) {
-                const int v = r.second;
-                subtrees.push_back(make_int2(v - size[v] + 1, v));
-                for (int w = v - size[v] + 1; w <= v; w++) s->in_sub[w] = 1;
+        std::sort(order.begin(), order.end()); // the long subtrees start early
+        for (auto& o : order) {
+            const int first = P.st_first[o.second], root = P.st_root[o.second];
+            SubtreeDev d;
+            d.Lbeg = P.Loff[first], d.Ubeg = P.Uoff[first], d.Dbeg = P.Doff[first];
+            d.root_rows = P.rows_ptr[root];
+            d.cbeg = P.c0[first], d.ncols = P.c0[root] + P.p[root] - P.c0[first], d.next = P.u[root];
+            d.nfr = root - first + 1;
+            d.tgt_beg = (long long)st_tgt.size(), d.pu_beg = (int)st_pu.size();
+            int64_t lc = 0, uc = 0, dc = 0;
+            const int cend = d.cbeg + d.ncols;
+            const int* rroot = &P.rows[P.rows_ptr[root]];
+            for (int w = first; w <= root; w++) {
+                const int p = P.p[w], u = P.u[w];
+                lc += (((int64_t)(p + u) * p + 3) & ~3), uc += (((int64_t)u * p + 3) & ~3), dc += (((int64_t)p * p + 3) & ~3);
+                st_pu.push_back(make_uchar2((unsigned char)p, (unsigned char)u));
+                const int* r = &P.rows[P.rows_ptr[w]];
+                for (int i = 0; i < u; i++) {
+                    int t;
+                    if (r[i] < cend) t = r[i] - d.cbeg; // a column of this subtree
+                    else {                               // leaves the subtree: a row of the root's update set
+                        const int* it = std::lower_bound(rroot, rroot + d.next, r[i]);
+                        if (it == rroot + d.next || *it != r[i]) return B200_ERROR_ANALYSIS + 2;
+                        t = d.ncols + (int)(it - rroot);
+                    }
+                    st_tgt.push_back((unsigned short)t);
+                }
             }
+            while (st_tgt.size() & 7) st_tgt.push_back(0);
+            while (st_pu.size() & 7) st_pu.push_back(make_uchar2(0, 0));
+            d.Lcount = (int)lc, d.Ucount = (int)uc, d.Dcount = (int)dc;
+            d.tgt_count = (int)(st_tgt.size() - (size_t)d.tgt_beg);
+            d.pan = (int)std::max(lc, uc + dc);
+            sub_smem = std::max(sub_smem, sub_smem_bytes(d.pan, d.ncols, d.next, d.tgt_count, d.nfr));
+            subtrees.push_back(d);
         }
     }
+    s->sub_smem = sub_smem;
     s->n_subtrees = (int)subtrees.size();
     std::vector<AsmItem> asm_items;
     std::vector<PanelItem> panel_items;
@@ -1036,6 +1068,8 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     UP(d_asm_ranges, asm_ranges);
     UP(d_big_ranges, big_ranges);
     UP(d_subtrees, subtrees);
+    UP(d_st_tgt, st_tgt);
+    UP(d_st_pu, st_pu);
     {
         std::vector<ChildRec> child_rec(P.child_idx.size());
         for (size_t e = 0; e < P.child_idx.size(); e++) {

@@ -6,6 +6,8 @@
 // amalgamation with an explicit-zero budget); the code is written from scratch for the flat, GPU-facing
 // Plan layout in plan.hpp.
 #include "plan.hpp"
+#include <iterator>
+#include <map>
 
 #include <algorithm>
 #include <cassert>
@@ -611,17 +613,118 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
         for (int v = 0; v < nnodes; v++) P.level_nodes[fill[P.level[v]]++] = v;
     }
     // storage offsets + stats
+    // ---- solve-phase subtrees: maximal subtrees whose fronts are all small (nodes are in postorder: the subtree rooted at
+    //      v is the contiguous range [v - size + 1, v])
+    P.in_sub.assign(nnodes, 0);
+    if (opt.st_enable) {
+        std::vector<int64_t> ent(nnodes, 0);
+        std::vector<int> size(nnodes, 1), cols(nnodes, 0);
+        std::vector<char> elig(nnodes, 1);
+        for (int v = 0; v < nnodes; v++) { // children precede parents: the sums of v are final when v is visited
+            ent[v] += round_up4((int64_t)P.p[v] * (P.p[v] + P.u[v]));
+            cols[v] += P.p[v];
+            if (P.p[v] + P.u[v] > opt.st_maxf || P.p[v] > opt.st_pmax || ent[v] > opt.st_budget || cols[v] + P.u[v] > opt.st_maxcols)
+                elig[v] = 0;
+            const int par = P.parent[v];
+            if (par >= 0) {
+                ent[par] += ent[v], size[par] += size[v], cols[par] += cols[v];
+                if (!elig[v]) elig[par] = 0;
+            }
+        }
+        int count = 0;
+        for (int v = 0; v < nnodes; v++)
+            if (elig[v] && (P.parent[v] < 0 || !elig[P.parent[v]])) count++;
+        if (count >= opt.st_min_count)
+            for (int v = 0; v < nnodes; v++)
+                if (elig[v] && (P.parent[v] < 0 || !elig[P.parent[v]])) {
+                    P.st_first.push_back(v - size[v] + 1), P.st_root.push_back(v);
+                    for (int w = v - size[v] + 1; w <= v; w++) P.in_sub[w] = 1;
+                }
+    }
     int64_t fo = 0, co = 0, dof = 0;
+    {
+        size_t si = 0;
+        for (int v = 0; v < nnodes;) {
+            if (si < P.st_first.size() && P.st_first[si] == v) { // a subtree: all L panels, then all U panels
+                const int r = P.st_root[si++];
+                for (int w = v; w <= r; w++) P.Loff[w] = fo, fo = round_up4(fo + (int64_t)(P.p[w] + P.u[w]) * P.p[w]);
+                for (int w = v; w <= r; w++) P.Uoff[w] = fo, fo = round_up4(fo + (int64_t)P.u[w] * P.p[w]);
+                v = r + 1;
+            } else {
+                const int64_t p = P.p[v], u = P.u[v];
+                P.Loff[v] = fo, fo = round_up4(fo + (p + u) * p);
+                P.Uoff[v] = fo, fo = round_up4(fo + u * p);
+                v++;
+            }
+        }
+    }
     for (int v = 0; v < nnodes; v++) {
         int64_t p = P.p[v], u = P.u[v], f = p + u;
-        P.Loff[v] = fo, fo = round_up4(fo + f * p);
-        P.Uoff[v] = fo, fo = round_up4(fo + u * p);
-        P.Coff[v] = co, co = round_up4(co + u * u);
+        if (!opt.cb_reuse) P.Coff[v] = co, co = round_up4(co + u * u);
         P.Doff[v] = dof, dof = round_up4(dof + p * p);
         P.nnz_L += f * p;
         P.nnz_U += u * p;
         P.flops += (2.0 / 3.0) * p * p * p + 2.0 * p * p * u + 2.0 * (double)p * u * u;
         P.max_front = std::max<int>(P.max_front, (int)f);
+    }
+    if (opt.cb_reuse) {
+        // Contribution blocks live only from the level that first writes them to the level of their parent, and the
+        // device executes the tree level by level: blocks whose lifetimes do not overlap share storage.  (One block per
+        // front for the whole factorization costs sum(u^2): 159 GB for a 64^3 27-point grid, TBs at 115^3.)
+        //   born(v) = level(v), or the level of its only child when that child may write v's block from its Schur
+        //             epilogue (chain links of a split supernode);   dies(v) = level(parent(v)).
+        std::vector<int> born(nnodes), dies(nnodes);
+        for (int v = 0; v < nnodes; v++) {
+            born[v] = P.level[v];
+            if (P.child_ptr[v + 1] - P.child_ptr[v] == 1) born[v] = std::min(born[v], P.level[P.child_idx[P.child_ptr[v]]]);
+            dies[v] = P.parent[v] >= 0 ? P.level[P.parent[v]] : P.level[v];
+        }
+        std::vector<std::vector<int>> born_at(nlev), dies_at(nlev);
+        for (int v = 0; v < nnodes; v++)
+            if (P.u[v] > 0) born_at[born[v]].push_back(v), dies_at[dies[v]].push_back(v);
+        std::map<int64_t, int64_t> free_by_off;            // offset -> size (coalesced)
+        std::multimap<int64_t, int64_t> free_by_size;      // size -> offset
+        auto erase_size = [&](int64_t size, int64_t off) {
+            auto r = free_by_size.equal_range(size);
+            for (auto it = r.first; it != r.second; ++it)
+                if (it->second == off) { free_by_size.erase(it); return; }
+        };
+        auto release = [&](int64_t off, int64_t size) {
+            auto nx = free_by_off.lower_bound(off);
+            if (nx != free_by_off.begin()) {
+                auto pv = std::prev(nx);
+                if (pv->first + pv->second == off) { off = pv->first, size += pv->second; erase_size(pv->second, pv->first); free_by_off.erase(pv); }
+            }
+            if (nx != free_by_off.end() && off + size == nx->first) { size += nx->second; erase_size(nx->second, nx->first); free_by_off.erase(nx); }
+            free_by_off[off] = size;
+            free_by_size.insert({size, off});
+        };
+        for (int l = 0; l < nlev; l++) {
+            // largest first: big blocks take the big holes
+            std::sort(born_at[l].begin(), born_at[l].end(), [&](int a, int b) { return P.u[a] != P.u[b] ? P.u[a] > P.u[b] : a < b; });
+            for (int v : born_at[l]) {
+                const int64_t need = round_up4((int64_t)P.u[v] * P.u[v]);
+                auto it = free_by_size.lower_bound(need); // best fit
+                if (it != free_by_size.end()) {
+                    const int64_t off = it->second, size = it->first;
+                    free_by_size.erase(it);
+                    free_by_off.erase(off);
+                    P.Coff[v] = off;
+                    if (size > need) release(off + need, size - need);
+                } else {
+                    // grow the arena: a free block that ends at the top is extended instead of wasted
+                    int64_t off = co;
+                    if (!free_by_off.empty()) {
+                        auto last = std::prev(free_by_off.end());
+                        if (last->first + last->second == co) { off = last->first; erase_size(last->second, last->first); free_by_off.erase(last); }
+                    }
+                    P.Coff[v] = off;
+                    co = off + need;
+                }
+            }
+            for (int v : dies_at[l]) // reusable from the NEXT level on
+                release(P.Coff[v], round_up4((int64_t)P.u[v] * P.u[v]));
+        }
     }
     P.fac_size = fo, P.cb_size = co, P.dinv_size = dof;
 
