@@ -40,8 +40,8 @@ struct AnalyzeOptions {
     int st_enable = 1;
     int st_maxf = 96;          // largest front order inside a subtree
     int st_pmax = 32;          // most pivots per front inside a subtree
-    int st_budget = 5632;      // stored L entries (padded) per subtree: 44 KB of shared memory for the panels
-    int st_maxcols = 2560;     // columns of a subtree + update rows of its root (shared-memory solution segment)
+    int st_budget = 8192;      // stored L entries (padded) per subtree
+    int st_maxcols = 1024;     // columns of a subtree + update rows of its root (shared-memory solution segment of one warp)
     int st_min_count = 64;     // fewer subtrees than this are not worth a launch of their own
     bool cb_reuse = true;      // contribution blocks with disjoint lifetimes (tree levels) share storage; a walk in
                                // postorder (the test suite's scalar host walk) needs private, zero-initialised blocks: false

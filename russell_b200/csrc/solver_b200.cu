@@ -119,21 +119,25 @@ struct InterfaceB200 {
     // persistent top-of-tree sweep (sweep_top.cuh)
     int top_max_nodes = 1600; // (measured optimum at config 2) levels with at most this many fronts belong to the persistent sweep region
     // bottom of the tree: one CTA per small subtree (k_fwd_subtree / k_bwd_subtree)
-    int use_subtree = 1, subtree_maxf = 96, subtree_budget = 5632; // eligibility: every front f <= maxf, p <= 32, stored L entries of the subtree <= budget
+    int use_subtree = 1, subtree_maxf = 96, subtree_budget = 0; // (0: the variant's default)
+    int sub_variant = 1; // 1 = one warp per subtree, panels from global memory (k_*_stree_w); 0 = one CTA per subtree, bulk-staged in shared memory (k_*_stree)
+    // eligibility: every front f <= maxf, p <= 32, stored L entries of the subtree <= budget
     std::vector<char> in_sub;   // per front: handled by a subtree CTA in the solve phase
     int n_subtrees = 0;
     SubtreeDev* d_subtrees = nullptr; // descriptors, largest first (sweep_sub.cuh)
     unsigned short* d_st_tgt = nullptr;
     uchar2* d_st_pu = nullptr;
     size_t sub_smem = 0;
-    ChildRec* d_child_rec = nullptr;
     bool fac_cleared = false;      // the host entry points clear the factor arena on the side stream, under their H2D copy
-    int invert_all = 0;            // 1: explicit pivot-block inverses for every front (the subtree kernels do not need them)
     std::vector<int> inv_skip_ptr; // NIC+1: fronts whose inverses are skipped, by class, inside d_inv_skip
     int* d_inv_skip = nullptr;
     unsigned long long* d_trace = nullptr; // optional per-item timestamps of the persistent sweeps (option "trace")
     int want_trace = 0;
     int *d_node_slot = nullptr, *d_bdone = nullptr; // k_bwd_top3: scratch slot base per front, partial-products-done counters
+    int top_variant = 4;      // 4 = LL protocol (k_fwd_top_ll / k_bwd_top_ll: data and flag in one 16-byte line), 3 = completion counters (k_fwd_top2 / k_bwd_top3)
+    ulonglong2 *d_wll = nullptr, *d_xll = nullptr, *d_pll = nullptr; // LL lines: update vectors of the top fronts, solution of the top columns, partial dot products
+    int* d_wll_off = nullptr;
+    long long wll_size = 0;
     int use_top = 1, ltop = 0, n_top_items = 0, top_grid = 0, top_grid_b = 0, n_slots = 0; // (the backward kernel needs less shared memory: its own, larger co-resident grid)
     bool sweep_dirty = false;          // a persistent sweep aborted: counters must be re-armed
     std::vector<int> cdone_init;       // host copy of the initial completion counters
@@ -217,7 +221,7 @@ void release_device(InterfaceB200* s) {
     dfree(s->d_trace);
     dfree(s->d_subtrees), dfree(s->d_st_tgt), dfree(s->d_st_pu);
     dfree(s->d_node_slot), dfree(s->d_bdone);
-    dfree(s->d_child_rec);
+    dfree(s->d_wll), dfree(s->d_xll), dfree(s->d_pll), dfree(s->d_wll_off);
     dfree(s->d_inv_skip);
     dfree(s->d_big_items), dfree(s->d_big_slot), dfree(s->d_top_items), dfree(s->d_top_ranges), dfree(s->d_top_slot),
     dfree(s->d_cdone), dfree(s->d_xdone), dfree(s->d_epoch), dfree(s->d_abort), dfree(s->d_asm_ranges), dfree(s->d_big_ranges), dfree(s->d_big_scratch), dfree(s->d_big_tickets);
@@ -515,6 +519,12 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
             cnt++;
         }
     }
+    if (s->n_subtrees > 0 && !s->inv_skip_ptr.empty() && s->inv_skip_ptr[NIC] > 0) {
+        // pivot blocks of the subtree fronts, packed for the subtree solve kernels (they keep no explicit inverses)
+        const int nn = s->inv_skip_ptr[NIC];
+        k_pack_pivot_blocks<<<std::min((nn + 7) / 8, 148 * 8), 256, 0, s->stream>>>(s->d_inv_skip, nn, s->d_nodes, s->d_fac, s->d_dinv);
+        cnt++;
+    }
     if (launches) *launches = cnt;
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
@@ -535,11 +545,23 @@ __global__ void __launch_bounds__(256) k_minmax_abs(int n, const double* __restr
     if ((threadIdx.x & 31) == 0) atomicMin(mm, lo), atomicMax(mm + 1, hi);
 }
 void k_fwd_top_launch(InterfaceB200* s) {
+    if (s->top_variant >= 4) {
+        k_fwd_top_ll<<<s->top_grid, 256, B200_TOP3_SMEM, s->stream>>>(s->d_top_items, s->n_top_items, s->d_nodes, s->d_rel, s->d_fac, s->d_dinv,
+                                                                   s->d_lperm, s->d_top_ranges, s->d_wll_off, s->d_y, s->d_z, s->d_wv, s->d_wll,
+                                                                   s->d_epoch, s->d_abort, s->d_trace);
+        return;
+    }
     k_fwd_top2<<<s->top_grid, 256, B200_TOP3_SMEM, s->stream>>>(s->d_top_items, s->n_top_items, s->d_nodes, s->d_rel, s->d_fac, s->d_dinv,
                                                              s->d_lperm, s->d_top_ranges, s->d_y, s->d_z, s->d_wv, s->d_cdone, s->d_epoch,
                                                              s->d_abort, s->d_trace);
 }
 void k_bwd_top_launch(InterfaceB200* s) {
+    if (s->top_variant >= 4) {
+        k_bwd_top_ll<<<s->top_grid_b, 256, B200_TOP3_SMEM, s->stream>>>(s->d_top_items, s->n_top_items, s->d_nodes, s->d_rows, s->d_fac, s->d_dinv,
+                                                                     s->d_z, s->d_xp, s->d_xll, s->d_pll, s->d_node_slot, s->d_bdone, s->d_epoch,
+                                                                     s->d_abort, s->d_trace ? s->d_trace + 4 * (size_t)s->n_top_items : nullptr);
+        return;
+    }
     k_bwd_top3<<<s->top_grid_b, 256, B200_TOP3_SMEM, s->stream>>>(s->d_top_items, s->n_top_items, s->d_nodes, s->d_rows, s->d_fac, s->d_dinv,
                                                               s->d_z, s->d_xp, s->d_big_scratch, s->d_node_slot, s->d_bdone, s->d_epoch,
                                                               s->d_abort, s->d_trace ? s->d_trace + 4 * (size_t)s->n_top_items : nullptr);
@@ -551,8 +573,12 @@ int enqueue_sweep_levels(InterfaceB200* s, int* launches) {
     int cnt = 0;
     const int lsplit = s->n_top_items > 0 ? s->ltop : P.nlevels; // levels >= lsplit run in the persistent kernels
     if (s->n_subtrees > 0) {
-        k_fwd_stree<<<s->n_subtrees, B200_SUB_THREADS, s->sub_smem, s->stream>>>(s->d_subtrees, s->d_fac, s->d_st_tgt, s->d_st_pu, s->d_lperm,
-                                                                                 s->d_y, s->d_z, s->d_wv);
+        if (s->sub_variant == 1)
+            k_fwd_stree_w<<<(s->n_subtrees + B200_SUBW_WARPS - 1) / B200_SUBW_WARPS, 32 * B200_SUBW_WARPS, 0, s->stream>>>(
+                s->d_subtrees, s->n_subtrees, s->d_fac, s->d_st_tgt, s->d_st_pu, s->d_lperm, s->d_y, s->d_z, s->d_wv);
+        else
+            k_fwd_stree<<<s->n_subtrees, B200_SUB_THREADS, s->sub_smem, s->stream>>>(s->d_subtrees, s->d_fac, s->d_st_tgt, s->d_st_pu, s->d_lperm,
+                                                                                     s->d_y, s->d_z, s->d_wv);
         cnt++;
     }
     for (int l = 0; l < lsplit; l++) {
@@ -593,8 +619,12 @@ int enqueue_sweep_levels(InterfaceB200* s, int* launches) {
         }
     }
     if (s->n_subtrees > 0) {
-        k_bwd_stree<<<s->n_subtrees, B200_SUB_THREADS, s->sub_smem, s->stream>>>(s->d_subtrees, s->d_fac, s->d_dinv, s->d_st_tgt, s->d_st_pu,
-                                                                                 s->d_rows, s->d_z, s->d_xp);
+        if (s->sub_variant == 1)
+            k_bwd_stree_w<<<(s->n_subtrees + B200_SUBW_WARPS - 1) / B200_SUBW_WARPS, 32 * B200_SUBW_WARPS, 0, s->stream>>>(
+                s->d_subtrees, s->n_subtrees, s->d_fac, s->d_dinv, s->d_st_tgt, s->d_st_pu, s->d_rows, s->d_z, s->d_xp);
+        else
+            k_bwd_stree<<<s->n_subtrees, B200_SUB_THREADS, s->sub_smem, s->stream>>>(s->d_subtrees, s->d_fac, s->d_dinv, s->d_st_tgt, s->d_st_pu,
+                                                                                     s->d_rows, s->d_z, s->d_xp);
         cnt++;
     }
     if (launches) *launches = cnt;
@@ -728,6 +758,7 @@ struct InterfaceB200* solver_b200_new(void) {
     if ((e = getenv("B200_FUSED_VARIANT"))) s->fused_variant = atoi(e);
     if ((e = getenv("B200_USE_FUSED"))) s->use_fused = atoi(e);
     if ((e = getenv("B200_USE_TOP"))) s->use_top = atoi(e);
+    if ((e = getenv("B200_TOP_VARIANT"))) s->top_variant = atoi(e);
     if ((e = getenv("B200_USE_SUBTREE"))) s->use_subtree = atoi(e);
     if ((e = getenv("B200_SUBTREE_MAXF"))) s->subtree_maxf = atoi(e);
     if ((e = getenv("B200_SUBTREE_BUDGET"))) s->subtree_budget = atoi(e);
@@ -778,11 +809,12 @@ int32_t solver_b200_set_option(struct InterfaceB200* s, const char* key, double 
     else if (k == "fused_w8_max") s->fused_w8_max = (int)value;
     else if (k == "use_fused") s->use_fused = value != 0.0;
     else if (k == "use_top") s->use_top = value != 0.0;
+    else if (k == "top_variant") s->top_variant = (int)value;
     else if (k == "trace") s->want_trace = value != 0.0;
     else if (k == "use_subtree") s->use_subtree = value != 0.0;
-    else if (k == "invert_all") s->invert_all = value != 0.0;
     else if (k == "subtree_maxf") s->subtree_maxf = std::max(1, (int)value);
-    else if (k == "subtree_budget") s->subtree_budget = std::max(1, (int)value);
+    else if (k == "subtree_budget") s->subtree_budget = std::max(0, (int)value);
+    else if (k == "sub_variant") s->sub_variant = (int)value;
     else if (k == "diag_variant") s->diag_variant = (int)value;
     else if (k == "fuse_chain") s->fuse_chain = value != 0.0;
     else if (k == "top_max_nodes") s->top_max_nodes = std::max(1, (int)value);
@@ -831,7 +863,8 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     opt.verbose = verbose;
     opt.st_enable = s->use_subtree;
     opt.st_maxf = std::max(1, std::min(s->subtree_maxf, 200));
-    opt.st_budget = std::max(16, s->subtree_budget);
+    opt.st_budget = std::max(16, s->subtree_budget > 0 ? s->subtree_budget : (s->sub_variant == 1 ? 8192 : 5632));
+    opt.st_maxcols = s->sub_variant == 1 ? B200_SUBW_XS : 2560;
     if (ordering == B200_ORDERING_NONE) opt.ordering = ORDERING_NATURAL;
     else if (ordering == B200_ORDERING_AMD) opt.ordering = ORDERING_MINDEG;
     else opt.ordering = ORDERING_ND;
@@ -968,7 +1001,8 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
 
     // persistent top-of-tree sweep: all levels above the last "wide" level (more than 96 fronts)
     std::vector<SolveItem> top_items;
-    std::vector<int> top_ranges, top_slot, cdone_init(P.nnodes, 1 << 30), node_slot(P.nnodes, -1);
+    std::vector<int> top_ranges, top_slot, cdone_init(P.nnodes, 1 << 30), node_slot(P.nnodes, -1), wll_off(P.nnodes, -1);
+    long long wll_size = 0;
     s->ltop = P.nlevels;
     if (s->use_top) {
         std::vector<int> cnt(P.nlevels, 0); // fronts per level outside the subtree region
@@ -986,10 +1020,14 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
             const int nsl = std::max(1, (u + B200_SLICE - 1) / B200_SLICE);
             cdone_init[v] = 0;
             node_slot[v] = nslots;
+            wll_off[v] = (int)wll_size, wll_size += u;
+            if (wll_size > 0x7fff0000LL) return B200_ERROR_MALLOC;
+            int top_children = 0; // children inside the persistent region (lower levels: already visited)
+            for (int c = P.child_ptr[v]; c < P.child_ptr[v + 1]; c++) top_children += wll_off[P.child_idx[c]] >= 0;
             for (int sl = 0; sl < nsl; sl++) {
                 const int r0 = sl * B200_SLICE;
                 const int nrows = std::max(0, std::min(B200_SLICE, u - r0));
-                top_items.push_back({v, r0, nrows, sl, (int)top_ranges.size(), 0});
+                top_items.push_back({v, r0, nrows, sl, (int)top_ranges.size(), top_children == 0 ? 1 : 0});
                 top_slot.push_back(nslots);
                 for (int c = P.child_ptr[v]; c < P.child_ptr[v + 1]; c++) {
                     const int ch = P.child_idx[c];
@@ -1002,7 +1040,7 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
                     top_ranges.push_back((int)(uint32_t)((uint64_t)P.rows_ptr[ch] & 0xffffffffu));
                     top_ranges.push_back((int)(uint32_t)((uint64_t)P.rows_ptr[ch] >> 32));
                     top_ranges.push_back(std::max(1, (P.u[ch] + B200_SLICE - 1) / B200_SLICE));
-                    top_ranges.push_back(0);
+                    top_ranges.push_back(wll_off[ch]); // first LL line of the child's update vector, -1: child below the region (plain wv)
                 }
             }
             nslots += nsl;
@@ -1039,7 +1077,7 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
                     int cls = 0;
                     while (cls < NIC - 1 && P.p[v] > IC_MAXP[cls]) cls++;
                     const bool early = s->lv.inv_split >= 0 && P.level[v] < s->lv.inv_split;
-                    if (s->in_sub[v] && !s->invert_all) continue; // the subtree kernels substitute with L11 / U11 directly
+                    if (s->in_sub[v]) continue; // the subtree kernels substitute with L11 / U11 directly (their slots hold the packed pivot blocks)
                     if (cls == c && early == (pass == 0)) inv_nodes.push_back(v);
                 }
                 if (pass == 0) s->lv.inv_early[c] = (int)inv_nodes.size() - s->lv.inv_ptr[c];
@@ -1054,7 +1092,7 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
             for (int v = 0; v < P.nnodes; v++) {
                 int cls = 0;
                 while (cls < NIC - 1 && P.p[v] > IC_MAXP[cls]) cls++;
-                if (cls == c && s->in_sub[v] && !s->invert_all) skip_nodes.push_back(v);
+                if (cls == c && s->in_sub[v]) skip_nodes.push_back(v);
             }
             s->inv_skip_ptr[c + 1] = (int)skip_nodes.size();
         }
@@ -1070,18 +1108,11 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     UP(d_subtrees, subtrees);
     UP(d_st_tgt, st_tgt);
     UP(d_st_pu, st_pu);
-    {
-        std::vector<ChildRec> child_rec(P.child_idx.size());
-        for (size_t e = 0; e < P.child_idx.size(); e++) {
-            const int c = P.child_idx[e];
-            child_rec[e].c = c, child_rec[e].u = P.u[c], child_rec[e].rows_ptr = P.rows_ptr[c];
-        }
-        UP(d_child_rec, child_rec);
-    }
     UP(d_top_items, top_items);
     UP(d_top_ranges, top_ranges);
     UP(d_top_slot, top_slot);
     UP(d_node_slot, node_slot);
+    UP(d_wll_off, wll_off);
     UP(d_cdone, cdone_init);
     s->cdone_init = cdone_init;
     s->n_slots = nslots;
@@ -1127,6 +1158,15 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     DM(d_xdone, P.nnodes, int);
     DM(d_bdone, P.nnodes, int);
     CUDA_TRY(cudaMemset(s->d_bdone, 0, (size_t)std::max(P.nnodes, 1) * sizeof(int)), B200_ERROR_CUDA_MALLOC);
+    if (s->n_top_items > 0 && s->top_variant >= 4) {
+        s->wll_size = wll_size;
+        DM(d_wll, wll_size, ulonglong2);
+        DM(d_xll, P.n, ulonglong2);
+        DM(d_pll, (size_t)std::max(nslots, 1) * B200_MAXP, ulonglong2);
+        CUDA_TRY(cudaMemset(s->d_wll, 0, std::max<size_t>((size_t)wll_size, 1) * sizeof(ulonglong2)), B200_ERROR_CUDA_MALLOC);
+        CUDA_TRY(cudaMemset(s->d_xll, 0, (size_t)P.n * sizeof(ulonglong2)), B200_ERROR_CUDA_MALLOC);
+        CUDA_TRY(cudaMemset(s->d_pll, 0, (size_t)std::max(nslots, 1) * B200_MAXP * sizeof(ulonglong2)), B200_ERROR_CUDA_MALLOC);
+    }
     DM(d_epoch, 4, int); // [0] sweep epoch, [1] / [2] item tickets of the forward / backward persistent kernels
     DM(d_abort, 1, int);
     CUDA_TRY(cudaMemset(s->d_xdone, 0, (size_t)std::max(P.nnodes, 1) * sizeof(int)), B200_ERROR_CUDA_MALLOC);
@@ -1154,13 +1194,25 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     CUDA_TRY(cudaFuncSetAttribute(k_schur_dmma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_schur_dmma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_assemble_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, B200_ASM_SMEM_MAX), B200_ERROR_NOT_AVAILABLE);
+    if (s->n_subtrees > 0 && s->sub_variant != 1) {
+        if (s->sub_smem > (size_t)200 * 1024) return B200_ERROR_NOT_AVAILABLE; // (subtree_budget / subtree_maxf out of range)
+        CUDA_TRY(cudaFuncSetAttribute(k_fwd_stree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->sub_smem), B200_ERROR_NOT_AVAILABLE);
+        CUDA_TRY(cudaFuncSetAttribute(k_bwd_stree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->sub_smem), B200_ERROR_NOT_AVAILABLE);
+    }
     (void)W;
     if (s->n_top_items > 0) {
         CUDA_TRY(cudaFuncSetAttribute(k_fwd_top2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_TOP3_SMEM), B200_ERROR_NOT_AVAILABLE);
         CUDA_TRY(cudaFuncSetAttribute(k_bwd_top3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_TOP3_SMEM), B200_ERROR_NOT_AVAILABLE);
+        CUDA_TRY(cudaFuncSetAttribute(k_fwd_top_ll, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_TOP3_SMEM), B200_ERROR_NOT_AVAILABLE);
+        CUDA_TRY(cudaFuncSetAttribute(k_bwd_top_ll, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_TOP3_SMEM), B200_ERROR_NOT_AVAILABLE);
         int occ_f = 0, occ_b = 0, nsm = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_fwd_top2, 256, B200_TOP3_SMEM), B200_ERROR_NOT_AVAILABLE);
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_bwd_top3, 256, B200_TOP3_SMEM), B200_ERROR_NOT_AVAILABLE);
+        if (s->top_variant >= 4) {
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_fwd_top_ll, 256, B200_TOP3_SMEM), B200_ERROR_NOT_AVAILABLE);
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_bwd_top_ll, 256, B200_TOP3_SMEM), B200_ERROR_NOT_AVAILABLE);
+        } else {
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_fwd_top2, 256, B200_TOP3_SMEM), B200_ERROR_NOT_AVAILABLE);
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_bwd_top3, 256, B200_TOP3_SMEM), B200_ERROR_NOT_AVAILABLE);
+        }
         CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device), B200_ERROR_NOT_AVAILABLE);
         int occ = std::min(occ_f, occ_b);
         if (occ < 1) s->n_top_items = 0; // the kernels cannot run at all: fall back to per-level launches
@@ -1187,6 +1239,10 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
         cudaMemGetInfo(&fr, &tot);
         printf("solver_b200_initialize: analysis done: %d fronts, %d levels, nnz(L+U)=%lld, %.3e flops, device memory used %.2f GB\n",
                P.nnodes, P.nlevels, (long long)(P.nnz_L + P.nnz_U), P.flops, (tot - fr) / 1e9);
+        long long nsubfr = 0;
+        for (int v = 0; v < P.nnodes; v++) nsubfr += s->in_sub[v];
+        printf("solver_b200_initialize: solve phase: %d subtree CTAs (%lld fronts, %zu B of shared memory each), %d persistent items above level %d\n",
+               s->n_subtrees, nsubfr, s->sub_smem, s->n_top_items, s->ltop);
     }
     s->t_init_host = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_host0).count();
     s->initialized = true;
@@ -1207,6 +1263,11 @@ int32_t solver_b200_factorize_device(struct InterfaceB200* s, const double* d_va
         CUDA_TRY(cudaMemsetAsync(s->d_bdone, 0, (size_t)std::max(P.nnodes, 1) * sizeof(int), s->stream), B200_ERROR_CUDA_MEMCPY);
         CUDA_TRY(cudaMemsetAsync(s->d_epoch, 0, 4 * sizeof(int), s->stream), B200_ERROR_CUDA_MEMCPY);
         CUDA_TRY(cudaMemsetAsync(s->d_abort, 0, sizeof(int), s->stream), B200_ERROR_CUDA_MEMCPY);
+        if (s->d_wll) { // the epoch restarts at zero: lines tagged by earlier sweeps must not match again
+            CUDA_TRY(cudaMemsetAsync(s->d_wll, 0, std::max<size_t>((size_t)s->wll_size, 1) * sizeof(ulonglong2), s->stream), B200_ERROR_CUDA_MEMCPY);
+            CUDA_TRY(cudaMemsetAsync(s->d_xll, 0, (size_t)s->n * sizeof(ulonglong2), s->stream), B200_ERROR_CUDA_MEMCPY);
+            CUDA_TRY(cudaMemsetAsync(s->d_pll, 0, (size_t)std::max(s->n_slots, 1) * B200_MAXP * sizeof(ulonglong2), s->stream), B200_ERROR_CUDA_MEMCPY);
+        }
         CUDA_TRY(cudaMemsetAsync(s->d_big_tickets, 0, (size_t)std::max(s->n_slots, 1) * sizeof(int), s->stream), B200_ERROR_CUDA_MEMCPY);
         CUDA_TRY(cudaStreamSynchronize(s->stream), B200_ERROR_CUDA_SYNCHRONIZE);
         s->sweep_dirty = false;
@@ -1629,8 +1690,15 @@ int32_t solver_b200_debug_copy_factors(struct InterfaceB200* s, double* fac, int
         }
         CUDA_TRY(cudaStreamSynchronize(s->stream), B200_ERROR_CUDA_SYNCHRONIZE);
     }
+    if (dinv) {
+        CUDA_TRY(cudaMemcpy(dinv, s->d_dinv, std::min<int64_t>(dinv_len, s->plan.dinv_size) * sizeof(double), cudaMemcpyDeviceToHost), B200_ERROR_CUDA_MEMCPY);
+        if (s->n_subtrees > 0 && !s->inv_skip_ptr.empty() && s->inv_skip_ptr[NIC] > 0) { // give the subtree fronts their packed pivot blocks back
+            const int nn = s->inv_skip_ptr[NIC];
+            k_pack_pivot_blocks<<<std::min((nn + 7) / 8, 148 * 8), 256, 0, s->stream>>>(s->d_inv_skip, nn, s->d_nodes, s->d_fac, s->d_dinv);
+            CUDA_TRY(cudaStreamSynchronize(s->stream), B200_ERROR_CUDA_SYNCHRONIZE);
+        }
+    }
     if (fac) CUDA_TRY(cudaMemcpy(fac, s->d_fac, std::min<int64_t>(fac_len, s->plan.fac_size) * sizeof(double), cudaMemcpyDeviceToHost), B200_ERROR_CUDA_MEMCPY);
-    if (dinv) CUDA_TRY(cudaMemcpy(dinv, s->d_dinv, std::min<int64_t>(dinv_len, s->plan.dinv_size) * sizeof(double), cudaMemcpyDeviceToHost), B200_ERROR_CUDA_MEMCPY);
     if (lperm) CUDA_TRY(cudaMemcpy(lperm, s->d_lperm, std::min<int64_t>(n, s->n) * sizeof(int), cudaMemcpyDeviceToHost), B200_ERROR_CUDA_MEMCPY);
     return B200_SUCCESSFUL_EXIT;
 }

@@ -39,6 +39,7 @@ for name, tr in (("fwd", out[: 4 * nit].reshape(nit, 4)), ("bwd", out[4 * nit:].
     tr = tr.astype(np.int64)
     t0 = tr[:, 0][tr[:, 0] > 0].min()
     start, dep, end = (tr[:, 0] - t0) / 1e3, (tr[:, 1] - t0) / 1e3, (tr[:, 2] - t0) / 1e3
+    mid = (tr[:, 3] - t0) / 1e3  # (forward LL kernel: all dependent values in shared memory)
     print("==", name, "kernel span %.1f us" % (end.max() - start.min()))
     print("level nfronts nitems  first_start  first_dep  last_dep  last_end | med(dep->end) max(dep->end) | level_latency")
     levels = np.unique(desc[:, 1])
@@ -49,6 +50,7 @@ for name, tr in (("fwd", out[: 4 * nit].reshape(nit, 4)), ("bwd", out[4 * nit:].
         nf = len(np.unique(desc[m, 0]))
         work = end[m] - dep[m]
         lat = (end[m].max() - prev_end) if prev_end is not None else float("nan")
-        print("%4d %6d %6d   %9.1f %9.1f %9.1f %9.1f | %6.2f %6.2f | %6.2f" % (lv, nf, m.sum(), start[m].min(), dep[m].min(), dep[m].max(), end[m].max(),
-                                                                            np.median(work), work.max(), lat))
+        gath = np.median(mid[m] - dep[m]) if (tr[:, 3][m] > 0).all() else float("nan")
+        print("%4d %6d %6d   %9.1f %9.1f %9.1f %9.1f | %6.2f %6.2f | %6.2f | dep->gathered %5.2f" % (lv, nf, m.sum(), start[m].min(), dep[m].min(), dep[m].max(), end[m].max(),
+                                                                            np.median(work), work.max(), lat, gath))
         prev_end = end[m].max()
