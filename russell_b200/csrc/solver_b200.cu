@@ -24,6 +24,7 @@
 #include "kernels.cuh"
 #include "sweep_top.cuh"
 #include "sweep_sub.cuh"
+#include "sweep_chain.cuh"
 #include "plan.hpp"
 #include "coo_guard.hpp"
 #include <atomic>
@@ -134,7 +135,17 @@ struct InterfaceB200 {
     unsigned long long* d_trace = nullptr; // optional per-item timestamps of the persistent sweeps (option "trace")
     int want_trace = 0;
     int *d_node_slot = nullptr, *d_bdone = nullptr; // k_bwd_top3: scratch slot base per front, partial-products-done counters
-    int top_variant = 4;      // 4 = LL protocol (k_fwd_top_ll / k_bwd_top_ll: data and flag in one 16-byte line), 3 = completion counters (k_fwd_top2 / k_bwd_top3)
+    // top_variant 5 (default): pipelined supernode chains, one CTA per 64-row block (sweep_chain.cuh)
+    ChainItem* d_ch_items = nullptr;
+    ChainDev* d_chains = nullptr;
+    ChainPanel* d_ch_panels = nullptr;
+    int* d_ch_ranges = nullptr;
+    ulonglong2* d_zll = nullptr;
+    int n_ch_items = 0, ch_grid_f = 0, ch_grid_b = 0;
+    std::vector<ChainItem> h_ch_items; // host copies for the trace tool
+    std::vector<int> h_ch_level, h_ch_K;
+    long long pll_lines = 0;
+    int top_variant = 5;      // 4 = LL protocol (k_fwd_top_ll / k_bwd_top_ll: data and flag in one 16-byte line), 3 = completion counters (k_fwd_top2 / k_bwd_top3)
     ulonglong2 *d_wll = nullptr, *d_xll = nullptr, *d_pll = nullptr; // LL lines: update vectors of the top fronts, solution of the top columns, partial dot products
     int* d_wll_off = nullptr;
     long long wll_size = 0;
@@ -222,6 +233,7 @@ void release_device(InterfaceB200* s) {
     dfree(s->d_subtrees), dfree(s->d_st_tgt), dfree(s->d_st_pu);
     dfree(s->d_node_slot), dfree(s->d_bdone);
     dfree(s->d_wll), dfree(s->d_xll), dfree(s->d_pll), dfree(s->d_wll_off);
+    dfree(s->d_ch_items), dfree(s->d_chains), dfree(s->d_ch_panels), dfree(s->d_ch_ranges), dfree(s->d_zll);
     dfree(s->d_inv_skip);
     dfree(s->d_big_items), dfree(s->d_big_slot), dfree(s->d_top_items), dfree(s->d_top_ranges), dfree(s->d_top_slot),
     dfree(s->d_cdone), dfree(s->d_xdone), dfree(s->d_epoch), dfree(s->d_abort), dfree(s->d_asm_ranges), dfree(s->d_big_ranges), dfree(s->d_big_scratch), dfree(s->d_big_tickets);
@@ -545,6 +557,12 @@ __global__ void __launch_bounds__(256) k_minmax_abs(int n, const double* __restr
     if ((threadIdx.x & 31) == 0) atomicMin(mm, lo), atomicMax(mm + 1, hi);
 }
 void k_fwd_top_launch(InterfaceB200* s) {
+    if (s->n_ch_items > 0) {
+        k_fwd_chain<<<s->ch_grid_f, 256, B200_CHF_SMEM, s->stream>>>(s->d_ch_items, s->n_ch_items, s->d_chains, s->d_ch_panels, s->d_nodes, s->d_rel,
+                                                                  s->d_fac, s->d_dinv, s->d_lperm, s->d_ch_ranges, s->d_y, s->d_z, s->d_wv, s->d_wll,
+                                                                  s->d_zll, s->d_epoch, s->d_abort, s->d_trace);
+        return;
+    }
     if (s->top_variant >= 4) {
         k_fwd_top_ll<<<s->top_grid, 256, B200_TOP3_SMEM, s->stream>>>(s->d_top_items, s->n_top_items, s->d_nodes, s->d_rel, s->d_fac, s->d_dinv,
                                                                    s->d_lperm, s->d_top_ranges, s->d_wll_off, s->d_y, s->d_z, s->d_wv, s->d_wll,
@@ -556,6 +574,12 @@ void k_fwd_top_launch(InterfaceB200* s) {
                                                              s->d_abort, s->d_trace);
 }
 void k_bwd_top_launch(InterfaceB200* s) {
+    if (s->n_ch_items > 0) {
+        k_bwd_chain<<<s->ch_grid_b, 256, B200_CHB_SMEM, s->stream>>>(s->d_ch_items, s->n_ch_items, s->d_chains, s->d_ch_panels, s->d_nodes, s->d_rows,
+                                                                  s->d_fac, s->d_dinv, s->d_z, s->d_xp, s->d_xll, s->d_pll, s->d_epoch, s->d_abort,
+                                                                  s->d_trace ? s->d_trace + 4 * (size_t)s->n_ch_items : nullptr);
+        return;
+    }
     if (s->top_variant >= 4) {
         k_bwd_top_ll<<<s->top_grid_b, 256, B200_TOP3_SMEM, s->stream>>>(s->d_top_items, s->n_top_items, s->d_nodes, s->d_rows, s->d_fac, s->d_dinv,
                                                                      s->d_z, s->d_xp, s->d_xll, s->d_pll, s->d_node_slot, s->d_bdone, s->d_epoch,
@@ -1047,6 +1071,88 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
         }
     s->n_top_items = (int)top_items.size();
 
+    // ---- top_variant 5: supernode chains of the persistent region and their 64-row blocks (sweep_chain.cuh)
+    std::vector<ChainItem> ch_items;
+    std::vector<ChainDev> chains;
+    std::vector<ChainPanel> ch_panels;
+    std::vector<int> ch_ranges;
+    long long ch_wll = 0, ch_pll_groups = 0;
+    if (s->n_top_items > 0 && s->top_variant >= 5) {
+        auto intop = [&](int v) { return P.level[v] >= s->ltop && !s->in_sub[v]; };
+        std::vector<int> chain_of(P.nnodes, -1);
+        std::vector<std::vector<int>> members;
+        for (int v = 0; v < P.nnodes; v++) { // ascending = children first: a chain is met at its first panel
+            if (!intop(v) || chain_of[v] >= 0) continue;
+            std::vector<int> mem(1, v);
+            int w = v;
+            for (;;) {
+                const int par = P.parent[w];
+                if (par < 0 || !intop(par) || P.child_ptr[par + 1] - P.child_ptr[par] != 1 || P.u[w] != P.p[par] + P.u[par]) break;
+                const int* rel = &P.rel[P.rows_ptr[w]];
+                bool ident = true;
+                for (int i = 0; i < P.u[w] && ident; i++) ident = rel[i] == i;
+                if (!ident) break;
+                mem.push_back(par), w = par;
+            }
+            for (int m : mem) chain_of[m] = (int)members.size();
+            members.push_back(mem);
+        }
+        // chains in dependency order: by the level of their first panel (children chains end below their parent's first panel)
+        std::vector<int> order(members.size());
+        for (size_t t = 0; t < order.size(); t++) order[t] = (int)t;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return P.level[members[a][0]] < P.level[members[b][0]]; });
+        std::vector<int> newid(members.size());
+        for (size_t k = 0; k < order.size(); k++) newid[order[k]] = (int)k;
+        std::vector<long long> wll_of_chain(members.size(), -1); // by NEW chain id
+        chains.resize(members.size());
+        for (size_t k = 0; k < order.size(); k++) {
+            const std::vector<int>& mem = members[order[k]];
+            ChainDev& c = chains[k];
+            c.panel_ptr = (int)ch_panels.size(), c.K = (int)mem.size();
+            int off = 0;
+            for (int m : mem) ch_panels.push_back({m, off}), off += P.p[m];
+            c.P = off, c.U = P.u[mem.back()], c.last_node = mem.back();
+            c.nblocks = c.K + (c.U + B200_CH_B - 1) / B200_CH_B;
+            c.wll_off = ch_wll, ch_wll += c.U;
+            c.pbase = ch_pll_groups, ch_pll_groups += (long long)c.K * c.nblocks;
+            wll_of_chain[k] = c.wll_off;
+        }
+        for (size_t k = 0; k < order.size(); k++) {
+            const std::vector<int>& mem = members[order[k]];
+            const ChainDev& c = chains[k];
+            const int v0 = mem[0];
+            for (int jb = 0; jb < c.nblocks; jb++) {
+                ChainItem it;
+                it.chain = (int)k, it.block = jb;
+                if (jb < c.K) it.row0 = ch_panels[c.panel_ptr + jb].off, it.nrows = P.p[mem[jb]];
+                else it.row0 = c.P + (jb - c.K) * B200_CH_B, it.nrows = std::min(B200_CH_B, c.P + c.U - it.row0);
+                it.rng = (int)ch_ranges.size(), it.nch = 0;
+                for (int e = P.child_ptr[v0]; e < P.child_ptr[v0 + 1]; e++) { // children of the first front whose rows land in this block
+                    const int cnode = P.child_idx[e];
+                    const int* rel = &P.rel[P.rows_ptr[cnode]];
+                    const int a = (int)(std::lower_bound(rel, rel + P.u[cnode], it.row0) - rel);
+                    const int b = (int)(std::lower_bound(rel, rel + P.u[cnode], it.row0 + it.nrows) - rel);
+                    if (b <= a) continue;
+                    const long long wofs = P.rows_ptr[cnode];
+                    const long long llo = intop(cnode) ? wll_of_chain[newid[chain_of[cnode]]] : -1;
+                    ch_ranges.push_back(a), ch_ranges.push_back(b);
+                    ch_ranges.push_back((int)(uint32_t)((uint64_t)wofs & 0xffffffffu)), ch_ranges.push_back((int)(uint32_t)((uint64_t)wofs >> 32));
+                    ch_ranges.push_back((int)(uint32_t)((uint64_t)llo & 0xffffffffu)), ch_ranges.push_back((int)(uint32_t)((uint64_t)llo >> 32));
+                    ch_ranges.push_back(0), ch_ranges.push_back(0);
+                    it.nch++;
+                }
+                ch_items.push_back(it);
+            }
+        }
+    }
+    s->n_ch_items = (int)ch_items.size();
+    if (s->want_trace) {
+        s->h_ch_items = ch_items;
+        s->h_ch_level.resize(chains.size());
+        s->h_ch_K.resize(chains.size());
+        for (size_t k = 0; k < chains.size(); k++) s->h_ch_level[k] = P.level[ch_panels[chains[k].panel_ptr].node], s->h_ch_K[k] = chains[k].K;
+    }
+
 #define UP(dst, vec) CUDA_TRY(upload(&s->dst, vec), B200_ERROR_CUDA_MALLOC)
     UP(d_nodes, nodes);
     UP(d_rows, P.rows);
@@ -1113,6 +1219,10 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     UP(d_top_slot, top_slot);
     UP(d_node_slot, node_slot);
     UP(d_wll_off, wll_off);
+    UP(d_ch_items, ch_items);
+    UP(d_chains, chains);
+    UP(d_ch_panels, ch_panels);
+    UP(d_ch_ranges, ch_ranges);
     UP(d_cdone, cdone_init);
     s->cdone_init = cdone_init;
     s->n_slots = nslots;
@@ -1158,14 +1268,22 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     DM(d_xdone, P.nnodes, int);
     DM(d_bdone, P.nnodes, int);
     CUDA_TRY(cudaMemset(s->d_bdone, 0, (size_t)std::max(P.nnodes, 1) * sizeof(int)), B200_ERROR_CUDA_MALLOC);
+    long long nslots_pll = nslots;
+    if (s->n_ch_items > 0) { // (the chain kernels keep their own, chain-indexed LL areas)
+        wll_size = ch_wll;
+        nslots_pll = ch_pll_groups;
+        DM(d_zll, P.n, ulonglong2);
+        CUDA_TRY(cudaMemset(s->d_zll, 0, (size_t)P.n * sizeof(ulonglong2)), B200_ERROR_CUDA_MALLOC);
+    }
     if (s->n_top_items > 0 && s->top_variant >= 4) {
         s->wll_size = wll_size;
         DM(d_wll, wll_size, ulonglong2);
         DM(d_xll, P.n, ulonglong2);
-        DM(d_pll, (size_t)std::max(nslots, 1) * B200_MAXP, ulonglong2);
+        s->pll_lines = std::max<long long>(nslots_pll, 1) * B200_MAXP;
+        DM(d_pll, (size_t)s->pll_lines, ulonglong2);
         CUDA_TRY(cudaMemset(s->d_wll, 0, std::max<size_t>((size_t)wll_size, 1) * sizeof(ulonglong2)), B200_ERROR_CUDA_MALLOC);
         CUDA_TRY(cudaMemset(s->d_xll, 0, (size_t)P.n * sizeof(ulonglong2)), B200_ERROR_CUDA_MALLOC);
-        CUDA_TRY(cudaMemset(s->d_pll, 0, (size_t)std::max(nslots, 1) * B200_MAXP * sizeof(ulonglong2)), B200_ERROR_CUDA_MALLOC);
+        CUDA_TRY(cudaMemset(s->d_pll, 0, (size_t)s->pll_lines * sizeof(ulonglong2)), B200_ERROR_CUDA_MALLOC);
     }
     DM(d_epoch, 4, int); // [0] sweep epoch, [1] / [2] item tickets of the forward / backward persistent kernels
     DM(d_abort, 1, int);
@@ -1174,8 +1292,9 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     CUDA_TRY(cudaMemset(s->d_abort, 0, sizeof(int)), B200_ERROR_CUDA_MALLOC);
 #undef DM
     if (s->want_trace && s->n_top_items > 0) { // must precede the first graph capture of the sweep (the pointer is a kernel argument)
-        CUDA_TRY(cudaMalloc((void**)&s->d_trace, 8 * (size_t)s->n_top_items * sizeof(unsigned long long)), B200_ERROR_CUDA_MALLOC);
-        CUDA_TRY(cudaMemset(s->d_trace, 0, 8 * (size_t)s->n_top_items * sizeof(unsigned long long)), B200_ERROR_CUDA_MALLOC);
+        const size_t nt = (size_t)std::max(s->n_top_items, s->n_ch_items);
+        CUDA_TRY(cudaMalloc((void**)&s->d_trace, 8 * nt * sizeof(unsigned long long)), B200_ERROR_CUDA_MALLOC);
+        CUDA_TRY(cudaMemset(s->d_trace, 0, 8 * nt * sizeof(unsigned long long)), B200_ERROR_CUDA_MALLOC);
     }
     CUDA_TRY(cudaMallocHost((void**)&s->h_norms, 4 * sizeof(double)), B200_ERROR_MALLOC);
     CUDA_TRY(cudaMallocHost((void**)&s->h_counters, 16 * sizeof(int)), B200_ERROR_MALLOC);
@@ -1214,6 +1333,16 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_bwd_top3, 256, B200_TOP3_SMEM), B200_ERROR_NOT_AVAILABLE);
         }
         CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device), B200_ERROR_NOT_AVAILABLE);
+        if (s->n_ch_items > 0) {
+            CUDA_TRY(cudaFuncSetAttribute(k_fwd_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_CHF_SMEM), B200_ERROR_NOT_AVAILABLE);
+            CUDA_TRY(cudaFuncSetAttribute(k_bwd_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_CHB_SMEM), B200_ERROR_NOT_AVAILABLE);
+            int of = 0, ob = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&of, k_fwd_chain, 256, B200_CHF_SMEM), B200_ERROR_NOT_AVAILABLE);
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ob, k_bwd_chain, 256, B200_CHB_SMEM), B200_ERROR_NOT_AVAILABLE);
+            if (of < 1 || ob < 1) s->n_ch_items = 0;
+            s->ch_grid_f = std::max(1, std::min(s->n_ch_items, of * nsm));
+            s->ch_grid_b = std::max(1, std::min(s->n_ch_items, ob * nsm));
+        }
         int occ = std::min(occ_f, occ_b);
         if (occ < 1) s->n_top_items = 0; // the kernels cannot run at all: fall back to per-level launches
         s->top_grid = std::max(1, std::min(s->n_top_items, occ_f * nsm)); // (a performance choice only: items are handed out by ticket)
@@ -1266,7 +1395,8 @@ int32_t solver_b200_factorize_device(struct InterfaceB200* s, const double* d_va
         if (s->d_wll) { // the epoch restarts at zero: lines tagged by earlier sweeps must not match again
             CUDA_TRY(cudaMemsetAsync(s->d_wll, 0, std::max<size_t>((size_t)s->wll_size, 1) * sizeof(ulonglong2), s->stream), B200_ERROR_CUDA_MEMCPY);
             CUDA_TRY(cudaMemsetAsync(s->d_xll, 0, (size_t)s->n * sizeof(ulonglong2), s->stream), B200_ERROR_CUDA_MEMCPY);
-            CUDA_TRY(cudaMemsetAsync(s->d_pll, 0, (size_t)std::max(s->n_slots, 1) * B200_MAXP * sizeof(ulonglong2), s->stream), B200_ERROR_CUDA_MEMCPY);
+            CUDA_TRY(cudaMemsetAsync(s->d_pll, 0, (size_t)s->pll_lines * sizeof(ulonglong2), s->stream), B200_ERROR_CUDA_MEMCPY);
+            if (s->d_zll) CUDA_TRY(cudaMemsetAsync(s->d_zll, 0, (size_t)s->n * sizeof(ulonglong2), s->stream), B200_ERROR_CUDA_MEMCPY);
         }
         CUDA_TRY(cudaMemsetAsync(s->d_big_tickets, 0, (size_t)std::max(s->n_slots, 1) * sizeof(int), s->stream), B200_ERROR_CUDA_MEMCPY);
         CUDA_TRY(cudaStreamSynchronize(s->stream), B200_ERROR_CUDA_SYNCHRONIZE);
@@ -1660,6 +1790,19 @@ int32_t solver_b200_debug_trace(struct InterfaceB200* s, unsigned long long* out
     if (!s || !s->d_trace || !s->initialized) return -1;
     cudaSetDevice(s->device);
     cudaStreamSynchronize(s->stream);
+    if (s->n_ch_items > 0) { // chain kernels: desc = (chain, level of its first panel, block, rows)
+        const int nc = std::min(cap, s->n_ch_items);
+        if (out) {
+            cudaMemcpy(out, s->d_trace, 4 * (size_t)nc * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+            cudaMemcpy(out + 4 * (size_t)nc, s->d_trace + 4 * (size_t)s->n_ch_items, 4 * (size_t)nc * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+        }
+        if (desc)
+            for (int i = 0; i < nc && i < (int)s->h_ch_items.size(); i++) {
+                const ChainItem& it = s->h_ch_items[i];
+                desc[4 * i] = it.chain, desc[4 * i + 1] = s->h_ch_level[it.chain] + std::min(it.block, s->h_ch_K[it.chain] - 1), desc[4 * i + 2] = it.block, desc[4 * i + 3] = it.nrows;
+            }
+        return s->n_ch_items;
+    }
     const int n = std::min(cap, s->n_top_items);
     if (out) {
         cudaMemcpy(out, s->d_trace, 4 * (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
