@@ -135,9 +135,10 @@ struct InterfaceB200 {
     unsigned long long* d_trace = nullptr; // optional per-item timestamps of the persistent sweeps (option "trace")
     int want_trace = 0;
     int *d_node_slot = nullptr, *d_bdone = nullptr; // k_bwd_top3: scratch slot base per front, partial-products-done counters
-    // top_variant 5 (default): pipelined supernode chains, one CTA per 64-row block (sweep_chain.cuh)
+    // top_variant 5: pipelined supernode chains, one CTA per 64-row block (sweep_chain.cuh).  Built and measured in round 2:
+    // correct, but slower than the slice kernels at config 2 (0.84-1.05 ms per sweep vs 0.80 ms): twice the items, and a
+    // per-item cost of ~5 us at the wide levels (profiles/r2j_trace_chain.txt).  Kept as an option for the A/B evidence.
     ChainItem* d_ch_items = nullptr;
-    ChainDev* d_chains = nullptr;
     ChainPanel* d_ch_panels = nullptr;
     int* d_ch_ranges = nullptr;
     ulonglong2* d_zll = nullptr;
@@ -145,7 +146,7 @@ struct InterfaceB200 {
     std::vector<ChainItem> h_ch_items; // host copies for the trace tool
     std::vector<int> h_ch_level, h_ch_K;
     long long pll_lines = 0;
-    int top_variant = 5;      // 4 = LL protocol (k_fwd_top_ll / k_bwd_top_ll: data and flag in one 16-byte line), 3 = completion counters (k_fwd_top2 / k_bwd_top3)
+    int top_variant = 3;      // 4 = LL protocol (k_fwd_top_ll / k_bwd_top_ll: data and flag in one 16-byte line), 3 = completion counters (k_fwd_top2 / k_bwd_top3)
     ulonglong2 *d_wll = nullptr, *d_xll = nullptr, *d_pll = nullptr; // LL lines: update vectors of the top fronts, solution of the top columns, partial dot products
     int* d_wll_off = nullptr;
     long long wll_size = 0;
@@ -233,7 +234,7 @@ void release_device(InterfaceB200* s) {
     dfree(s->d_subtrees), dfree(s->d_st_tgt), dfree(s->d_st_pu);
     dfree(s->d_node_slot), dfree(s->d_bdone);
     dfree(s->d_wll), dfree(s->d_xll), dfree(s->d_pll), dfree(s->d_wll_off);
-    dfree(s->d_ch_items), dfree(s->d_chains), dfree(s->d_ch_panels), dfree(s->d_ch_ranges), dfree(s->d_zll);
+    dfree(s->d_ch_items), dfree(s->d_ch_panels), dfree(s->d_ch_ranges), dfree(s->d_zll);
     dfree(s->d_inv_skip);
     dfree(s->d_big_items), dfree(s->d_big_slot), dfree(s->d_top_items), dfree(s->d_top_ranges), dfree(s->d_top_slot),
     dfree(s->d_cdone), dfree(s->d_xdone), dfree(s->d_epoch), dfree(s->d_abort), dfree(s->d_asm_ranges), dfree(s->d_big_ranges), dfree(s->d_big_scratch), dfree(s->d_big_tickets);
@@ -558,9 +559,8 @@ __global__ void __launch_bounds__(256) k_minmax_abs(int n, const double* __restr
 }
 void k_fwd_top_launch(InterfaceB200* s) {
     if (s->n_ch_items > 0) {
-        k_fwd_chain<<<s->ch_grid_f, 256, B200_CHF_SMEM, s->stream>>>(s->d_ch_items, s->n_ch_items, s->d_chains, s->d_ch_panels, s->d_nodes, s->d_rel,
-                                                                  s->d_fac, s->d_dinv, s->d_lperm, s->d_ch_ranges, s->d_y, s->d_z, s->d_wv, s->d_wll,
-                                                                  s->d_zll, s->d_epoch, s->d_abort, s->d_trace);
+        k_fwd_chain<<<s->ch_grid_f, 256, 0, s->stream>>>(s->d_ch_items, s->n_ch_items, s->d_ch_panels, s->d_rel, s->d_fac, s->d_dinv, s->d_lperm,
+                                                      s->d_ch_ranges, s->d_y, s->d_z, s->d_wv, s->d_wll, s->d_zll, s->d_epoch, s->d_abort, s->d_trace);
         return;
     }
     if (s->top_variant >= 4) {
@@ -575,9 +575,9 @@ void k_fwd_top_launch(InterfaceB200* s) {
 }
 void k_bwd_top_launch(InterfaceB200* s) {
     if (s->n_ch_items > 0) {
-        k_bwd_chain<<<s->ch_grid_b, 256, B200_CHB_SMEM, s->stream>>>(s->d_ch_items, s->n_ch_items, s->d_chains, s->d_ch_panels, s->d_nodes, s->d_rows,
-                                                                  s->d_fac, s->d_dinv, s->d_z, s->d_xp, s->d_xll, s->d_pll, s->d_epoch, s->d_abort,
-                                                                  s->d_trace ? s->d_trace + 4 * (size_t)s->n_ch_items : nullptr);
+        k_bwd_chain<<<s->ch_grid_b, 256, 0, s->stream>>>(s->d_ch_items, s->n_ch_items, s->d_ch_panels, s->d_rows, s->d_fac, s->d_dinv, s->d_z, s->d_xp,
+                                                      s->d_xll, s->d_pll, s->d_epoch, s->d_abort,
+                                                      s->d_trace ? s->d_trace + 4 * (size_t)s->n_ch_items : nullptr);
         return;
     }
     if (s->top_variant >= 4) {
@@ -902,6 +902,7 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     int rc = analyze(ndim, row_pointers, col_indices, values, general_symmetric != 0 || positive_definite != 0, opt, s->plan);
     if (rc == -1) return B200_ERROR_SINGULAR;
     if (rc != 0) return B200_ERROR_ANALYSIS + 2;
+    if (verbose) fprintf(stderr, "solver_b200_initialize:   analysis done at %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_host0).count());
     Plan& P = s->plan;
     s->n = P.n;
     s->nnz_in = P.nnz_in;
@@ -973,6 +974,7 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     }
     s->sub_smem = sub_smem;
     s->n_subtrees = (int)subtrees.size();
+    if (verbose) fprintf(stderr, "solver_b200_initialize:   subtree descriptors built at %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_host0).count());
     std::vector<AsmItem> asm_items;
     std::vector<PanelItem> panel_items;
     std::vector<SchurItem> schur_items;
@@ -1008,6 +1010,7 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
         s->lv.big_ptr[l + 1] = (int)big_items.size();
     }
 
+    if (verbose) fprintf(stderr, "solver_b200_initialize:   work lists built at %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_host0).count());
     // SpMV row blocks (rows never split; at most B200_SPMV_NNZ nonzeros and 1024 rows per block)
     std::vector<int> rowblk;
     {
@@ -1073,9 +1076,8 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
 
     // ---- top_variant 5: supernode chains of the persistent region and their 64-row blocks (sweep_chain.cuh)
     std::vector<ChainItem> ch_items;
-    std::vector<ChainDev> chains;
     std::vector<ChainPanel> ch_panels;
-    std::vector<int> ch_ranges;
+    std::vector<int> ch_ranges, ch_level, ch_K;
     long long ch_wll = 0, ch_pll_groups = 0;
     if (s->n_top_items > 0 && s->top_variant >= 5) {
         auto intop = [&](int v) { return P.level[v] >= s->ltop && !s->in_sub[v]; };
@@ -1104,28 +1106,42 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
         std::vector<int> newid(members.size());
         for (size_t k = 0; k < order.size(); k++) newid[order[k]] = (int)k;
         std::vector<long long> wll_of_chain(members.size(), -1); // by NEW chain id
-        chains.resize(members.size());
+        struct ChainHost { int panel_ptr, K, P, U, nblocks, last_node; long long wll_off, pbase; };
+        std::vector<ChainHost> chh(members.size());
         for (size_t k = 0; k < order.size(); k++) {
             const std::vector<int>& mem = members[order[k]];
-            ChainDev& c = chains[k];
+            ChainHost& c = chh[k];
             c.panel_ptr = (int)ch_panels.size(), c.K = (int)mem.size();
             int off = 0;
-            for (int m : mem) ch_panels.push_back({m, off}), off += P.p[m];
+            for (int m : mem) {
+                ChainPanel cp;
+                cp.Loff = P.Loff[m], cp.Uoff = P.Uoff[m], cp.off = off, cp.p = P.p[m], cp.f = P.p[m] + P.u[m], cp.u = P.u[m], cp.c0 = P.c0[m], cp.pad = m;
+                ch_panels.push_back(cp), off += P.p[m];
+            }
             c.P = off, c.U = P.u[mem.back()], c.last_node = mem.back();
             c.nblocks = c.K + (c.U + B200_CH_B - 1) / B200_CH_B;
             c.wll_off = ch_wll, ch_wll += c.U;
             c.pbase = ch_pll_groups, ch_pll_groups += (long long)c.K * c.nblocks;
             wll_of_chain[k] = c.wll_off;
         }
+        ch_level.resize(order.size()), ch_K.resize(order.size());
         for (size_t k = 0; k < order.size(); k++) {
             const std::vector<int>& mem = members[order[k]];
-            const ChainDev& c = chains[k];
+            const ChainHost& c = chh[k];
             const int v0 = mem[0];
+            ch_level[k] = P.level[v0], ch_K[k] = c.K;
             for (int jb = 0; jb < c.nblocks; jb++) {
                 ChainItem it;
-                it.chain = (int)k, it.block = jb;
-                if (jb < c.K) it.row0 = ch_panels[c.panel_ptr + jb].off, it.nrows = P.p[mem[jb]];
-                else it.row0 = c.P + (jb - c.K) * B200_CH_B, it.nrows = std::min(B200_CH_B, c.P + c.U - it.row0);
+                it.chain = (int)k, it.block = jb, it.K = c.K, it.nblocks = c.nblocks, it.panel_ptr = c.panel_ptr, it.pgrp = c.pbase;
+                it.c0j = 0, it.Doff = 0, it.out = 0, it.rows_off = 0;
+                if (jb < c.K) {
+                    it.row0 = ch_panels[c.panel_ptr + jb].off, it.nrows = P.p[mem[jb]];
+                    it.c0j = P.c0[mem[jb]], it.Doff = P.Doff[mem[jb]];
+                } else {
+                    it.row0 = c.P + (jb - c.K) * B200_CH_B, it.nrows = std::min(B200_CH_B, c.P + c.U - it.row0);
+                    it.out = c.wll_off + (it.row0 - c.P);
+                    it.rows_off = P.rows_ptr[c.last_node] + (it.row0 - c.P);
+                }
                 it.rng = (int)ch_ranges.size(), it.nch = 0;
                 for (int e = P.child_ptr[v0]; e < P.child_ptr[v0 + 1]; e++) { // children of the first front whose rows land in this block
                     const int cnode = P.child_idx[e];
@@ -1146,13 +1162,9 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
         }
     }
     s->n_ch_items = (int)ch_items.size();
-    if (s->want_trace) {
-        s->h_ch_items = ch_items;
-        s->h_ch_level.resize(chains.size());
-        s->h_ch_K.resize(chains.size());
-        for (size_t k = 0; k < chains.size(); k++) s->h_ch_level[k] = P.level[ch_panels[chains[k].panel_ptr].node], s->h_ch_K[k] = chains[k].K;
-    }
+    if (s->want_trace) s->h_ch_items = ch_items, s->h_ch_level = ch_level, s->h_ch_K = ch_K;
 
+    if (verbose) fprintf(stderr, "solver_b200_initialize:   top items built at %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_host0).count());
 #define UP(dst, vec) CUDA_TRY(upload(&s->dst, vec), B200_ERROR_CUDA_MALLOC)
     UP(d_nodes, nodes);
     UP(d_rows, P.rows);
@@ -1220,7 +1232,6 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     UP(d_node_slot, node_slot);
     UP(d_wll_off, wll_off);
     UP(d_ch_items, ch_items);
-    UP(d_chains, chains);
     UP(d_ch_panels, ch_panels);
     UP(d_ch_ranges, ch_ranges);
     UP(d_cdone, cdone_init);
@@ -1243,6 +1254,7 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     if (!P.full_src.empty()) UP(d_full_src, P.full_src);
     UP(d_rowblk, rowblk);
 #undef UP
+    if (verbose) fprintf(stderr, "solver_b200_initialize:   plan uploaded at %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_host0).count());
 #define DM(ptr, count, type) CUDA_TRY(cudaMalloc((void**)&s->ptr, std::max<size_t>((size_t)(count), 1) * sizeof(type)), B200_ERROR_CUDA_MALLOC)
     DM(d_vals, P.nnz_in, double);
     if (P.sym_lower) DM(d_fullvals, s->fnnz, double);
@@ -1299,6 +1311,7 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     CUDA_TRY(cudaMallocHost((void**)&s->h_norms, 4 * sizeof(double)), B200_ERROR_MALLOC);
     CUDA_TRY(cudaMallocHost((void**)&s->h_counters, 16 * sizeof(int)), B200_ERROR_MALLOC);
 
+    if (verbose) fprintf(stderr, "solver_b200_initialize:   arenas allocated at %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_host0).count());
     // kernels that need more than 48 KB of dynamic shared memory
     const int W = s->opt_panel_width;
     CUDA_TRY(cudaFuncSetAttribute(k_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_diag(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
@@ -1334,11 +1347,9 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
         }
         CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device), B200_ERROR_NOT_AVAILABLE);
         if (s->n_ch_items > 0) {
-            CUDA_TRY(cudaFuncSetAttribute(k_fwd_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_CHF_SMEM), B200_ERROR_NOT_AVAILABLE);
-            CUDA_TRY(cudaFuncSetAttribute(k_bwd_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_CHB_SMEM), B200_ERROR_NOT_AVAILABLE);
             int of = 0, ob = 0;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&of, k_fwd_chain, 256, B200_CHF_SMEM), B200_ERROR_NOT_AVAILABLE);
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ob, k_bwd_chain, 256, B200_CHB_SMEM), B200_ERROR_NOT_AVAILABLE);
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&of, k_fwd_chain, 256, 0), B200_ERROR_NOT_AVAILABLE);
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ob, k_bwd_chain, 256, 0), B200_ERROR_NOT_AVAILABLE);
             if (of < 1 || ob < 1) s->n_ch_items = 0;
             s->ch_grid_f = std::max(1, std::min(s->n_ch_items, of * nsm));
             s->ch_grid_b = std::max(1, std::min(s->n_ch_items, ob * nsm));

@@ -8,6 +8,7 @@
 #include "plan.hpp"
 #include <iterator>
 #include <map>
+#include <set>
 
 #include <algorithm>
 #include <cassert>
@@ -324,6 +325,7 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
     P.rowperm.resize(n);
     for (int k = 0; k < n; k++) P.rowperm[k] = rowmatch[q[k]];
 
+    if (opt.verbose >= 2) fprintf(stderr, "b200 analyze:   phase etree done at %.3f s\n", now_s() - t0);
     // ---- fundamental supernodes, then amalgamation over the supernode tree -------------------------------
     // Any child may be merged into its parent (not only a contiguous last child): columns of different
     // subtrees are independent, so the merged children's columns can be moved right in front of the parent's
@@ -479,6 +481,7 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
         sparent[s] = parent[lastc] < 0 ? -1 : col2sn[parent[lastc]];
     }
 
+    if (opt.verbose >= 2) fprintf(stderr, "b200 analyze:   phase amalgamation done at %.3f s\n", now_s() - t0);
     // ---- row structure of every supernode (rows beyond its last column, ascending) ----------------------
     std::vector<std::vector<int>> srows(ns);
     {
@@ -516,6 +519,7 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
     }
     g = Graph();
 
+    if (opt.verbose >= 2) fprintf(stderr, "b200 analyze:   phase rowstruct done at %.3f s\n", now_s() - t0);
     // ---- split wide supernodes into panels: the front tree ------------------------------------------------
     std::vector<int> sn_firstnode(ns), sn_npieces(ns);
     int nnodes = 0;
@@ -613,6 +617,7 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
         for (int v = 0; v < nnodes; v++) P.level_nodes[fill[P.level[v]]++] = v;
     }
     // storage offsets + stats
+    if (opt.verbose >= 2) fprintf(stderr, "b200 analyze:   phase fronttree done at %.3f s\n", now_s() - t0);
     // ---- solve-phase subtrees: maximal subtrees whose fronts are all small (nodes are in postorder: the subtree rooted at
     //      v is the contiguous range [v - size + 1, v])
     P.in_sub.assign(nnodes, 0);
@@ -683,19 +688,14 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
         for (int v = 0; v < nnodes; v++)
             if (P.u[v] > 0) born_at[born[v]].push_back(v), dies_at[dies[v]].push_back(v);
         std::map<int64_t, int64_t> free_by_off;            // offset -> size (coalesced)
-        std::multimap<int64_t, int64_t> free_by_size;      // size -> offset
-        auto erase_size = [&](int64_t size, int64_t off) {
-            auto r = free_by_size.equal_range(size);
-            for (auto it = r.first; it != r.second; ++it)
-                if (it->second == off) { free_by_size.erase(it); return; }
-        };
+        std::set<std::pair<int64_t, int64_t>> free_by_size; // (size, offset)
         auto release = [&](int64_t off, int64_t size) {
             auto nx = free_by_off.lower_bound(off);
             if (nx != free_by_off.begin()) {
                 auto pv = std::prev(nx);
-                if (pv->first + pv->second == off) { off = pv->first, size += pv->second; erase_size(pv->second, pv->first); free_by_off.erase(pv); }
+                if (pv->first + pv->second == off) { off = pv->first, size += pv->second; free_by_size.erase({pv->second, pv->first}); free_by_off.erase(pv); }
             }
-            if (nx != free_by_off.end() && off + size == nx->first) { size += nx->second; erase_size(nx->second, nx->first); free_by_off.erase(nx); }
+            if (nx != free_by_off.end() && off + size == nx->first) { size += nx->second; free_by_size.erase({nx->second, nx->first}); free_by_off.erase(nx); }
             free_by_off[off] = size;
             free_by_size.insert({size, off});
         };
@@ -704,9 +704,9 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
             std::sort(born_at[l].begin(), born_at[l].end(), [&](int a, int b) { return P.u[a] != P.u[b] ? P.u[a] > P.u[b] : a < b; });
             for (int v : born_at[l]) {
                 const int64_t need = round_up4((int64_t)P.u[v] * P.u[v]);
-                auto it = free_by_size.lower_bound(need); // best fit
+                auto it = free_by_size.lower_bound({need, (int64_t)0}); // best fit
                 if (it != free_by_size.end()) {
-                    const int64_t off = it->second, size = it->first;
+                    const int64_t size = it->first, off = it->second;
                     free_by_size.erase(it);
                     free_by_off.erase(off);
                     P.Coff[v] = off;
@@ -716,7 +716,7 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
                     int64_t off = co;
                     if (!free_by_off.empty()) {
                         auto last = std::prev(free_by_off.end());
-                        if (last->first + last->second == co) { off = last->first; erase_size(last->second, last->first); free_by_off.erase(last); }
+                        if (last->first + last->second == co) { off = last->first; free_by_size.erase({last->second, last->first}); free_by_off.erase(last); }
                     }
                     P.Coff[v] = off;
                     co = off + need;
@@ -728,6 +728,7 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
     }
     P.fac_size = fo, P.cb_size = co, P.dinv_size = dof;
 
+    if (opt.verbose >= 2) fprintf(stderr, "b200 analyze:   phase subtrees+layout+cb done at %.3f s\n", now_s() - t0);
     // ---- value scatter map ---------------------------------------------------------------------------
     const bool scaled = !P.rscale.empty();
     P.a_src.resize(fnnz);
@@ -767,6 +768,7 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
             if (scaled) P.a_scl[k] = P.rscale[i] * P.cscale[j];
         }
     }
+    if (opt.verbose >= 2) fprintf(stderr, "b200 analyze:   phase scattermap done at %.3f s\n", now_s() - t0);
     P.t_symbolic = now_s() - t0;
     if (opt.verbose) {
         fprintf(stderr,

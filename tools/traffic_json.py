@@ -20,8 +20,10 @@ for r in rows:
     else:
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
         k["dram_read_bytes" if "read" in m else "dram_write_bytes"] += v * scale
-for name in per:
-    per[name]["launches"] = len(ids[name])
+for name in per:  # per LAUNCH (the capture may hold several solves)
+    nl = per[name]["launches"] = len(ids[name])
+    for key in ("time_us", "dram_read_bytes", "dram_write_bytes"):
+        per[name][key] /= nl
 sweep = sum(v["dram_read_bytes"] + v["dram_write_bytes"] for k, v in per.items() if "spmv" not in k)
 spmv = sum(v["dram_read_bytes"] + v["dram_write_bytes"] for k, v in per.items() if "spmv" in k)
 json.dump({"workload": "5-point 2D Laplacian %dx%d, one forward+backward SpTRSV sweep (no refinement step)" % (grid, grid), "grid": grid,
