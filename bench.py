@@ -298,7 +298,9 @@ def main():
     h_x = torch.zeros(n, dtype=torch.float64).pin_memory()
     d_vals = h_vals.cuda()
     d_rhs = h_rhs.cuda()
-    d_x = torch.zeros(n, dtype=torch.float64, device="cuda")
+    # one system per rank: the solve writes x straight into this rank's slot of the preallocated gather buffer
+    gatherer = batch.SolutionGatherer(world, world, rank, n, torch.float64, torch.device("cuda", local_rank))
+    d_x = gatherer.block[0]
     em, ep = ctypes.c_int32(0), ctypes.c_int32(0)
 
     def step_device():
@@ -307,7 +309,8 @@ def main():
         rc = lib.solver_b200_solve_device(h, d_x.data_ptr(), d_rhs.data_ptr())
         assert rc == 0, rc
         if world > 1:
-            batch.gather_solutions(d_x[None, :], world, world, rank)  # system r lives on rank r
+            with torch.cuda.stream(stream):  # ordered after the solve on the solver's own stream: no host synchronisation
+                gatherer.gather()  # system r lives on rank r
 
     def step_e2e():
         rc = lib.solver_b200_factorize(h, ctypes.byref(em), ctypes.byref(ep), 0, ctypes.cast(h_vals.data_ptr(), p_f64))
@@ -315,7 +318,9 @@ def main():
         rc = lib.solver_b200_solve(h, ctypes.cast(h_x.data_ptr(), p_f64), ctypes.cast(h_rhs.data_ptr(), p_f64), 0)
         assert rc == 0, rc
         if world > 1:
-            batch.gather_solutions(d_x.copy_(h_x, non_blocking=True)[None, :], world, world, rank)
+            with torch.cuda.stream(stream):
+                d_x.copy_(h_x, non_blocking=True)
+                gatherer.gather()
 
     def get_stats():
         out = np.zeros(len(rb.SolverB200.STAT_NAMES))

@@ -222,6 +222,12 @@ int32_t complex_solver_b200_get_stats(struct InterfaceComplexB200 *solver, doubl
 int32_t complex_solver_b200_set_option(struct InterfaceComplexB200 *solver, const char *key, double value);
 struct InterfaceB200 *complex_solver_b200_real_handle(struct InterfaceComplexB200 *solver);
 
+/* the tcgen05 Schur-complement kernel on its own (tests / profiling): C (u x u, column-major) <- C - A * B^T, A and B u x k
+ * column-major, all HOST pointers.  Same operand split (8 signed 7-bit slices per entry), tile layout and kernel
+ * (tcgen05.mma.kind::i8, TMEM accumulators, TMA bulk loads, f64 recombination) as schur_variant = 2 of the factorization:
+ * russell_b200/csrc/ozaki_tc.cuh.  *ms = device time of split + GEMM. */
+int32_t solver_b200_ozaki_gemm(int32_t u, int32_t k, const double *a, const double *b, double *c, double *ms);
+
 /* library identification string (static storage) */
 const char *solver_b200_version(void);
 

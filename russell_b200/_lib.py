@@ -33,6 +33,7 @@ SIGNATURES = {
     "solver_b200_factorize_coo_device": (c_i32, [p_void, p_void]),
     "solver_b200_factorize_coo_checked": (c_i32, [p_void, p_i32, p_i32, c_i32, c_i32, p_i32, p_i32, p_f64]),
     "solver_b200_rcond": (c_i32, [p_void, p_f64]),
+    "solver_b200_ozaki_gemm": (c_i32, [c_i32, c_i32, p_f64, p_f64, p_f64, p_f64]),
     "solver_b200_solve_device": (c_i32, [p_void, p_void, p_void]),
     "solver_b200_residual": (c_i32, [p_void, p_f64, p_f64, p_f64]),
     "solver_b200_spmv": (c_i32, [p_void, p_f64, p_f64]),

@@ -35,6 +35,35 @@ def gather_solutions(x_local, nsys, world, rank):
     return out
 
 
+class SolutionGatherer:
+    """The per-step gather of bench.py without per-step allocations or Python loops (round-1 review: three fresh tensors,
+    a list-form all_gather and 2N copies per step cost 0.33 ms of a 9 ms step at N = 8).  Buffers are allocated once;
+    `block` is this rank's slot block -- a solver can write its solution straight into `block[slot]` -- and `gather()`
+    issues ONE all_gather_into_tensor on the CURRENT stream (call it under `torch.cuda.stream(solver_stream)` so that it
+    is ordered after the solve without a cross-stream synchronisation).  With one system per rank the gathered tensor is
+    already in system order; otherwise a precomputed index restores it."""
+
+    def __init__(self, nsys, world, rank, n, dtype=torch.float64, device="cpu"):
+        self.nsys, self.world, self.rank, self.n = nsys, world, rank, n
+        self.per = slots_per_rank(nsys, world)
+        self.block = torch.zeros((self.per, n), dtype=dtype, device=device)
+        self.out = torch.empty((world * self.per, n), dtype=dtype, device=device) if world > 1 else self.block
+        rows = [0] * nsys
+        for r in range(world):
+            for slot, i in enumerate(shard(nsys, world, r)):
+                rows[i] = r * self.per + slot
+        self.identity = rows == list(range(nsys))
+        self.index = None if self.identity else torch.tensor(rows, dtype=torch.long, device=device)
+
+    def gather(self):
+        """all ranks' blocks -> (nsys, n) in system order (a view of the preallocated buffer when possible)"""
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.out, self.block)
+        if self.identity:
+            return self.out[: self.nsys]
+        return self.out.index_select(0, self.index)
+
+
 def max_over_ranks(value, world, device="cpu"):
     """timing rule of bench.py: a multi-rank number is the MAX over ranks"""
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)

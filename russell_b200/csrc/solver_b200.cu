@@ -25,6 +25,7 @@
 #include "sweep_top.cuh"
 #include "sweep_sub.cuh"
 #include "sweep_chain.cuh"
+#include "ozaki_tc.cuh"
 #include "plan.hpp"
 #include "coo_guard.hpp"
 #include <atomic>
@@ -1734,6 +1735,55 @@ int32_t solver_b200_determinant(struct InterfaceB200* s, double* coefficient, do
     }
     *coefficient = mant;
     *exponent = ex;
+    return B200_SUCCESSFUL_EXIT;
+}
+
+// standalone entry of the tcgen05 Schur kernel (tests / profiling): C (u x u, column-major, host) <- C - A * B^T with A, B
+// u x k column-major host arrays -- the operation k_schur_ozaki performs for one front, through the same split kernel,
+// the same tile layout and the same launch as the factorization uses.  Returns the kernel time in *ms_out.
+int32_t solver_b200_ozaki_gemm(int32_t u, int32_t k, const double* a, const double* b, double* c, double* ms_out) {
+    if (!a || !b || !c || u < 1 || k < 1) return B200_ERROR_NULL_POINTER;
+    InterfaceB200* s = nullptr;
+    const int kch = (k + OZ_KC - 1) / OZ_KC;
+    const int nta = (u + OZ_BM - 1) / OZ_BM, ntb = (u + OZ_BN - 1) / OZ_BN;
+    const size_t a_bytes = (size_t)nta * kch * OZ_S * OZ_A_BYTES, b_bytes = (size_t)ntb * kch * OZ_S * OZ_B_BYTES;
+    double *d_ab = nullptr, *d_c = nullptr, *d_sc = nullptr;
+    signed char* d_tiles = nullptr;
+    OzakiSplitItem* d_split = nullptr;
+    OzakiItem* d_items = nullptr;
+    CUDA_TRY(cudaMalloc(&d_ab, (size_t)2 * u * k * sizeof(double)), B200_ERROR_CUDA_MALLOC);
+    CUDA_TRY(cudaMalloc(&d_c, (size_t)u * u * sizeof(double)), B200_ERROR_CUDA_MALLOC);
+    CUDA_TRY(cudaMalloc(&d_sc, (size_t)2 * u * sizeof(double)), B200_ERROR_CUDA_MALLOC);
+    CUDA_TRY(cudaMalloc(&d_tiles, a_bytes + b_bytes), B200_ERROR_CUDA_MALLOC);
+    CUDA_TRY(cudaMemcpy(d_ab, a, (size_t)u * k * sizeof(double), cudaMemcpyHostToDevice), B200_ERROR_CUDA_MEMCPY);
+    CUDA_TRY(cudaMemcpy(d_ab + (size_t)u * k, b, (size_t)u * k * sizeof(double), cudaMemcpyHostToDevice), B200_ERROR_CUDA_MEMCPY);
+    CUDA_TRY(cudaMemcpy(d_c, c, (size_t)u * u * sizeof(double), cudaMemcpyHostToDevice), B200_ERROR_CUDA_MEMCPY);
+    std::vector<OzakiSplitItem> split = {{0, 0, 0, u, k, u, OZ_BM}, {(long long)u * k, (long long)a_bytes, u, u, k, u, OZ_BN}};
+    std::vector<OzakiItem> items;
+    for (int tj = 0; tj < ntb; tj++)
+        for (int ti = 0; ti < nta; ti++) items.push_back({0, (long long)a_bytes, 0, u, 0, u, kch, ti, tj});
+    CUDA_TRY(cudaMalloc(&d_split, split.size() * sizeof(OzakiSplitItem)), B200_ERROR_CUDA_MALLOC);
+    CUDA_TRY(cudaMalloc(&d_items, items.size() * sizeof(OzakiItem)), B200_ERROR_CUDA_MALLOC);
+    CUDA_TRY(cudaMemcpy(d_split, split.data(), split.size() * sizeof(OzakiSplitItem), cudaMemcpyHostToDevice), B200_ERROR_CUDA_MEMCPY);
+    CUDA_TRY(cudaMemcpy(d_items, items.data(), items.size() * sizeof(OzakiItem), cudaMemcpyHostToDevice), B200_ERROR_CUDA_MEMCPY);
+    CUDA_TRY(cudaFuncSetAttribute(k_schur_ozaki, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM), B200_ERROR_NOT_AVAILABLE);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0), cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    k_ozaki_split<<<dim3((nta * OZ_BM + 127) / 128, 2), 128>>>(d_split, d_ab, d_tiles, d_sc);
+    k_schur_ozaki<<<std::min((int)items.size(), 148), 128, OZ_SMEM>>>(d_items, (int)items.size(), d_tiles, d_sc, d_c);
+    cudaEventRecord(e1);
+    cudaError_t err = cudaDeviceSynchronize();
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms_out) *ms_out = ms;
+    if (err == cudaSuccess) err = cudaMemcpy(c, d_c, (size_t)u * u * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaEventDestroy(e0), cudaEventDestroy(e1);
+    cudaFree(d_ab), cudaFree(d_c), cudaFree(d_sc), cudaFree(d_tiles), cudaFree(d_split), cudaFree(d_items);
+    if (err != cudaSuccess) {
+        fprintf(stderr, "solver_b200_ozaki_gemm: %s\n", cudaGetErrorString(err));
+        return B200_ERROR_NUM_FACTORIZATION + 1;
+    }
     return B200_SUCCESSFUL_EXIT;
 }
 

@@ -269,3 +269,27 @@ def test_two_large_handles_solve_concurrently():
     [t.start() for t in ts]
     [t.join() for t in ts]
     assert not errors, errors
+
+
+# ---- solve_matrix_market driver: the reference's StatsLinSol JSON schema -----------------------------------------------
+def test_solve_matrix_market_emits_the_reference_schema():
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "solve_matrix_market.py"), helpers.mm_path("bfwb62.mtx"), "-r", "2", "-d"],
+                         capture_output=True, text=True, check=True).stdout
+    doc = json.loads(out)
+    # the sections and fields of stats_lin_sol.rs:14-115
+    assert set(doc) >= {"main", "matrix", "requests", "output", "determinant", "verify", "time_human", "time_nanoseconds", "mumps_stats"}
+    assert doc["main"]["solver"] == "B200" and doc["main"]["out_of_memory"] is False
+    assert doc["matrix"] == {"name": "bfwb62", "nrow": 62, "ncol": 62, "nnz": 202, "nnz_actual": 202, "complex": False, "symmetric": "YesLower"}
+    assert set(doc["output"]) == {"effective_ordering", "effective_scaling", "effective_matching", "effective_pivoting",
+                                  "effective_mumps_num_threads", "openmp_num_threads", "umfpack_strategy", "umfpack_rcond_estimate"}
+    assert 0.0 < doc["output"]["umfpack_rcond_estimate"] <= 1.0
+    assert doc["verify"]["relative_error"] <= 1e-14  # README run of the reference: 5.55e-16 (russell_sparse/README.md:266-271)
+    tn = doc["time_nanoseconds"]
+    assert len(tn["total_ifs_array"]) == 2 and tn["total_ifs"] == sum(tn["total_ifs_array"]) // 2
+    assert doc["determinant"]["base"] == 10.0 and doc["determinant"]["mantissa_real"] != 0.0

@@ -27,6 +27,12 @@ def _worker(rank, world, port, nsys, n, out_dir):
         # stub "solver": system i is diag(i+2) x = ones  ->  x = 1/(i+2)
         xs = torch.stack([torch.full((n,), 1.0 / (i + 2), dtype=torch.float64) for i in mine]) if mine else torch.zeros((0, n), dtype=torch.float64)
         allx = batch.gather_solutions(xs, nsys, world, rank)
+        g = batch.SolutionGatherer(nsys, world, rank, n)  # the preallocated path bench.py uses
+        for rep in range(2):  # buffers are reused from step to step
+            g.block.zero_()
+            if mine:
+                g.block[: len(mine)] = xs
+            assert torch.equal(g.gather(), allx)
         tmax = batch.max_over_ranks(10.0 + rank, world)
         np.save(os.path.join(out_dir, "x_%d.npy" % rank), allx.numpy())
         np.save(os.path.join(out_dir, "t_%d.npy" % rank), np.array([tmax]))
@@ -46,6 +52,9 @@ def test_shard_is_round_robin_and_complete():
 def test_gather_world_1():
     x = torch.arange(6, dtype=torch.float64).reshape(2, 3)
     assert torch.equal(batch.gather_solutions(x, 2, 1, 0), x)
+    g = batch.SolutionGatherer(2, 1, 0, 3)
+    g.block[:2] = x
+    assert torch.equal(g.gather(), x)
     assert batch.max_over_ranks(3.5, 1) == 3.5
 
 
