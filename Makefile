@@ -14,11 +14,11 @@ $(LIB): $(OBJ)
 	mkdir -p russell_b200/lib
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -cudart static -lpthread
 
-build/solver_b200.o: $(CSRC)/solver_b200.cu $(CSRC)/kernels.cuh $(CSRC)/sweep_top.cuh $(CSRC)/plan.hpp include/solver_b200.h
+build/solver_b200.o: $(CSRC)/solver_b200.cu $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.hpp) include/solver_b200.h
 	mkdir -p build
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> build/ptxas_solver_b200.log || (cat build/ptxas_solver_b200.log; false)
 
-build/complex_b200.o: $(CSRC)/complex_b200.cu include/solver_b200.h
+build/complex_b200.o: $(CSRC)/complex_b200.cu $(wildcard $(CSRC)/*.hpp) include/solver_b200.h
 	mkdir -p build
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 

@@ -73,6 +73,9 @@ struct LevelLists {
     int inv_split = -1;         // first level of the "narrow" top of the tree (few fronts per level); -1: no overlap
     std::vector<size_t> fused_smem; // per (level, class): dynamic shared memory of the fused launch
     std::vector<size_t> asm_smem;   // per level: largest tile (bytes) of k_assemble_tile
+    // schur_variant 2: fronts with u >= ozaki_min_u take the tcgen05 kernel (ozaki_tc.cuh)
+    std::vector<int> oz_split_ptr, oz_item_ptr, oz_rows_max; // nlevels+1 / nlevels+1 / nlevels
+    size_t oz_tile_bytes = 0, oz_scales = 0;                 // arena sizes (largest level)
 };
 
 struct InterfaceB200 {
@@ -84,7 +87,12 @@ struct InterfaceB200 {
     // options
     int opt_panel_width = 64, opt_nd_leaf = 32; // (nd_leaf: measured at config 2 -- 96: 8.68 ms, 48: 8.46, 32: 8.27, 24: 8.29, 12: 8.20 ms per factorization)
     int use_graph = 1;
-    int schur_variant = 1; // 0 = FMA, 1 = DMMA
+    int schur_variant = 1; // 0 = FMA, 1 = DMMA (mma.sync f64), 2 = DMMA + tcgen05 int8 Ozaki kernel for fronts with u >= ozaki_min_u
+    int ozaki_min_u = 1024;
+    OzakiSplitItem* d_oz_split = nullptr;
+    OzakiItem* d_oz_items = nullptr;
+    signed char* d_oz_tiles = nullptr;
+    double* d_oz_scales = nullptr;
     int relax_small = -1;                                // supernode amalgamation knobs of the host analysis (plan.hpp); < 0: defaults
     double relax_z1 = -1.0, relax_z2 = -1.0, relax_z3 = -1.0;
     int schur_occ3_min = 1 << 30; // launches with at least this many Schur tiles use the 3-CTAs-per-SM build of k_schur_dmma
@@ -231,6 +239,7 @@ void release_device(InterfaceB200* s) {
     if (s->g_sweep) cudaGraphExecDestroy(s->g_sweep), s->g_sweep = nullptr;
     dfree(s->d_nodes), dfree(s->d_rows), dfree(s->d_rel), dfree(s->d_child_idx), dfree(s->d_fact_nodes), dfree(s->d_solve_nodes), dfree(s->d_inv_nodes);
     dfree(s->d_asm), dfree(s->d_panel), dfree(s->d_schur);
+    dfree(s->d_oz_split), dfree(s->d_oz_items), dfree(s->d_oz_tiles), dfree(s->d_oz_scales);
     dfree(s->d_trace);
     dfree(s->d_subtrees), dfree(s->d_st_tgt), dfree(s->d_st_pu);
     dfree(s->d_node_slot), dfree(s->d_bdone);
@@ -264,7 +273,7 @@ size_t smem_fused(int f, int p) { return ((size_t)(f | 1) * f) * sizeof(double) 
 
 void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::vector<PanelItem>& panel_items,
                       std::vector<SchurItem>& schur_items, std::vector<int>& fact_nodes, std::vector<int>& solve_nodes,
-                      std::vector<int>& asm_ranges) {
+                      std::vector<int>& asm_ranges, std::vector<OzakiSplitItem>& oz_split, std::vector<OzakiItem>& oz_items) {
     const Plan& P = s->plan;
     LevelLists& lv = s->lv;
     lv.asm_ptr.assign(P.nlevels + 1, 0);
@@ -277,6 +286,9 @@ void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::ve
     lv.solve_pmax.assign(P.nlevels, 1);
     lv.fused_smem.assign((size_t)P.nlevels * NFC, 0);
     lv.asm_smem.assign(P.nlevels, 0);
+    lv.oz_split_ptr.assign(P.nlevels + 1, 0), lv.oz_item_ptr.assign(P.nlevels + 1, 0), lv.oz_rows_max.assign(P.nlevels, 0);
+    lv.oz_tile_bytes = 0, lv.oz_scales = 0;
+    auto ozaki = [&](int v) { return s->schur_variant == 2 && P.u[v] >= s->ozaki_min_u; };
     auto fclass = [&](int f) {
         if (!s->use_fused || f > s->fused_maxf) return NFC;
         for (int c = 0; c < NFC; c++)
@@ -286,9 +298,10 @@ void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::ve
     // a front is fed by the fused Schur epilogue of its single child when it is a later panel of a split supernode
     // (update set of the child == this front, identity relative indices) and both run on the multi-kernel path
     auto chain_fused = [&](int v) {
-        if (!s->fuse_chain || s->schur_variant != 1) return false;
+        if (!s->fuse_chain || s->schur_variant < 1) return false;
         if (P.child_ptr[v + 1] - P.child_ptr[v] != 1) return false;
         const int c = P.child_idx[P.child_ptr[v]];
+        if (ozaki(c)) return false; // the tcgen05 kernel updates its own contribution block; the parent assembles it
         if (P.u[c] != P.p[v] + P.u[v]) return false;
         if (fclass(P.p[v] + P.u[v]) != NFC || fclass(P.p[c] + P.u[c]) != NFC) return false;
         const int* rel = &P.rel[P.rows_ptr[c]];
@@ -302,6 +315,7 @@ void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::ve
         return NSC - 1;
     };
     for (int l = 0; l < P.nlevels; l++) {
+        size_t lvl_tiles = 0, lvl_scales = 0; // the sliced operands live for one level only
         for (int c = 0; c <= NFC; c++) {
             for (int e = P.level_ptr[l]; e < P.level_ptr[l + 1]; e++) {
                 const int v = P.level_nodes[e];
@@ -367,16 +381,33 @@ void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::ve
                 const int TR = (s->panel_variant >= 1) ? B200_PW_ROWS : B200_TR;
                 for (int r0 = 0; r0 < u; r0 += TR) panel_items.push_back({v, r0, std::min(TR, u - r0), 0});
                 for (int r0 = 0; r0 < u; r0 += TR) panel_items.push_back({v, r0, std::min(TR, u - r0), 1});
-                int nt = (u + B200_TS - 1) / B200_TS;
-                const int par = P.parent[v];
-                const int fuse_into = (par >= 0 && chain_fused(par)) ? par : -1;
-                for (int tj = 0; tj < nt; tj++)
-                    for (int ti = 0; ti < nt; ti++) schur_items.push_back({v, ti, tj, fuse_into});
+                if (ozaki(v) && fclass(f) == NFC) {
+                    // operands split into int8 slices (tile-canonical layout), then one item per 128 x 64 tile of C
+                    const int kch = (p + OZ_KC - 1) / OZ_KC;
+                    const int nta = (u + OZ_BM - 1) / OZ_BM, ntb = (u + OZ_BN - 1) / OZ_BN;
+                    const long long a_t = (long long)lvl_tiles, b_t = a_t + (long long)nta * kch * OZ_S * OZ_A_BYTES;
+                    lvl_tiles = (size_t)b_t + (size_t)ntb * kch * OZ_S * OZ_B_BYTES;
+                    const long long a_s = (long long)lvl_scales, b_s = a_s + u;
+                    lvl_scales += 2 * (size_t)u;
+                    oz_split.push_back({P.Loff[v] + p, a_t, a_s, u, p, (int)f, OZ_BM});
+                    oz_split.push_back({P.Uoff[v], b_t, b_s, u, p, u, OZ_BN});
+                    lv.oz_rows_max[l] = std::max(lv.oz_rows_max[l], nta * OZ_BM);
+                    for (int tj = 0; tj < ntb; tj++)
+                        for (int ti = 0; ti < nta; ti++) oz_items.push_back({a_t, b_t, a_s, b_s, P.Coff[v], u, kch, ti, tj});
+                } else {
+                    int nt = (u + B200_TS - 1) / B200_TS;
+                    const int par = P.parent[v];
+                    const int fuse_into = (par >= 0 && chain_fused(par)) ? par : -1;
+                    for (int tj = 0; tj < nt; tj++)
+                        for (int ti = 0; ti < nt; ti++) schur_items.push_back({v, ti, tj, fuse_into});
+                }
             }
         }
         lv.asm_ptr[l + 1] = (int)asm_items.size();
         lv.panel_ptr[l + 1] = (int)panel_items.size();
         lv.schur_ptr[l + 1] = (int)schur_items.size();
+        lv.oz_split_ptr[l + 1] = (int)oz_split.size(), lv.oz_item_ptr[l + 1] = (int)oz_items.size();
+        lv.oz_tile_bytes = std::max(lv.oz_tile_bytes, lvl_tiles), lv.oz_scales = std::max(lv.oz_scales, lvl_scales);
         // look-ahead order: tiles of chain links in tile row 0 / tile column 0 (they become the parent's pivot block and
         // panels) first; everything else (the parent's contribution block, tiles of non-chain fronts) afterwards
         auto first = schur_items.begin() + lv.schur_ptr[l];
@@ -489,13 +520,21 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
                 k_panel<<<np, 256, smem_panel(W), s->stream>>>(s->d_panel + lv.panel_ptr[l], s->d_nodes, s->d_fac, s->d_lperm);
             cnt++;
         }
+        const int noz = lv.oz_item_ptr[l + 1] - lv.oz_item_ptr[l];
+        if (noz > 0) { // tcgen05 path: split the two panels into int8 slices, then the Schur tiles on the tensor cores
+            const int nsp = lv.oz_split_ptr[l + 1] - lv.oz_split_ptr[l];
+            k_ozaki_split<<<dim3((lv.oz_rows_max[l] + 127) / 128, nsp), 128, 0, s->stream>>>(s->d_oz_split + lv.oz_split_ptr[l], s->d_fac, s->d_oz_tiles,
+                                                                                          s->d_oz_scales);
+            k_schur_ozaki<<<std::min(noz, 148), 128, OZ_SMEM, s->stream>>>(s->d_oz_items + lv.oz_item_ptr[l], noz, s->d_oz_tiles, s->d_oz_scales, s->d_cb);
+            cnt += 2;
+        }
         int nsch = lv.schur_ptr[l + 1] - lv.schur_ptr[l];
         if (nsch > 0) {
             // every Schur tile of this level reads contribution blocks completed by the previous level's side launch
             if (pending_rest) cudaStreamWaitEvent(s->stream, s->ev_rest, 0), pending_rest = false;
             const int ncrit = lv.schur_crit[l];
-            const bool la = s->lookahead && s->schur_variant == 1 && ncrit > 0 && ncrit < nsch;
-            if (s->schur_variant == 1) {
+            const bool la = s->lookahead && s->schur_variant >= 1 && ncrit > 0 && ncrit < nsch;
+            if (s->schur_variant >= 1) {
                 if (la) { // fork before the critical tiles: the side launch only needs this level's panels
                     cudaEventRecord(s->ev_la, s->stream);
                     cudaStreamWaitEvent(s->side, s->ev_la, 0);
@@ -817,6 +856,7 @@ int32_t solver_b200_set_option(struct InterfaceB200* s, const char* key, double 
     else if (k == "nd_leaf") s->opt_nd_leaf = std::max(4, (int)value);
     else if (k == "use_graph") s->use_graph = value != 0.0;
     else if (k == "schur_variant") s->schur_variant = (int)value;
+    else if (k == "ozaki_min_u") s->ozaki_min_u = std::max(1, (int)value);
     else if (k == "panel_variant") s->panel_variant = (int)value;
     else if (k == "panel_row_max") s->panel_row_max = (int)value;
     else if (k == "use_leaf_reg") s->use_leaf_reg = value != 0.0;
@@ -980,7 +1020,9 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     std::vector<PanelItem> panel_items;
     std::vector<SchurItem> schur_items;
     std::vector<int> fact_nodes, solve_nodes, asm_ranges, big_ranges;
-    build_work_lists(s, asm_items, panel_items, schur_items, fact_nodes, solve_nodes, asm_ranges);
+    std::vector<OzakiSplitItem> oz_split;
+    std::vector<OzakiItem> oz_items;
+    build_work_lists(s, asm_items, panel_items, schur_items, fact_nodes, solve_nodes, asm_ranges, oz_split, oz_items);
     // big solve class: row slices of the update set; a node with no update rows still needs one (head-only) item
     std::vector<SolveItem> big_items;
     std::vector<int> big_slot;
@@ -1220,6 +1262,8 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     UP(d_asm, asm_items);
     UP(d_panel, panel_items);
     UP(d_schur, schur_items);
+    UP(d_oz_split, oz_split);
+    UP(d_oz_items, oz_items);
     UP(d_big_items, big_items);
     UP(d_big_slot, big_slot);
     UP(d_asm_ranges, asm_ranges);
@@ -1262,6 +1306,11 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     DM(d_fac, P.fac_size, double);
     DM(d_cb, P.cb_size, double);
     DM(d_dinv, P.dinv_size, double);
+    if (!oz_items.empty()) {
+        DM(d_oz_tiles, s->lv.oz_tile_bytes, signed char);
+        DM(d_oz_scales, s->lv.oz_scales, double);
+        CUDA_TRY(cudaFuncSetAttribute(k_schur_ozaki, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM), B200_ERROR_NOT_AVAILABLE);
+    }
     DM(d_upiv, P.n, double);
     DM(d_lperm, P.n, int);
     DM(d_counters, 4, int);
