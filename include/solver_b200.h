@@ -150,7 +150,8 @@ int32_t solver_b200_determinant(struct InterfaceB200 *solver, double *coefficien
 #define B200_STAT_EFFECTIVE_SCALING 25    /* 0 = none, 1 = row/column scaling from the max-product matching (UMFPACK_SCALE, interface_umfpack.c:181) */
 #define B200_STAT_RCOND 26                /* last solver_b200_rcond value, -1 when not computed for the current factors */
 #define B200_STAT_T_INITIALIZE_HOST_S 27  /* wall time of the host analysis (matching + ordering + symbolic + plan) */
-#define B200_STAT_COUNT 28
+#define B200_STAT_PLAN_CACHE_HIT 28        /* 1: the plan was served from the process-wide cache of analysed patterns */
+#define B200_STAT_COUNT 29
 int32_t solver_b200_get_stats(struct InterfaceB200 *solver, double *out, int32_t n_out);
 
 /* tuning knobs, to be set before initialize ("ir_tol", "refinement_nstep" and "strict_residual" also later).  Host analysis: "panel_width",

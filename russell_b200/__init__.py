@@ -387,7 +387,7 @@ class SolverB200:
                   "t_symbolic_s", "n_perturbed", "last_rel_residual", "last_refine_steps", "ms_factorize_device",
                   "ms_solve_device", "ms_sptrsv_device", "ms_spmv_device", "launches_factorize", "launches_solve",
                   "sptrsv_bytes", "spmv_bytes", "matched", "t_match_s", "last_backward_error", "effective_ordering",
-                  "effective_scaling", "rcond", "t_initialize_host_s"]
+                  "effective_scaling", "rcond", "t_initialize_host_s", "plan_cache_hit"]
 
     def __init__(self, coo_boundary=True):
         """coo_boundary=True: the triplet structure is analysed once (solver_b200_initialize_coo) and every later

@@ -31,6 +31,8 @@
 #include <atomic>
 #include <chrono>
 #include <thread>
+#include <memory>
+#include <mutex>
 
 using namespace b200;
 
@@ -51,7 +53,6 @@ static const int FC_THREADS[NFC] = {32, 64, 64, 128, 256, 256};
 // pivot-count classes of the batched inverse post-pass
 static const int NIC = 3;
 static const int IC_MAXP[NIC] = {16, 32, B200_MAXP};
-static const int IC_THREADS[NIC] = {32, 64, 256};
 // solve classes: CTA size by front order
 static const int NSC = 3;
 static const int SC_MAXF[NSC] = {32, 256, 1 << 30};
@@ -61,7 +62,6 @@ static const int SC_MAXP[NSC] = {32, B200_MAXP, B200_MAXP};
 struct LevelLists {
     // offsets (nlevels+1) into the concatenated device item arrays (big fronts only)
     std::vector<int> asm_ptr, panel_ptr, schur_ptr;
-    std::vector<int> schur_crit; // per level: the first schur_crit[l] Schur tiles feed the NEXT level's pivot block and panels
     // fact_ptr[l*(NFC+1)+c .. +1]: nodes of level l and factorization class c inside d_fact_nodes (class NFC = big)
     std::vector<int> fact_ptr;
     // solve_ptr[l*NSC+c .. +1] inside d_solve_nodes
@@ -69,8 +69,6 @@ struct LevelLists {
     std::vector<int> solve_threads, solve_pmax; // per level: block size and largest pivot count of the small launch
     std::vector<int> big_ptr; // nlevels+1: slices of the big solve class inside d_big_items
     std::vector<int> inv_ptr; // NIC+1: fronts by pivot-count class inside d_inv_nodes
-    std::vector<int> inv_early; // NIC: per class, how many fronts (the first ones of the class) lie below level inv_split
-    int inv_split = -1;         // first level of the "narrow" top of the tree (few fronts per level); -1: no overlap
     std::vector<size_t> fused_smem; // per (level, class): dynamic shared memory of the fused launch
     std::vector<size_t> asm_smem;   // per level: largest tile (bytes) of k_assemble_tile
     // schur_variant 2: fronts with u >= ozaki_min_u take the tcgen05 kernel (ozaki_tc.cuh)
@@ -95,10 +93,7 @@ struct InterfaceB200 {
     double* d_oz_scales = nullptr;
     int relax_small = -1;                                // supernode amalgamation knobs of the host analysis (plan.hpp); < 0: defaults
     double relax_z1 = -1.0, relax_z2 = -1.0, relax_z3 = -1.0;
-    int schur_occ3_min = 1 << 30; // launches with at least this many Schur tiles use the 3-CTAs-per-SM build of k_schur_dmma
     int asm_variant = 1;     // 0 = k_assemble (read-modify-write in global memory), 1 = k_assemble_tile (tile in shared memory)
-    int small_reg_maxf = 0;  // fronts WITH children of order <= this (16 or 32) may use the register kernel too; measured slower than
-                             // the shared-memory kernel (7.50 -> 7.58 / 7.67 ms per factorization): off
     int use_leaf_reg = 1;    // leaf fronts of order <= 32: k_leaf_reg (one warp per front, registers only)
     int panel_row_max = 160; // launches of at most this many 128-row panel items use k_panel_row (one warp per four rows)
     int panel_variant = 1; // 0 = k_panel (32-row tiles, barrier per column), 1 = k_panel_warp (thread per row, 128-row items)
@@ -194,21 +189,17 @@ struct InterfaceB200 {
 
     cudaGraphExec_t g_fact = nullptr, g_sweep = nullptr;
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    cudaStream_t side = nullptr;          // low-priority side stream: pivot-block inverses of the wide bottom of the tree
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr; //   run there, under the latency-bound chain of top-of-tree launches
+    cudaStream_t side = nullptr;          // side stream: the factor arena is cleared there, under the H2D copy of the new values
     cudaEvent_t ev_clr0 = nullptr, ev_clr1 = nullptr; // fork / join of the factor-arena clear that runs under the H2D copy
-    cudaEvent_t ev_la = nullptr, ev_rest = nullptr;   // look-ahead fork / join
-    int overlap_invert = 0;
     int fused_variant = 2;  // 0 = shared-memory LU (k_front_fused), 1 = register-resident (k_front_fused_w8) for f <= 64,
                             // 2 = register-resident only for launches of at most fused_w8_max fronts (measured crossover)
     int fused_w8_max = 2000;
-    int invert_variant = 1; // 0 = rank-1 sweeps with a barrier per step (k_invert), 1 = one thread per column (k_invert_col)
-    int lookahead = 0; // Schur tiles that do not feed the next level's pivot block / panels run on the side stream
 
     // stats
     int n_perturbed = 0;
     double rcond = -1.0;      // last value computed by solver_b200_rcond (-1: not computed for these factors)
     double t_init_host = 0.0; // wall time of the host analysis inside initialize
+    int plan_cache_hit = 0;   // 1: this handle's plan came from the process-wide plan cache
     double last_rel_residual = -1.0, last_backward_error = -1.0;
     int last_refine_steps = 0;
     float ms_factorize = 0, ms_solve = 0, ms_sptrsv = 0, ms_spmv = 0;
@@ -217,6 +208,53 @@ struct InterfaceB200 {
 };
 
 namespace {
+
+// ---- plan cache: identical sparsity patterns are analysed once per process ("symbolic analysis shared on the
+// host when patterns are identical" -- a sweep of LinSolver::new over one mesh, the handles of a parameter study, one handle
+// per GPU driven from one process).  Key = two independent 64-bit hashes of (n, row pointers, column indices) + the analysis
+// options; only plans WITHOUT matching / scaling are shared (those depend on the pattern alone), and a request is served from
+// the cache only if its own values would not trigger the matching either.  B200_PLAN_CACHE=0 turns it off.
+struct PlanCacheEntry {
+    uint64_t h1, h2;
+    int n, nnz;
+    bool sym_lower;
+    AnalyzeOptions opt;
+    std::shared_ptr<const Plan> plan;
+};
+std::mutex g_plan_mu;
+std::vector<PlanCacheEntry> g_plan_cache; // most recent last, at most 3 entries
+
+void hash_pattern(int n, const int* rp, const int* ci, uint64_t& h1, uint64_t& h2) {
+    uint64_t a = 0x9e3779b97f4a7c15ull ^ (uint64_t)n, b = 0xc2b2ae3d27d4eb4full + (uint64_t)n;
+    auto mix = [&](uint64_t v) {
+        a = (a ^ v) * 0xff51afd7ed558ccdull, a ^= a >> 29;
+        b = (b + v) * 0xc4ceb9fe1a85ec53ull, b ^= b >> 31;
+    };
+    for (int i = 0; i <= n; i++) mix((uint32_t)rp[i]);
+    const int nnz = rp[n];
+    int k = 0;
+    for (; k + 1 < nnz; k += 2) mix(((uint64_t)(uint32_t)ci[k] << 32) | (uint32_t)ci[k + 1]);
+    if (k < nnz) mix((uint32_t)ci[k]);
+    h1 = a, h2 = b;
+}
+bool same_options(const AnalyzeOptions& x, const AnalyzeOptions& y) {
+    return x.ordering == y.ordering && x.panel_width == y.panel_width && x.nd_leaf == y.nd_leaf && x.relax_small == y.relax_small &&
+           x.relax_z1 == y.relax_z1 && x.relax_z2 == y.relax_z2 && x.relax_z3 == y.relax_z3 && x.st_enable == y.st_enable &&
+           x.st_maxf == y.st_maxf && x.st_pmax == y.st_pmax && x.st_budget == y.st_budget && x.st_maxcols == y.st_maxcols &&
+           x.st_min_count == y.st_min_count && x.cb_reuse == y.cb_reuse;
+}
+// would these values make the analysis run the matching?  (plan.hpp: matching = 1 always, 2 = only if a diagonal entry is
+// structurally or numerically zero)
+bool values_need_matching(int matching, int n, const int* rp, const int* ci, const double* vals) {
+    if (matching == 0) return false;
+    if (matching == 1) return true;
+    for (int i = 0; i < n; i++) {
+        bool ok = false;
+        for (int k = rp[i]; k < rp[i + 1] && !ok; k++) ok = ci[k] == i && vals[k] != 0.0;
+        if (!ok) return true;
+    }
+    return false;
+}
 
 template <typename T>
 cudaError_t upload(T** dptr, const std::vector<T>& h) {
@@ -279,7 +317,6 @@ void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::ve
     lv.asm_ptr.assign(P.nlevels + 1, 0);
     lv.panel_ptr.assign(P.nlevels + 1, 0);
     lv.schur_ptr.assign(P.nlevels + 1, 0);
-    lv.schur_crit.assign(P.nlevels, 0);
     lv.fact_ptr.assign((size_t)P.nlevels * (NFC + 1) + 1, 0);
     lv.solve_ptr.assign((size_t)P.nlevels * NSC + 1, 0);
     lv.solve_threads.assign(P.nlevels, 32);
@@ -408,11 +445,6 @@ void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::ve
         lv.schur_ptr[l + 1] = (int)schur_items.size();
         lv.oz_split_ptr[l + 1] = (int)oz_split.size(), lv.oz_item_ptr[l + 1] = (int)oz_items.size();
         lv.oz_tile_bytes = std::max(lv.oz_tile_bytes, lvl_tiles), lv.oz_scales = std::max(lv.oz_scales, lvl_scales);
-        // look-ahead order: tiles of chain links in tile row 0 / tile column 0 (they become the parent's pivot block and
-        // panels) first; everything else (the parent's contribution block, tiles of non-chain fronts) afterwards
-        auto first = schur_items.begin() + lv.schur_ptr[l];
-        auto mid = std::stable_partition(first, schur_items.end(), [](const SchurItem& t) { return t.parent >= 0 && (t.ti == 0 || t.tj == 0); });
-        lv.schur_crit[l] = (int)(mid - first);
     }
 }
 
@@ -429,37 +461,13 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
     const LevelLists& lv = s->lv;
     const int W = s->opt_panel_width;
     int cnt = 0;
-    bool forked = false, pending_rest = false;
     for (int l = 0; l < P.nlevels; l++) {
-        if (l == lv.inv_split) { // fork: inverses of all fronts below this level, on the low-priority side stream
-            cudaEventRecord(s->ev_fork, s->stream);
-            cudaStreamWaitEvent(s->side, s->ev_fork, 0);
-            for (int c = 0; c < NIC; c++)
-                if (lv.inv_early[c] > 0) {
-                    // a few CTAs per SM only: the chain kernels of the main stream must always find free slots
-                    if (s->invert_variant == 1)
-                        k_invert_col<<<std::min(lv.inv_early[c], 148 * 4), 2 * IC_MAXP[c], smem_invert(IC_MAXP[c]), s->side>>>(
-                            s->d_inv_nodes + lv.inv_ptr[c], s->d_nodes, s->d_fac, s->d_dinv, IC_MAXP[c], lv.inv_early[c]);
-                    else
-                        k_invert<<<std::min(lv.inv_early[c], 148 * 4), IC_THREADS[c], smem_invert(IC_MAXP[c]), s->side>>>(
-                            s->d_inv_nodes + lv.inv_ptr[c], s->d_nodes, s->d_fac, s->d_dinv, IC_MAXP[c], lv.inv_early[c]);
-                    cnt++;
-                }
-            cudaEventRecord(s->ev_join, s->side);
-            forked = true;
-        }
         const int* fp = &lv.fact_ptr[(size_t)l * (NFC + 1)];
-        // fused fronts and the assembly kernel read their children's contribution blocks: wait for the side launch.
-        // A level made of chain links only goes straight to its pivot blocks (their inputs came from the critical tiles).
-        if (pending_rest && (fp[NFC] - fp[0] > 0 || lv.asm_ptr[l + 1] - lv.asm_ptr[l] > 0))
-            cudaStreamWaitEvent(s->stream, s->ev_rest, 0), pending_rest = false;
         for (int c = 0; c < NFC; c++) {
             int nn = fp[c + 1] - fp[c];
             if (nn > 0) {
-                // register-resident LU (one warp per 8 front columns): wins when the launch is latency bound (few fronts),
-                // loses to the leaner shared-memory kernel when tens of thousands of fronts compete for thread slots
-                if (FC_MAXF[c] <= 32 && ((l == 0 && s->use_leaf_reg) || (l > 0 && FC_MAXF[c] <= s->small_reg_maxf))) {
-                    // leaves (level 0) and small fronts with children: the whole front in one warp's registers
+                if (FC_MAXF[c] <= 32 && l == 0 && s->use_leaf_reg) {
+                    // leaves: the whole front in one warp's registers
                     const int gridw = (nn + B200_LEAF_WARPS - 1) / B200_LEAF_WARPS;
                     if (FC_MAXF[c] <= 16)
                         k_small_reg<16><<<gridw, 32 * B200_LEAF_WARPS, 0, s->stream>>>(s->d_fact_nodes + fp[c], nn, s->d_nodes, s->d_child_idx,
@@ -470,6 +478,8 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
                                                                                       s->d_rel, s->d_fac, s->d_cb, s->d_lperm, s->d_upiv,
                                                                                       s->d_amax, s->pivot_eps, s->d_counters);
                 }
+                // register-resident LU (one warp per 8 front columns): wins when the launch is latency bound (few fronts),
+                // loses to the leaner shared-memory kernel when tens of thousands of fronts compete for thread slots
                 else if (FC_MAXF[c] <= 64 && (s->fused_variant == 1 || (s->fused_variant == 2 && nn <= s->fused_w8_max)))
                     k_front_fused_w8<<<nn, 32 * ((FC_MAXF[c] + 7) / 8), lv.fused_smem[(size_t)l * NFC + c], s->stream>>>(
                         s->d_fact_nodes + fp[c], s->d_nodes, s->d_child_idx, s->d_rel, s->d_fac, s->d_cb, s->d_lperm,
@@ -495,24 +505,13 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
         if (s->diag_variant == 4)
             k_diag_w8<<<nbig, 256, 0, s->stream>>>(s->d_fact_nodes + fp[NFC], s->d_nodes, s->d_fac, s->d_lperm, s->d_upiv, s->d_amax,
                                                    s->pivot_eps, s->d_counters);
-        else if (s->diag_variant == 3)
-            k_diag_reg2<<<nbig, 512, 0, s->stream>>>(s->d_fact_nodes + fp[NFC], s->d_nodes, s->d_fac, s->d_lperm, s->d_upiv, s->d_amax,
-                                                     s->pivot_eps, s->d_counters);
-        else if (s->diag_variant == 2)
-            k_diag_blk<<<nbig, 256, 0, s->stream>>>(s->d_fact_nodes + fp[NFC], s->d_nodes, s->d_fac, s->d_lperm, s->d_upiv, s->d_amax,
-                                                    s->pivot_eps, s->d_counters);
-        else if (s->diag_variant == 1)
-            k_diag_reg<<<nbig, 512, 0, s->stream>>>(s->d_fact_nodes + fp[NFC], s->d_nodes, s->d_fac, s->d_lperm, s->d_upiv, s->d_amax,
-                                                    s->pivot_eps, s->d_counters);
         else
             k_diag<<<nbig, 512, smem_diag(W), s->stream>>>(s->d_fact_nodes + fp[NFC], s->d_nodes, s->d_fac,
                                                            s->d_lperm, s->d_upiv, s->d_amax, s->pivot_eps, s->d_counters);
         cnt++;
         int np = lv.panel_ptr[l + 1] - lv.panel_ptr[l];
         if (np > 0) {
-            if (s->panel_variant == 2)
-                k_panel_mma<<<np, 128, B200_PM_SMEM, s->stream>>>(s->d_panel + lv.panel_ptr[l], s->d_nodes, s->d_fac, s->d_lperm);
-            else if (s->panel_variant == 1 && np <= s->panel_row_max) // few rows: the launch is latency bound
+            if (s->panel_variant == 1 && np <= s->panel_row_max) // few rows: the launch is latency bound
                 k_panel_row<<<np * 4, 256, 0, s->stream>>>(s->d_panel + lv.panel_ptr[l], s->d_nodes, s->d_fac, s->d_lperm);
             else if (s->panel_variant == 1)
                 k_panel_warp<<<np, 128, B200_PW_SMEM, s->stream>>>(s->d_panel + lv.panel_ptr[l], s->d_nodes, s->d_fac, s->d_lperm);
@@ -530,45 +529,20 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
         }
         int nsch = lv.schur_ptr[l + 1] - lv.schur_ptr[l];
         if (nsch > 0) {
-            // every Schur tile of this level reads contribution blocks completed by the previous level's side launch
-            if (pending_rest) cudaStreamWaitEvent(s->stream, s->ev_rest, 0), pending_rest = false;
-            const int ncrit = lv.schur_crit[l];
-            const bool la = s->lookahead && s->schur_variant >= 1 && ncrit > 0 && ncrit < nsch;
-            if (s->schur_variant >= 1) {
-                if (la) { // fork before the critical tiles: the side launch only needs this level's panels
-                    cudaEventRecord(s->ev_la, s->stream);
-                    cudaStreamWaitEvent(s->side, s->ev_la, 0);
-                }
-                if ((la ? ncrit : nsch) >= s->schur_occ3_min) // many tiles: three CTAs per SM (80 registers) beat two (128 registers)
-                    k_schur_dmma<3><<<la ? ncrit : nsch, 256, smem_schur_dmma(), s->stream>>>(s->d_schur + lv.schur_ptr[l], s->d_nodes, s->d_fac, s->d_cb);
-                else
-                    k_schur_dmma<2><<<la ? ncrit : nsch, 256, smem_schur_dmma(), s->stream>>>(s->d_schur + lv.schur_ptr[l], s->d_nodes, s->d_fac, s->d_cb);
-                if (la) {
-                    // lookahead == 2: the side launch asks for more shared memory than it needs, so only ONE of its CTAs fits
-                    // on an SM and the next level's pivot-block / panel CTAs always find registers and a slot
-                    k_schur_dmma<2><<<nsch - ncrit, 256, s->lookahead == 2 ? (size_t)120 * 1024 : smem_schur_dmma(), s->side>>>(
-                        s->d_schur + lv.schur_ptr[l] + ncrit, s->d_nodes, s->d_fac, s->d_cb);
-                    cudaEventRecord(s->ev_rest, s->side);
-                    pending_rest = true;
-                    cnt++;
-                }
-            } else
+            if (s->schur_variant >= 1)
+                k_schur_dmma<<<nsch, 256, smem_schur_dmma(), s->stream>>>(s->d_schur + lv.schur_ptr[l], s->d_nodes, s->d_fac, s->d_cb);
+            else
                 k_schur_fma<<<nsch, 256, smem_schur_fma(W), s->stream>>>(s->d_schur + lv.schur_ptr[l], s->d_nodes, s->d_fac, s->d_cb);
             cnt++;
         }
     }
-    if (pending_rest) cudaStreamWaitEvent(s->stream, s->ev_rest, 0), pending_rest = false;
-    if (forked) cudaStreamWaitEvent(s->stream, s->ev_join, 0); // join
+    // explicit inverses of the pivot blocks, all fronts outside the subtree region in one batched launch per size class:
+    // only the solve phase needs them
     for (int c = 0; c < NIC; c++) {
-        const int first = forked ? lv.inv_early[c] : 0;
-        int nn = lv.inv_ptr[c + 1] - lv.inv_ptr[c] - first;
+        int nn = lv.inv_ptr[c + 1] - lv.inv_ptr[c];
         if (nn > 0) {
-            if (s->invert_variant == 1)
-                k_invert_col<<<nn, 2 * IC_MAXP[c], smem_invert(IC_MAXP[c]), s->stream>>>(s->d_inv_nodes + lv.inv_ptr[c] + first, s->d_nodes,
-                                                                                          s->d_fac, s->d_dinv, IC_MAXP[c], nn);
-            else
-                k_invert<<<nn, IC_THREADS[c], smem_invert(IC_MAXP[c]), s->stream>>>(s->d_inv_nodes + lv.inv_ptr[c] + first, s->d_nodes,
-                                                                                     s->d_fac, s->d_dinv, IC_MAXP[c], nn);
+            k_invert_col<<<nn, 2 * IC_MAXP[c], smem_invert(IC_MAXP[c]), s->stream>>>(s->d_inv_nodes + lv.inv_ptr[c], s->d_nodes, s->d_fac, s->d_dinv,
+                                                                                      IC_MAXP[c], nn);
             cnt++;
         }
     }
@@ -767,21 +741,13 @@ static bool create_streams(InterfaceB200* s) {
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     if (cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, hi) != cudaSuccess) return false;
     if (cudaStreamCreateWithPriority(&s->side, cudaStreamNonBlocking, lo) != cudaSuccess) return false;
-    if (cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) != cudaSuccess) return false;
-    if (cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming) != cudaSuccess) return false;
-    if (cudaEventCreateWithFlags(&s->ev_la, cudaEventDisableTiming) != cudaSuccess) return false;
     if (cudaEventCreateWithFlags(&s->ev_clr0, cudaEventDisableTiming) != cudaSuccess) return false;
     if (cudaEventCreateWithFlags(&s->ev_clr1, cudaEventDisableTiming) != cudaSuccess) return false;
-    if (cudaEventCreateWithFlags(&s->ev_rest, cudaEventDisableTiming) != cudaSuccess) return false;
     return true;
 }
 static void destroy_streams(InterfaceB200* s) {
-    if (s->ev_fork) cudaEventDestroy(s->ev_fork), s->ev_fork = nullptr;
     if (s->ev_clr0) cudaEventDestroy(s->ev_clr0), s->ev_clr0 = nullptr;
     if (s->ev_clr1) cudaEventDestroy(s->ev_clr1), s->ev_clr1 = nullptr;
-    if (s->ev_join) cudaEventDestroy(s->ev_join), s->ev_join = nullptr;
-    if (s->ev_la) cudaEventDestroy(s->ev_la), s->ev_la = nullptr;
-    if (s->ev_rest) cudaEventDestroy(s->ev_rest), s->ev_rest = nullptr;
     if (s->side) cudaStreamDestroy(s->side), s->side = nullptr;
     if (s->stream) cudaStreamDestroy(s->stream), s->stream = nullptr;
 }
@@ -816,9 +782,6 @@ struct InterfaceB200* solver_b200_new(void) {
     if ((e = getenv("B200_PANEL_ROW_MAX"))) s->panel_row_max = atoi(e);
     if ((e = getenv("B200_USE_LEAF_REG"))) s->use_leaf_reg = atoi(e);
     if ((e = getenv("B200_ASM_VARIANT"))) s->asm_variant = atoi(e);
-    if ((e = getenv("B200_OVERLAP_INVERT"))) s->overlap_invert = atoi(e);
-    if ((e = getenv("B200_LOOKAHEAD"))) s->lookahead = atoi(e);
-    if ((e = getenv("B200_INVERT_VARIANT"))) s->invert_variant = atoi(e);
     if ((e = getenv("B200_FUSED_VARIANT"))) s->fused_variant = atoi(e);
     if ((e = getenv("B200_USE_FUSED"))) s->use_fused = atoi(e);
     if ((e = getenv("B200_USE_TOP"))) s->use_top = atoi(e);
@@ -860,16 +823,11 @@ int32_t solver_b200_set_option(struct InterfaceB200* s, const char* key, double 
     else if (k == "panel_variant") s->panel_variant = (int)value;
     else if (k == "panel_row_max") s->panel_row_max = (int)value;
     else if (k == "use_leaf_reg") s->use_leaf_reg = value != 0.0;
-    else if (k == "small_reg_maxf") s->small_reg_maxf = (int)value;
     else if (k == "asm_variant") s->asm_variant = (int)value;
-    else if (k == "schur_occ3_min") s->schur_occ3_min = (int)value;
     else if (k == "relax_small") s->relax_small = (int)value;
     else if (k == "relax_z1") s->relax_z1 = value;
     else if (k == "relax_z2") s->relax_z2 = value;
     else if (k == "relax_z3") s->relax_z3 = value;
-    else if (k == "overlap_invert") s->overlap_invert = (int)value;
-    else if (k == "lookahead") s->lookahead = (int)value;
-    else if (k == "invert_variant") s->invert_variant = (int)value;
     else if (k == "fused_variant") s->fused_variant = (int)value;
     else if (k == "fused_w8_max") s->fused_w8_max = (int)value;
     else if (k == "use_fused") s->use_fused = value != 0.0;
@@ -940,7 +898,35 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     else opt.matching = 1;
 
     const auto t_host0 = std::chrono::steady_clock::now();
-    int rc = analyze(ndim, row_pointers, col_indices, values, general_symmetric != 0 || positive_definite != 0, opt, s->plan);
+    const bool want_sym = general_symmetric != 0 || positive_definite != 0;
+    int rc = 0;
+    {
+        const char* pc = getenv("B200_PLAN_CACHE");
+        const bool cache_on = !(pc && atoi(pc) == 0) && ndim >= 4096 && row_pointers[0] == 0 && row_pointers[ndim] > 0;
+        uint64_t h1 = 0, h2 = 0;
+        std::shared_ptr<const Plan> hit;
+        s->plan_cache_hit = 0;
+        if (cache_on && !values_need_matching(opt.matching, ndim, row_pointers, col_indices, values)) {
+            hash_pattern(ndim, row_pointers, col_indices, h1, h2);
+            std::lock_guard<std::mutex> lock(g_plan_mu);
+            for (const PlanCacheEntry& e : g_plan_cache)
+                if (e.h1 == h1 && e.h2 == h2 && e.n == ndim && e.nnz == row_pointers[ndim] && e.sym_lower == want_sym && same_options(e.opt, opt)) hit = e.plan;
+        }
+        if (hit) {
+            s->plan = *hit; // (a copy: the handle releases parts of its plan after the upload)
+            s->plan_cache_hit = 1;
+            if (verbose) fprintf(stderr, "solver_b200_initialize:   plan served from the cache (identical pattern analysed before)\n");
+        } else {
+            rc = analyze(ndim, row_pointers, col_indices, values, want_sym, opt, s->plan);
+            if (rc == 0 && cache_on && !s->plan.matched && s->plan.rscale.empty()) {
+                if (h1 == 0 && h2 == 0) hash_pattern(ndim, row_pointers, col_indices, h1, h2);
+                auto copy = std::make_shared<const Plan>(s->plan);
+                std::lock_guard<std::mutex> lock(g_plan_mu);
+                if (g_plan_cache.size() >= 3) g_plan_cache.erase(g_plan_cache.begin());
+                g_plan_cache.push_back({h1, h2, ndim, row_pointers[ndim], want_sym, opt, copy});
+            }
+        }
+    }
     if (rc == -1) return B200_ERROR_SINGULAR;
     if (rc != 0) return B200_ERROR_ANALYSIS + 2;
     if (verbose) fprintf(stderr, "solver_b200_initialize:   analysis done at %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_host0).count());
@@ -1216,32 +1202,15 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     UP(d_fact_nodes, fact_nodes);
     UP(d_solve_nodes, solve_nodes);
     {
-        // the top of the tree is a chain of narrow levels (few fronts each, latency bound): the inverses of everything
-        // below it run on a side stream underneath that chain.  inv_split = first level from which no level has
-        // more than 128 multi-kernel fronts.
-        s->lv.inv_split = -1;
-        if (s->overlap_invert && P.nlevels > 8) {
-            int l = P.nlevels;
-            while (l > 0) {
-                const int* fp = &s->lv.fact_ptr[(size_t)(l - 1) * (NFC + 1)];
-                if (fp[NFC + 1] - fp[0] > 128) break;
-                l--;
-            }
-            if (l > 0 && P.nlevels - l >= 8) s->lv.inv_split = l;
-        }
+        // fronts that need explicit pivot-block inverses (everything outside the subtree region), by pivot-count class
         std::vector<int> inv_nodes;
         s->lv.inv_ptr.assign(NIC + 1, 0);
-        s->lv.inv_early.assign(NIC, 0);
         for (int c = 0; c < NIC; c++) {
-            for (int pass = 0; pass < 2; pass++) { // pass 0: fronts below the split (early), pass 1: the rest
-                for (int v = 0; v < P.nnodes; v++) {
-                    int cls = 0;
-                    while (cls < NIC - 1 && P.p[v] > IC_MAXP[cls]) cls++;
-                    const bool early = s->lv.inv_split >= 0 && P.level[v] < s->lv.inv_split;
-                    if (s->in_sub[v]) continue; // the subtree kernels substitute with L11 / U11 directly (their slots hold the packed pivot blocks)
-                    if (cls == c && early == (pass == 0)) inv_nodes.push_back(v);
-                }
-                if (pass == 0) s->lv.inv_early[c] = (int)inv_nodes.size() - s->lv.inv_ptr[c];
+            for (int v = 0; v < P.nnodes; v++) {
+                int cls = 0;
+                while (cls < NIC - 1 && P.p[v] > IC_MAXP[cls]) cls++;
+                if (s->in_sub[v]) continue; // the subtree kernels substitute with L11 / U11 directly (their slots hold the packed pivot blocks)
+                if (cls == c) inv_nodes.push_back(v);
             }
             s->lv.inv_ptr[c + 1] = (int)inv_nodes.size();
         }
@@ -1365,16 +1334,13 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     // kernels that need more than 48 KB of dynamic shared memory
     const int W = s->opt_panel_width;
     CUDA_TRY(cudaFuncSetAttribute(k_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_diag(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
-    CUDA_TRY(cudaFuncSetAttribute(k_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_invert(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_invert_col, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_invert(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_front_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused(B200_FUSED_MAXF, B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_front_fused_w8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused(64, B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_panel(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_panel_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_PW_SMEM), B200_ERROR_NOT_AVAILABLE);
-    CUDA_TRY(cudaFuncSetAttribute(k_panel_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_PM_SMEM), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_schur_fma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_schur_fma(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
-    CUDA_TRY(cudaFuncSetAttribute(k_schur_dmma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024), B200_ERROR_NOT_AVAILABLE);
-    CUDA_TRY(cudaFuncSetAttribute(k_schur_dmma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024), B200_ERROR_NOT_AVAILABLE);
+    CUDA_TRY(cudaFuncSetAttribute(k_schur_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_assemble_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, B200_ASM_SMEM_MAX), B200_ERROR_NOT_AVAILABLE);
     if (s->n_subtrees > 0 && s->sub_variant != 1) {
         if (s->sub_smem > (size_t)200 * 1024) return B200_ERROR_NOT_AVAILABLE; // (subtree_budget / subtree_maxf out of range)
@@ -1889,6 +1855,7 @@ int32_t solver_b200_get_stats(struct InterfaceB200* s, double* out, int32_t n_ou
     v[B200_STAT_EFFECTIVE_SCALING] = P.rscale.empty() ? 0.0 : 1.0;
     v[B200_STAT_RCOND] = s->rcond;
     v[B200_STAT_T_INITIALIZE_HOST_S] = s->t_init_host;
+    v[B200_STAT_PLAN_CACHE_HIT] = s->plan_cache_hit;
     for (int i = 0; i < n_out && i < B200_STAT_COUNT; i++) out[i] = v[i];
     return B200_SUCCESSFUL_EXIT;
 }

@@ -293,3 +293,23 @@ def test_solve_matrix_market_emits_the_reference_schema():
     tn = doc["time_nanoseconds"]
     assert len(tn["total_ifs_array"]) == 2 and tn["total_ifs"] == sum(tn["total_ifs_array"]) // 2
     assert doc["determinant"]["base"] == 10.0 and doc["determinant"]["mantissa_real"] != 0.0
+
+
+# ---- plan cache: identical patterns are analysed once per process -------------------------------------------
+def test_identical_patterns_share_the_host_analysis():
+    n, ai, aj, ax = helpers.convection_diffusion_triplets(180)  # n = 32,400 >= the cache's size floor
+    b = np.cos(0.2 * np.arange(n)) + 1.0
+    coo1 = rb.CooMatrix.from_triplets(n, n, ai, aj, ax, rb.Sym.No)
+    s1, x1 = _solve(coo1, b)
+    coo2 = rb.CooMatrix.from_triplets(n, n, ai, aj, ax * 1.5, rb.Sym.No)  # same pattern, other values
+    s2, x2 = _solve(coo2, b)
+    st1, st2 = s1.device_stats(), s2.device_stats()
+    assert st2["plan_cache_hit"] == 1.0
+    assert st2["t_initialize_host_s"] < st1["t_initialize_host_s"] or st1["plan_cache_hit"] == 1.0
+    assert helpers.host_rel_residual(n, ai, aj, ax * 1.5, x2, b) <= TOL_RESIDUAL
+    assert np.allclose(x2 * 1.5, x1, rtol=1e-9, atol=0)  # (1.5 A) x2 = b  <=>  x2 = x1 / 1.5
+    # a different pattern is analysed afresh; a matrix that needs the matching never takes a shared plan
+    n3, ai3, aj3, ax3 = helpers.saddle_point_triplets(70)
+    s3 = rb.SolverB200()
+    s3.factorize(rb.CooMatrix.from_triplets(n3, n3, ai3, aj3, ax3, rb.Sym.No))
+    assert s3.device_stats()["plan_cache_hit"] == 0.0
