@@ -154,13 +154,14 @@ int32_t solver_b200_determinant(struct InterfaceB200 *solver, double *coefficien
 #define B200_STAT_COUNT 29
 int32_t solver_b200_get_stats(struct InterfaceB200 *solver, double *out, int32_t n_out);
 
-/* tuning knobs, to be set before initialize ("ir_tol", "refinement_nstep" and "strict_residual" also later).  Host analysis: "panel_width",
- * "nd_leaf", "relax_small", "relax_z1", "relax_z2", "relax_z3", "force_no_matching".  Execution: "device", "use_graph",
- * "ir_tol", "refinement_nstep", "trace".  Kernel variants kept for A/B measurements (defaults = the measured optimum, see
- * DESIGN.md): "schur_variant", "schur_occ3_min", "panel_variant", "panel_row_max", "diag_variant", "invert_variant",
- * "invert_all", "use_fused", "fused_variant", "fused_maxf", "fused_w8_max", "use_leaf_reg", "small_reg_maxf", "asm_variant",
- * "fuse_chain", "lookahead", "overlap_invert", "use_top", "top_variant", "top_max_nodes", "use_subtree", "subtree_maxf",
- * "subtree_budget".  Unknown keys return B200_ERROR_NOT_AVAILABLE. */
+/* tuning knobs, to be set before initialize ("ir_tol", "refinement_nstep" and "strict_residual" also later).  Host analysis:
+ * "panel_width", "nd_leaf", "relax_small", "relax_z1", "relax_z2", "relax_z3", "force_no_matching", "use_subtree", "subtree_maxf",
+ * "subtree_budget".  Execution: "device", "use_graph", "ir_tol", "refinement_nstep", "strict_residual", "trace".  One fallback
+ * per stage is kept next to the default kernel: "diag_variant" (4 = register-resident k_diag_w8, 0 = shared-memory
+ * k_diag), "panel_variant" (1 = k_panel_warp / k_panel_row, 0 = k_panel), "panel_row_max", "schur_variant" (1 = f64 DMMA, 0 = FMA,
+ * 2 = DMMA + the tcgen05 int8 Ozaki kernel for fronts with at least "ozaki_min_u" update rows), "fuse_chain", "use_fused",
+ * "fused_variant", "fused_maxf", "fused_w8_max", "use_leaf_reg", "asm_variant", "use_top", "top_max_nodes".  Unknown keys return
+ * B200_ERROR_NOT_AVAILABLE. */
 int32_t solver_b200_set_option(struct InterfaceB200 *solver, const char *key, double value);
 
 /* debug/parity: copies factor panels (fac), pivot-block inverses (dinv) and local pivots to host buffers

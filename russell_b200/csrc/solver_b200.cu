@@ -24,7 +24,6 @@
 #include "kernels.cuh"
 #include "sweep_top.cuh"
 #include "sweep_sub.cuh"
-#include "sweep_chain.cuh"
 #include "ozaki_tc.cuh"
 #include "plan.hpp"
 #include "coo_guard.hpp"
@@ -123,37 +122,20 @@ struct InterfaceB200 {
     int* d_big_slot = nullptr;
     // persistent top-of-tree sweep (sweep_top.cuh)
     int top_max_nodes = 1600; // (measured optimum at config 2) levels with at most this many fronts belong to the persistent sweep region
-    // bottom of the tree: one CTA per small subtree (k_fwd_subtree / k_bwd_subtree)
+    // bottom of the tree: one warp per small subtree (sweep_sub.cuh)
     int use_subtree = 1, subtree_maxf = 96, subtree_budget = 0; // (0: the variant's default)
-    int sub_variant = 1; // 1 = one warp per subtree, panels from global memory (k_*_stree_w); 0 = one CTA per subtree, bulk-staged in shared memory (k_*_stree)
     // eligibility: every front f <= maxf, p <= 32, stored L entries of the subtree <= budget
     std::vector<char> in_sub;   // per front: handled by a subtree CTA in the solve phase
     int n_subtrees = 0;
     SubtreeDev* d_subtrees = nullptr; // descriptors, largest first (sweep_sub.cuh)
     unsigned short* d_st_tgt = nullptr;
     uchar2* d_st_pu = nullptr;
-    size_t sub_smem = 0;
     bool fac_cleared = false;      // the host entry points clear the factor arena on the side stream, under their H2D copy
     std::vector<int> inv_skip_ptr; // NIC+1: fronts whose inverses are skipped, by class, inside d_inv_skip
     int* d_inv_skip = nullptr;
     unsigned long long* d_trace = nullptr; // optional per-item timestamps of the persistent sweeps (option "trace")
     int want_trace = 0;
     int *d_node_slot = nullptr, *d_bdone = nullptr; // k_bwd_top3: scratch slot base per front, partial-products-done counters
-    // top_variant 5: pipelined supernode chains, one CTA per 64-row block (sweep_chain.cuh).  Built and measured in round 2:
-    // correct, but slower than the slice kernels at config 2 (0.84-1.05 ms per sweep vs 0.80 ms): twice the items, and a
-    // per-item cost of ~5 us at the wide levels (profiles/r2j_trace_chain.txt).  Kept as an option for the A/B evidence.
-    ChainItem* d_ch_items = nullptr;
-    ChainPanel* d_ch_panels = nullptr;
-    int* d_ch_ranges = nullptr;
-    ulonglong2* d_zll = nullptr;
-    int n_ch_items = 0, ch_grid_f = 0, ch_grid_b = 0;
-    std::vector<ChainItem> h_ch_items; // host copies for the trace tool
-    std::vector<int> h_ch_level, h_ch_K;
-    long long pll_lines = 0;
-    int top_variant = 3;      // 4 = LL protocol (k_fwd_top_ll / k_bwd_top_ll: data and flag in one 16-byte line), 3 = completion counters (k_fwd_top2 / k_bwd_top3)
-    ulonglong2 *d_wll = nullptr, *d_xll = nullptr, *d_pll = nullptr; // LL lines: update vectors of the top fronts, solution of the top columns, partial dot products
-    int* d_wll_off = nullptr;
-    long long wll_size = 0;
     int use_top = 1, ltop = 0, n_top_items = 0, top_grid = 0, top_grid_b = 0, n_slots = 0; // (the backward kernel needs less shared memory: its own, larger co-resident grid)
     bool sweep_dirty = false;          // a persistent sweep aborted: counters must be re-armed
     std::vector<int> cdone_init;       // host copy of the initial completion counters
@@ -281,8 +263,6 @@ void release_device(InterfaceB200* s) {
     dfree(s->d_trace);
     dfree(s->d_subtrees), dfree(s->d_st_tgt), dfree(s->d_st_pu);
     dfree(s->d_node_slot), dfree(s->d_bdone);
-    dfree(s->d_wll), dfree(s->d_xll), dfree(s->d_pll), dfree(s->d_wll_off);
-    dfree(s->d_ch_items), dfree(s->d_ch_panels), dfree(s->d_ch_ranges), dfree(s->d_zll);
     dfree(s->d_inv_skip);
     dfree(s->d_big_items), dfree(s->d_big_slot), dfree(s->d_top_items), dfree(s->d_top_ranges), dfree(s->d_top_slot),
     dfree(s->d_cdone), dfree(s->d_xdone), dfree(s->d_epoch), dfree(s->d_abort), dfree(s->d_asm_ranges), dfree(s->d_big_ranges), dfree(s->d_big_scratch), dfree(s->d_big_tickets);
@@ -572,34 +552,11 @@ __global__ void __launch_bounds__(256) k_minmax_abs(int n, const double* __restr
     if ((threadIdx.x & 31) == 0) atomicMin(mm, lo), atomicMax(mm + 1, hi);
 }
 void k_fwd_top_launch(InterfaceB200* s) {
-    if (s->n_ch_items > 0) {
-        k_fwd_chain<<<s->ch_grid_f, 256, 0, s->stream>>>(s->d_ch_items, s->n_ch_items, s->d_ch_panels, s->d_rel, s->d_fac, s->d_dinv, s->d_lperm,
-                                                      s->d_ch_ranges, s->d_y, s->d_z, s->d_wv, s->d_wll, s->d_zll, s->d_epoch, s->d_abort, s->d_trace);
-        return;
-    }
-    if (s->top_variant >= 4) {
-        k_fwd_top_ll<<<s->top_grid, 256, B200_TOP3_SMEM, s->stream>>>(s->d_top_items, s->n_top_items, s->d_nodes, s->d_rel, s->d_fac, s->d_dinv,
-                                                                   s->d_lperm, s->d_top_ranges, s->d_wll_off, s->d_y, s->d_z, s->d_wv, s->d_wll,
-                                                                   s->d_epoch, s->d_abort, s->d_trace);
-        return;
-    }
     k_fwd_top2<<<s->top_grid, 256, B200_TOP3_SMEM, s->stream>>>(s->d_top_items, s->n_top_items, s->d_nodes, s->d_rel, s->d_fac, s->d_dinv,
                                                              s->d_lperm, s->d_top_ranges, s->d_y, s->d_z, s->d_wv, s->d_cdone, s->d_epoch,
                                                              s->d_abort, s->d_trace);
 }
 void k_bwd_top_launch(InterfaceB200* s) {
-    if (s->n_ch_items > 0) {
-        k_bwd_chain<<<s->ch_grid_b, 256, 0, s->stream>>>(s->d_ch_items, s->n_ch_items, s->d_ch_panels, s->d_rows, s->d_fac, s->d_dinv, s->d_z, s->d_xp,
-                                                      s->d_xll, s->d_pll, s->d_epoch, s->d_abort,
-                                                      s->d_trace ? s->d_trace + 4 * (size_t)s->n_ch_items : nullptr);
-        return;
-    }
-    if (s->top_variant >= 4) {
-        k_bwd_top_ll<<<s->top_grid_b, 256, B200_TOP3_SMEM, s->stream>>>(s->d_top_items, s->n_top_items, s->d_nodes, s->d_rows, s->d_fac, s->d_dinv,
-                                                                     s->d_z, s->d_xp, s->d_xll, s->d_pll, s->d_node_slot, s->d_bdone, s->d_epoch,
-                                                                     s->d_abort, s->d_trace ? s->d_trace + 4 * (size_t)s->n_top_items : nullptr);
-        return;
-    }
     k_bwd_top3<<<s->top_grid_b, 256, B200_TOP3_SMEM, s->stream>>>(s->d_top_items, s->n_top_items, s->d_nodes, s->d_rows, s->d_fac, s->d_dinv,
                                                               s->d_z, s->d_xp, s->d_big_scratch, s->d_node_slot, s->d_bdone, s->d_epoch,
                                                               s->d_abort, s->d_trace ? s->d_trace + 4 * (size_t)s->n_top_items : nullptr);
@@ -611,12 +568,8 @@ int enqueue_sweep_levels(InterfaceB200* s, int* launches) {
     int cnt = 0;
     const int lsplit = s->n_top_items > 0 ? s->ltop : P.nlevels; // levels >= lsplit run in the persistent kernels
     if (s->n_subtrees > 0) {
-        if (s->sub_variant == 1)
-            k_fwd_stree_w<<<(s->n_subtrees + B200_SUBW_WARPS - 1) / B200_SUBW_WARPS, 32 * B200_SUBW_WARPS, 0, s->stream>>>(
-                s->d_subtrees, s->n_subtrees, s->d_fac, s->d_st_tgt, s->d_st_pu, s->d_lperm, s->d_y, s->d_z, s->d_wv);
-        else
-            k_fwd_stree<<<s->n_subtrees, B200_SUB_THREADS, s->sub_smem, s->stream>>>(s->d_subtrees, s->d_fac, s->d_st_tgt, s->d_st_pu, s->d_lperm,
-                                                                                     s->d_y, s->d_z, s->d_wv);
+        k_fwd_stree_w<<<(s->n_subtrees + B200_SUBW_WARPS - 1) / B200_SUBW_WARPS, 32 * B200_SUBW_WARPS, 0, s->stream>>>(
+            s->d_subtrees, s->n_subtrees, s->d_fac, s->d_st_tgt, s->d_st_pu, s->d_lperm, s->d_y, s->d_z, s->d_wv);
         cnt++;
     }
     for (int l = 0; l < lsplit; l++) {
@@ -657,12 +610,8 @@ int enqueue_sweep_levels(InterfaceB200* s, int* launches) {
         }
     }
     if (s->n_subtrees > 0) {
-        if (s->sub_variant == 1)
-            k_bwd_stree_w<<<(s->n_subtrees + B200_SUBW_WARPS - 1) / B200_SUBW_WARPS, 32 * B200_SUBW_WARPS, 0, s->stream>>>(
-                s->d_subtrees, s->n_subtrees, s->d_fac, s->d_dinv, s->d_st_tgt, s->d_st_pu, s->d_rows, s->d_z, s->d_xp);
-        else
-            k_bwd_stree<<<s->n_subtrees, B200_SUB_THREADS, s->sub_smem, s->stream>>>(s->d_subtrees, s->d_fac, s->d_dinv, s->d_st_tgt, s->d_st_pu,
-                                                                                     s->d_rows, s->d_z, s->d_xp);
+        k_bwd_stree_w<<<(s->n_subtrees + B200_SUBW_WARPS - 1) / B200_SUBW_WARPS, 32 * B200_SUBW_WARPS, 0, s->stream>>>(
+            s->d_subtrees, s->n_subtrees, s->d_fac, s->d_dinv, s->d_st_tgt, s->d_st_pu, s->d_rows, s->d_z, s->d_xp);
         cnt++;
     }
     if (launches) *launches = cnt;
@@ -785,7 +734,6 @@ struct InterfaceB200* solver_b200_new(void) {
     if ((e = getenv("B200_FUSED_VARIANT"))) s->fused_variant = atoi(e);
     if ((e = getenv("B200_USE_FUSED"))) s->use_fused = atoi(e);
     if ((e = getenv("B200_USE_TOP"))) s->use_top = atoi(e);
-    if ((e = getenv("B200_TOP_VARIANT"))) s->top_variant = atoi(e);
     if ((e = getenv("B200_USE_SUBTREE"))) s->use_subtree = atoi(e);
     if ((e = getenv("B200_SUBTREE_MAXF"))) s->subtree_maxf = atoi(e);
     if ((e = getenv("B200_SUBTREE_BUDGET"))) s->subtree_budget = atoi(e);
@@ -832,12 +780,10 @@ int32_t solver_b200_set_option(struct InterfaceB200* s, const char* key, double 
     else if (k == "fused_w8_max") s->fused_w8_max = (int)value;
     else if (k == "use_fused") s->use_fused = value != 0.0;
     else if (k == "use_top") s->use_top = value != 0.0;
-    else if (k == "top_variant") s->top_variant = (int)value;
     else if (k == "trace") s->want_trace = value != 0.0;
     else if (k == "use_subtree") s->use_subtree = value != 0.0;
     else if (k == "subtree_maxf") s->subtree_maxf = std::max(1, (int)value);
     else if (k == "subtree_budget") s->subtree_budget = std::max(0, (int)value);
-    else if (k == "sub_variant") s->sub_variant = (int)value;
     else if (k == "diag_variant") s->diag_variant = (int)value;
     else if (k == "fuse_chain") s->fuse_chain = value != 0.0;
     else if (k == "top_max_nodes") s->top_max_nodes = std::max(1, (int)value);
@@ -886,8 +832,8 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     opt.verbose = verbose;
     opt.st_enable = s->use_subtree;
     opt.st_maxf = std::max(1, std::min(s->subtree_maxf, 200));
-    opt.st_budget = std::max(16, s->subtree_budget > 0 ? s->subtree_budget : (s->sub_variant == 1 ? 8192 : 5632));
-    opt.st_maxcols = s->sub_variant == 1 ? B200_SUBW_XS : 2560;
+    opt.st_budget = std::max(16, s->subtree_budget > 0 ? s->subtree_budget : 8192);
+    opt.st_maxcols = B200_SUBW_XS;
     if (ordering == B200_ORDERING_NONE) opt.ordering = ORDERING_NATURAL;
     else if (ordering == B200_ORDERING_AMD) opt.ordering = ORDERING_MINDEG;
     else opt.ordering = ORDERING_ND;
@@ -954,7 +900,6 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     std::vector<unsigned short> st_tgt;
     std::vector<uchar2> st_pu;
     s->in_sub = P.in_sub;
-    size_t sub_smem = 0;
     {
         std::vector<std::pair<int64_t, int>> order;
         for (size_t i = 0; i < P.st_first.size(); i++) {
@@ -995,11 +940,9 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
             d.Lcount = (int)lc, d.Ucount = (int)uc, d.Dcount = (int)dc;
             d.tgt_count = (int)(st_tgt.size() - (size_t)d.tgt_beg);
             d.pan = (int)std::max(lc, uc + dc);
-            sub_smem = std::max(sub_smem, sub_smem_bytes(d.pan, d.ncols, d.next, d.tgt_count, d.nfr));
             subtrees.push_back(d);
         }
     }
-    s->sub_smem = sub_smem;
     s->n_subtrees = (int)subtrees.size();
     if (verbose) fprintf(stderr, "solver_b200_initialize:   subtree descriptors built at %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_host0).count());
     std::vector<AsmItem> asm_items;
@@ -1057,8 +1000,7 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
 
     // persistent top-of-tree sweep: all levels above the last "wide" level (more than 96 fronts)
     std::vector<SolveItem> top_items;
-    std::vector<int> top_ranges, top_slot, cdone_init(P.nnodes, 1 << 30), node_slot(P.nnodes, -1), wll_off(P.nnodes, -1);
-    long long wll_size = 0;
+    std::vector<int> top_ranges, top_slot, cdone_init(P.nnodes, 1 << 30), node_slot(P.nnodes, -1);
     s->ltop = P.nlevels;
     if (s->use_top) {
         std::vector<int> cnt(P.nlevels, 0); // fronts per level outside the subtree region
@@ -1076,14 +1018,10 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
             const int nsl = std::max(1, (u + B200_SLICE - 1) / B200_SLICE);
             cdone_init[v] = 0;
             node_slot[v] = nslots;
-            wll_off[v] = (int)wll_size, wll_size += u;
-            if (wll_size > 0x7fff0000LL) return B200_ERROR_MALLOC;
-            int top_children = 0; // children inside the persistent region (lower levels: already visited)
-            for (int c = P.child_ptr[v]; c < P.child_ptr[v + 1]; c++) top_children += wll_off[P.child_idx[c]] >= 0;
             for (int sl = 0; sl < nsl; sl++) {
                 const int r0 = sl * B200_SLICE;
                 const int nrows = std::max(0, std::min(B200_SLICE, u - r0));
-                top_items.push_back({v, r0, nrows, sl, (int)top_ranges.size(), top_children == 0 ? 1 : 0});
+                top_items.push_back({v, r0, nrows, sl, (int)top_ranges.size(), 0});
                 top_slot.push_back(nslots);
                 for (int c = P.child_ptr[v]; c < P.child_ptr[v + 1]; c++) {
                     const int ch = P.child_idx[c];
@@ -1096,102 +1034,13 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
                     top_ranges.push_back((int)(uint32_t)((uint64_t)P.rows_ptr[ch] & 0xffffffffu));
                     top_ranges.push_back((int)(uint32_t)((uint64_t)P.rows_ptr[ch] >> 32));
                     top_ranges.push_back(std::max(1, (P.u[ch] + B200_SLICE - 1) / B200_SLICE));
-                    top_ranges.push_back(wll_off[ch]); // first LL line of the child's update vector, -1: child below the region (plain wv)
+                    top_ranges.push_back(0);
                 }
             }
             nslots += nsl;
         }
     s->n_top_items = (int)top_items.size();
 
-    // ---- top_variant 5: supernode chains of the persistent region and their 64-row blocks (sweep_chain.cuh)
-    std::vector<ChainItem> ch_items;
-    std::vector<ChainPanel> ch_panels;
-    std::vector<int> ch_ranges, ch_level, ch_K;
-    long long ch_wll = 0, ch_pll_groups = 0;
-    if (s->n_top_items > 0 && s->top_variant >= 5) {
-        auto intop = [&](int v) { return P.level[v] >= s->ltop && !s->in_sub[v]; };
-        std::vector<int> chain_of(P.nnodes, -1);
-        std::vector<std::vector<int>> members;
-        for (int v = 0; v < P.nnodes; v++) { // ascending = children first: a chain is met at its first panel
-            if (!intop(v) || chain_of[v] >= 0) continue;
-            std::vector<int> mem(1, v);
-            int w = v;
-            for (;;) {
-                const int par = P.parent[w];
-                if (par < 0 || !intop(par) || P.child_ptr[par + 1] - P.child_ptr[par] != 1 || P.u[w] != P.p[par] + P.u[par]) break;
-                const int* rel = &P.rel[P.rows_ptr[w]];
-                bool ident = true;
-                for (int i = 0; i < P.u[w] && ident; i++) ident = rel[i] == i;
-                if (!ident) break;
-                mem.push_back(par), w = par;
-            }
-            for (int m : mem) chain_of[m] = (int)members.size();
-            members.push_back(mem);
-        }
-        // chains in dependency order: by the level of their first panel (children chains end below their parent's first panel)
-        std::vector<int> order(members.size());
-        for (size_t t = 0; t < order.size(); t++) order[t] = (int)t;
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return P.level[members[a][0]] < P.level[members[b][0]]; });
-        std::vector<int> newid(members.size());
-        for (size_t k = 0; k < order.size(); k++) newid[order[k]] = (int)k;
-        std::vector<long long> wll_of_chain(members.size(), -1); // by NEW chain id
-        struct ChainHost { int panel_ptr, K, P, U, nblocks, last_node; long long wll_off, pbase; };
-        std::vector<ChainHost> chh(members.size());
-        for (size_t k = 0; k < order.size(); k++) {
-            const std::vector<int>& mem = members[order[k]];
-            ChainHost& c = chh[k];
-            c.panel_ptr = (int)ch_panels.size(), c.K = (int)mem.size();
-            int off = 0;
-            for (int m : mem) {
-                ChainPanel cp;
-                cp.Loff = P.Loff[m], cp.Uoff = P.Uoff[m], cp.off = off, cp.p = P.p[m], cp.f = P.p[m] + P.u[m], cp.u = P.u[m], cp.c0 = P.c0[m], cp.pad = m;
-                ch_panels.push_back(cp), off += P.p[m];
-            }
-            c.P = off, c.U = P.u[mem.back()], c.last_node = mem.back();
-            c.nblocks = c.K + (c.U + B200_CH_B - 1) / B200_CH_B;
-            c.wll_off = ch_wll, ch_wll += c.U;
-            c.pbase = ch_pll_groups, ch_pll_groups += (long long)c.K * c.nblocks;
-            wll_of_chain[k] = c.wll_off;
-        }
-        ch_level.resize(order.size()), ch_K.resize(order.size());
-        for (size_t k = 0; k < order.size(); k++) {
-            const std::vector<int>& mem = members[order[k]];
-            const ChainHost& c = chh[k];
-            const int v0 = mem[0];
-            ch_level[k] = P.level[v0], ch_K[k] = c.K;
-            for (int jb = 0; jb < c.nblocks; jb++) {
-                ChainItem it;
-                it.chain = (int)k, it.block = jb, it.K = c.K, it.nblocks = c.nblocks, it.panel_ptr = c.panel_ptr, it.pgrp = c.pbase;
-                it.c0j = 0, it.Doff = 0, it.out = 0, it.rows_off = 0;
-                if (jb < c.K) {
-                    it.row0 = ch_panels[c.panel_ptr + jb].off, it.nrows = P.p[mem[jb]];
-                    it.c0j = P.c0[mem[jb]], it.Doff = P.Doff[mem[jb]];
-                } else {
-                    it.row0 = c.P + (jb - c.K) * B200_CH_B, it.nrows = std::min(B200_CH_B, c.P + c.U - it.row0);
-                    it.out = c.wll_off + (it.row0 - c.P);
-                    it.rows_off = P.rows_ptr[c.last_node] + (it.row0 - c.P);
-                }
-                it.rng = (int)ch_ranges.size(), it.nch = 0;
-                for (int e = P.child_ptr[v0]; e < P.child_ptr[v0 + 1]; e++) { // children of the first front whose rows land in this block
-                    const int cnode = P.child_idx[e];
-                    const int* rel = &P.rel[P.rows_ptr[cnode]];
-                    const int a = (int)(std::lower_bound(rel, rel + P.u[cnode], it.row0) - rel);
-                    const int b = (int)(std::lower_bound(rel, rel + P.u[cnode], it.row0 + it.nrows) - rel);
-                    if (b <= a) continue;
-                    const long long wofs = P.rows_ptr[cnode];
-                    const long long llo = intop(cnode) ? wll_of_chain[newid[chain_of[cnode]]] : -1;
-                    ch_ranges.push_back(a), ch_ranges.push_back(b);
-                    ch_ranges.push_back((int)(uint32_t)((uint64_t)wofs & 0xffffffffu)), ch_ranges.push_back((int)(uint32_t)((uint64_t)wofs >> 32));
-                    ch_ranges.push_back((int)(uint32_t)((uint64_t)llo & 0xffffffffu)), ch_ranges.push_back((int)(uint32_t)((uint64_t)llo >> 32));
-                    ch_ranges.push_back(0), ch_ranges.push_back(0);
-                    it.nch++;
-                }
-                ch_items.push_back(it);
-            }
-        }
-    }
-    s->n_ch_items = (int)ch_items.size();
-    if (s->want_trace) s->h_ch_items = ch_items, s->h_ch_level = ch_level, s->h_ch_K = ch_K;
 
     if (verbose) fprintf(stderr, "solver_b200_initialize:   top items built at %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_host0).count());
 #define UP(dst, vec) CUDA_TRY(upload(&s->dst, vec), B200_ERROR_CUDA_MALLOC)
@@ -1244,10 +1093,6 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     UP(d_top_ranges, top_ranges);
     UP(d_top_slot, top_slot);
     UP(d_node_slot, node_slot);
-    UP(d_wll_off, wll_off);
-    UP(d_ch_items, ch_items);
-    UP(d_ch_panels, ch_panels);
-    UP(d_ch_ranges, ch_ranges);
     UP(d_cdone, cdone_init);
     s->cdone_init = cdone_init;
     s->n_slots = nslots;
@@ -1299,23 +1144,6 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     DM(d_xdone, P.nnodes, int);
     DM(d_bdone, P.nnodes, int);
     CUDA_TRY(cudaMemset(s->d_bdone, 0, (size_t)std::max(P.nnodes, 1) * sizeof(int)), B200_ERROR_CUDA_MALLOC);
-    long long nslots_pll = nslots;
-    if (s->n_ch_items > 0) { // (the chain kernels keep their own, chain-indexed LL areas)
-        wll_size = ch_wll;
-        nslots_pll = ch_pll_groups;
-        DM(d_zll, P.n, ulonglong2);
-        CUDA_TRY(cudaMemset(s->d_zll, 0, (size_t)P.n * sizeof(ulonglong2)), B200_ERROR_CUDA_MALLOC);
-    }
-    if (s->n_top_items > 0 && s->top_variant >= 4) {
-        s->wll_size = wll_size;
-        DM(d_wll, wll_size, ulonglong2);
-        DM(d_xll, P.n, ulonglong2);
-        s->pll_lines = std::max<long long>(nslots_pll, 1) * B200_MAXP;
-        DM(d_pll, (size_t)s->pll_lines, ulonglong2);
-        CUDA_TRY(cudaMemset(s->d_wll, 0, std::max<size_t>((size_t)wll_size, 1) * sizeof(ulonglong2)), B200_ERROR_CUDA_MALLOC);
-        CUDA_TRY(cudaMemset(s->d_xll, 0, (size_t)P.n * sizeof(ulonglong2)), B200_ERROR_CUDA_MALLOC);
-        CUDA_TRY(cudaMemset(s->d_pll, 0, (size_t)s->pll_lines * sizeof(ulonglong2)), B200_ERROR_CUDA_MALLOC);
-    }
     DM(d_epoch, 4, int); // [0] sweep epoch, [1] / [2] item tickets of the forward / backward persistent kernels
     DM(d_abort, 1, int);
     CUDA_TRY(cudaMemset(s->d_xdone, 0, (size_t)std::max(P.nnodes, 1) * sizeof(int)), B200_ERROR_CUDA_MALLOC);
@@ -1323,7 +1151,7 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     CUDA_TRY(cudaMemset(s->d_abort, 0, sizeof(int)), B200_ERROR_CUDA_MALLOC);
 #undef DM
     if (s->want_trace && s->n_top_items > 0) { // must precede the first graph capture of the sweep (the pointer is a kernel argument)
-        const size_t nt = (size_t)std::max(s->n_top_items, s->n_ch_items);
+        const size_t nt = (size_t)s->n_top_items;
         CUDA_TRY(cudaMalloc((void**)&s->d_trace, 8 * nt * sizeof(unsigned long long)), B200_ERROR_CUDA_MALLOC);
         CUDA_TRY(cudaMemset(s->d_trace, 0, 8 * nt * sizeof(unsigned long long)), B200_ERROR_CUDA_MALLOC);
     }
@@ -1342,34 +1170,14 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     CUDA_TRY(cudaFuncSetAttribute(k_schur_fma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_schur_fma(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_schur_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_assemble_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, B200_ASM_SMEM_MAX), B200_ERROR_NOT_AVAILABLE);
-    if (s->n_subtrees > 0 && s->sub_variant != 1) {
-        if (s->sub_smem > (size_t)200 * 1024) return B200_ERROR_NOT_AVAILABLE; // (subtree_budget / subtree_maxf out of range)
-        CUDA_TRY(cudaFuncSetAttribute(k_fwd_stree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->sub_smem), B200_ERROR_NOT_AVAILABLE);
-        CUDA_TRY(cudaFuncSetAttribute(k_bwd_stree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->sub_smem), B200_ERROR_NOT_AVAILABLE);
-    }
     (void)W;
     if (s->n_top_items > 0) {
         CUDA_TRY(cudaFuncSetAttribute(k_fwd_top2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_TOP3_SMEM), B200_ERROR_NOT_AVAILABLE);
         CUDA_TRY(cudaFuncSetAttribute(k_bwd_top3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_TOP3_SMEM), B200_ERROR_NOT_AVAILABLE);
-        CUDA_TRY(cudaFuncSetAttribute(k_fwd_top_ll, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_TOP3_SMEM), B200_ERROR_NOT_AVAILABLE);
-        CUDA_TRY(cudaFuncSetAttribute(k_bwd_top_ll, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_TOP3_SMEM), B200_ERROR_NOT_AVAILABLE);
         int occ_f = 0, occ_b = 0, nsm = 0;
-        if (s->top_variant >= 4) {
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_fwd_top_ll, 256, B200_TOP3_SMEM), B200_ERROR_NOT_AVAILABLE);
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_bwd_top_ll, 256, B200_TOP3_SMEM), B200_ERROR_NOT_AVAILABLE);
-        } else {
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_fwd_top2, 256, B200_TOP3_SMEM), B200_ERROR_NOT_AVAILABLE);
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_bwd_top3, 256, B200_TOP3_SMEM), B200_ERROR_NOT_AVAILABLE);
-        }
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_fwd_top2, 256, B200_TOP3_SMEM), B200_ERROR_NOT_AVAILABLE);
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_bwd_top3, 256, B200_TOP3_SMEM), B200_ERROR_NOT_AVAILABLE);
         CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device), B200_ERROR_NOT_AVAILABLE);
-        if (s->n_ch_items > 0) {
-            int of = 0, ob = 0;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&of, k_fwd_chain, 256, 0), B200_ERROR_NOT_AVAILABLE);
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ob, k_bwd_chain, 256, 0), B200_ERROR_NOT_AVAILABLE);
-            if (of < 1 || ob < 1) s->n_ch_items = 0;
-            s->ch_grid_f = std::max(1, std::min(s->n_ch_items, of * nsm));
-            s->ch_grid_b = std::max(1, std::min(s->n_ch_items, ob * nsm));
-        }
         int occ = std::min(occ_f, occ_b);
         if (occ < 1) s->n_top_items = 0; // the kernels cannot run at all: fall back to per-level launches
         s->top_grid = std::max(1, std::min(s->n_top_items, occ_f * nsm)); // (a performance choice only: items are handed out by ticket)
@@ -1397,8 +1205,8 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
                P.nnodes, P.nlevels, (long long)(P.nnz_L + P.nnz_U), P.flops, (tot - fr) / 1e9);
         long long nsubfr = 0;
         for (int v = 0; v < P.nnodes; v++) nsubfr += s->in_sub[v];
-        printf("solver_b200_initialize: solve phase: %d subtree CTAs (%lld fronts, %zu B of shared memory each), %d persistent items above level %d\n",
-               s->n_subtrees, nsubfr, s->sub_smem, s->n_top_items, s->ltop);
+        printf("solver_b200_initialize: solve phase: %d subtrees (one warp each, %lld fronts), %d persistent items above level %d\n",
+               s->n_subtrees, nsubfr, s->n_top_items, s->ltop);
     }
     s->t_init_host = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_host0).count();
     s->initialized = true;
@@ -1419,12 +1227,6 @@ int32_t solver_b200_factorize_device(struct InterfaceB200* s, const double* d_va
         CUDA_TRY(cudaMemsetAsync(s->d_bdone, 0, (size_t)std::max(P.nnodes, 1) * sizeof(int), s->stream), B200_ERROR_CUDA_MEMCPY);
         CUDA_TRY(cudaMemsetAsync(s->d_epoch, 0, 4 * sizeof(int), s->stream), B200_ERROR_CUDA_MEMCPY);
         CUDA_TRY(cudaMemsetAsync(s->d_abort, 0, sizeof(int), s->stream), B200_ERROR_CUDA_MEMCPY);
-        if (s->d_wll) { // the epoch restarts at zero: lines tagged by earlier sweeps must not match again
-            CUDA_TRY(cudaMemsetAsync(s->d_wll, 0, std::max<size_t>((size_t)s->wll_size, 1) * sizeof(ulonglong2), s->stream), B200_ERROR_CUDA_MEMCPY);
-            CUDA_TRY(cudaMemsetAsync(s->d_xll, 0, (size_t)s->n * sizeof(ulonglong2), s->stream), B200_ERROR_CUDA_MEMCPY);
-            CUDA_TRY(cudaMemsetAsync(s->d_pll, 0, (size_t)s->pll_lines * sizeof(ulonglong2), s->stream), B200_ERROR_CUDA_MEMCPY);
-            if (s->d_zll) CUDA_TRY(cudaMemsetAsync(s->d_zll, 0, (size_t)s->n * sizeof(ulonglong2), s->stream), B200_ERROR_CUDA_MEMCPY);
-        }
         CUDA_TRY(cudaMemsetAsync(s->d_big_tickets, 0, (size_t)std::max(s->n_slots, 1) * sizeof(int), s->stream), B200_ERROR_CUDA_MEMCPY);
         CUDA_TRY(cudaStreamSynchronize(s->stream), B200_ERROR_CUDA_SYNCHRONIZE);
         s->sweep_dirty = false;
@@ -1867,19 +1669,6 @@ int32_t solver_b200_debug_trace(struct InterfaceB200* s, unsigned long long* out
     if (!s || !s->d_trace || !s->initialized) return -1;
     cudaSetDevice(s->device);
     cudaStreamSynchronize(s->stream);
-    if (s->n_ch_items > 0) { // chain kernels: desc = (chain, level of its first panel, block, rows)
-        const int nc = std::min(cap, s->n_ch_items);
-        if (out) {
-            cudaMemcpy(out, s->d_trace, 4 * (size_t)nc * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-            cudaMemcpy(out + 4 * (size_t)nc, s->d_trace + 4 * (size_t)s->n_ch_items, 4 * (size_t)nc * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-        }
-        if (desc)
-            for (int i = 0; i < nc && i < (int)s->h_ch_items.size(); i++) {
-                const ChainItem& it = s->h_ch_items[i];
-                desc[4 * i] = it.chain, desc[4 * i + 1] = s->h_ch_level[it.chain] + std::min(it.block, s->h_ch_K[it.chain] - 1), desc[4 * i + 2] = it.block, desc[4 * i + 3] = it.nrows;
-            }
-        return s->n_ch_items;
-    }
     const int n = std::min(cap, s->n_top_items);
     if (out) {
         cudaMemcpy(out, s->d_trace, 4 * (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost);

@@ -1,208 +1,47 @@
-// sweep_sub.cuh -- triangular solves over the BOTTOM of the front tree: one CTA per small subtree, everything in shared memory.
+// sweep_sub.cuh -- triangular solves over the BOTTOM of the front tree: one WARP per small subtree.
 //
 // Role in the reference: the inside of umfpack_di_solve / cudssExecute(SOLVE)
 // (russell_sparse/c_code/interface_umfpack.c:229, interface_cudss.cu:530) for the ~95 % of the fronts that are tiny.
 //
-// The first version of these kernels (k_fwd_subtree / k_bwd_subtree, round 1) walked a subtree front by front with the
-// multifrontal vector scheme: every front gathered its children's update vectors through relative indices, built its own
-// update vector and wrote it back to global memory.  ncu showed them bound by instruction issue (~900 warp instructions per
-// front for ~370 stored entries) and, in the backward direction, by p short column segments per front read out of the f x p
-// L panels (1.42x the algorithmic DRAM traffic).  This version is right-looking on a shared-memory segment of the solution
-// vector instead:
+// The round-1 kernels (k_fwd_subtree / k_bwd_subtree) walked a subtree front by front with the multifrontal vector scheme:
+// every front gathered its children's update vectors through relative indices, built its own update vector and wrote it
+// back to global memory.  ncu showed them bound by instruction issue (~900 warp instructions per front for ~370 stored
+// entries) and, in the backward direction, by p short column segments per front read out of the f x p L panels (1.42x the
+// algorithmic DRAM traffic).  These kernels are right-looking on a shared-memory segment of the solution vector instead:
 //   * the columns of a subtree are contiguous (postorder) -> xs[0 .. ncols) holds them, xs[ncols .. ncols + u_root) holds the
 //     update rows of the subtree's root (everything that leaves the subtree); a host-built 16-bit target index per update
 //     row says where a row of any front of the subtree lives in xs.  No child lists, no relative indices, no per-front
 //     update vectors, no global traffic between the fronts of a subtree;
 //   * the host analysis lays the subtree's L panels out contiguously, then its U panels; a post-pass of the factorization
-//     packs the pivot blocks (needed by both directions) next to each other.  ONE bulk-copy transaction per array
-//     (cp.async.bulk = TMA, completion on an mbarrier) stages what a direction needs: the forward kernel reads the L
-//     region, the backward kernel the U region + the packed pivot blocks -- exactly the algorithmic bytes, in full lines;
-//   * per front: two block barriers, a p-step substitution by shuffles inside warp 0, and one multiply-add per stored entry.
+//     (k_pack_pivot_blocks) packs the pivot blocks next to each other: the forward walk streams the L region, the backward
+//     walk the U region + the packed pivot blocks -- the algorithmic bytes, in full lines (measured: 196 MB of DRAM traffic
+//     per direction for 173 MB of panels at config 2);
+//   * a subtree needs only xs in shared memory (<= 8 KB), so 24-28 warps = subtrees are resident per SM; a warp requests all
+//     loads of a front at once (coalesced: lanes = rows), the other warps hide their latency, and nothing but __syncwarp
+//     orders the walk: ~100 instructions per front.
+// A first version staged a whole subtree (24 KB on average) in shared memory with ONE bulk copy per array (cp.async.bulk on
+// an mbarrier, one CTA per subtree): correct, but 4-5 CTAs per SM were too few fronts in flight -- 1.10 ms per sweep against
+// 0.92 ms for round 1 and 0.80 ms for the warp-per-subtree walk (profiles/r2c_*, r2e_*); it was removed.
 #pragma once
 #include "kernels.cuh"
 
 namespace b200 {
 
-struct SubtreeDev {          // 80 bytes, built once by the host
+struct SubtreeDev {          // built once by the host
     long long Lbeg, Ubeg, Dbeg; // first double of the subtree's L region / U region in fac, of its pivot-block copies in dinv
-    long long tgt_beg;          // first entry of its target indices (uint16) -- multiple of 8 entries (16 bytes)
+    long long tgt_beg;          // first entry of its target indices (uint16)
     long long root_rows;        // offset of the root's update-row list in rows[] / wv[]
     int Lcount, Ucount, Dcount; // doubles (multiples of 4)
     int tgt_count;              // uint16 entries, padded to a multiple of 8
-    int pu_beg;                 // first (p, u) pair of its fronts inside the pu array (multiple of 8 pairs = 16 bytes)
+    int pu_beg;                 // first (p, u) pair of its fronts inside the pu array
     int nfr;                    // fronts
     int cbeg, ncols;            // first column and number of columns
     int next;                   // update rows of the root
-    int pan;                    // doubles reserved for the panel region of this subtree's CTA: max(Lcount, Ucount + Dcount)
+    int pan;                    // max(Lcount, Ucount + Dcount)
 };
 
-#define B200_SUB_THREADS 64
-
-__device__ __forceinline__ void sub_bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     (unsigned)__cvta_generic_to_shared(smem_dst)),
-                 "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void sub_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ int sub_round4(int x) { return (x + 3) & ~3; }
 
-// dynamic shared memory of one CTA: panels (pan doubles) | xs (ncols + next, rounded up to even) | tgt (tgt_count uint16) |
-// pu (nfr pairs, rounded up to 8) | lps (ncols bytes); every region starts 16-byte aligned.  The launch reserves the largest
-// total over all subtrees (sub_smem_bytes on the host).
-__host__ __device__ __forceinline__ int sub_xs_doubles(int ncols, int next) { return (ncols + next + 1) & ~1; }
-__host__ __device__ __forceinline__ size_t sub_smem_bytes(int pan, int ncols, int next, int tgt_count, int nfr) {
-    return (size_t)pan * 8 + (size_t)sub_xs_doubles(ncols, next) * 8 + (size_t)tgt_count * 2 + (size_t)((nfr + 7) & ~7) * 2 + (size_t)((ncols + 15) & ~15);
-}
-
-// forward:  z = L^{-1} P y  on the subtree's columns; the root's update vector goes to wv (read by the front above)
-__global__ void __launch_bounds__(B200_SUB_THREADS) k_fwd_stree(const SubtreeDev* __restrict__ trees, const double* __restrict__ fac,
-                                                                const unsigned short* __restrict__ tgt_all, const uchar2* __restrict__ pu_all,
-                                                                const int* __restrict__ lperm, const double* __restrict__ y,
-                                                                double* __restrict__ zv, double* __restrict__ wv) {
-    extern __shared__ __align__(16) unsigned char smraw[];
-    __shared__ __align__(8) unsigned long long bar;
-    const SubtreeDev st = trees[blockIdx.x];
-    double* Ls = reinterpret_cast<double*>(smraw);
-    double* xs = Ls + st.pan;
-    unsigned short* tg = reinterpret_cast<unsigned short*>(xs + sub_xs_doubles(st.ncols, st.next));
-    uchar2* pu = reinterpret_cast<uchar2*>(tg + st.tgt_count);
-    unsigned char* lps = reinterpret_cast<unsigned char*>(pu + ((st.nfr + 7) & ~7));
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
-        mbar_init(&bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const unsigned nb_pu = (unsigned)(((st.nfr + 7) & ~7) * 2);
-        sub_expect_tx(&bar, (unsigned)st.Lcount * 8u + (unsigned)st.tgt_count * 2u + nb_pu);
-        sub_bulk_g2s(Ls, fac + st.Lbeg, (unsigned)st.Lcount * 8u, &bar);
-        if (st.tgt_count > 0) sub_bulk_g2s(tg, tgt_all + st.tgt_beg, (unsigned)st.tgt_count * 2u, &bar);
-        sub_bulk_g2s(pu, pu_all + st.pu_beg, nb_pu, &bar);
-    }
-    // the subtree's segment of the right-hand side and of the local pivot permutations, underneath the bulk copies
-    for (int i = tid; i < st.ncols; i += B200_SUB_THREADS) xs[i] = y[st.cbeg + i], lps[i] = (unsigned char)lperm[st.cbeg + i];
-    for (int i = tid; i < st.next; i += B200_SUB_THREADS) xs[st.ncols + i] = 0.0;
-    __syncthreads(); // (also publishes the mbarrier initialisation)
-    mbar_wait(&bar, 0);
-    int Lo = 0, c0 = 0, to = 0;
-    for (int fr = 0; fr < st.nfr; fr++) {
-        const uchar2 q = pu[fr];
-        const int p = q.x, u = q.y, f = p + u;
-        const double* L = Ls + Lo;
-        if (warp == 0) { // z1 = inv(L11) P t1 by forward substitution: lane = row, L11 unit lower triangular
-            double tv = lane < p ? xs[c0 + lps[c0 + lane]] : 0.0;
-            for (int m = 0; m + 1 < p; m++) {
-                const double zm = __shfl_sync(0xffffffffu, tv, m);
-                if (lane > m && lane < p) tv -= L[lane + m * f] * zm;
-            }
-            __syncwarp();
-            if (lane < p) xs[c0 + lane] = tv;
-        }
-        __syncthreads();
-        // update rows: one thread per row (u <= 96: at most two rows per thread), one multiply-add per stored entry
-        for (int i = tid; i < u; i += B200_SUB_THREADS) {
-            const double* row = L + p + i;
-            double a0 = 0.0, a1 = 0.0;
-            int k = 0;
-            for (; k + 1 < p; k += 2) a0 += row[k * f] * xs[c0 + k], a1 += row[(k + 1) * f] * xs[c0 + k + 1];
-            if (k < p) a0 += row[k * f] * xs[c0 + k];
-            xs[tg[to + i]] -= a0 + a1; // the rows of one front are distinct: no conflicting updates
-        }
-        __syncthreads();
-        Lo += sub_round4(f * p), c0 += p, to += u;
-    }
-    for (int i = tid; i < st.ncols; i += B200_SUB_THREADS) zv[st.cbeg + i] = xs[i];
-    for (int i = tid; i < st.next; i += B200_SUB_THREADS) wv[st.root_rows + i] = xs[st.ncols + i];
-}
-
-// backward:  x = U^{-1} z  on the subtree's columns, given the solution at the root's update rows (fronts above)
-__global__ void __launch_bounds__(B200_SUB_THREADS) k_bwd_stree(const SubtreeDev* __restrict__ trees, const double* __restrict__ fac,
-                                                                const double* __restrict__ dpack, const unsigned short* __restrict__ tgt_all,
-                                                                const uchar2* __restrict__ pu_all, const int* __restrict__ rows_all,
-                                                                const double* __restrict__ zv, double* __restrict__ xp) {
-    extern __shared__ __align__(16) unsigned char smraw[];
-    __shared__ __align__(8) unsigned long long bar;
-    __shared__ double red[8][32];
-    const SubtreeDev st = trees[blockIdx.x];
-    double* Us = reinterpret_cast<double*>(smraw); // U region, then the packed pivot blocks
-    double* xs = Us + st.pan;
-    unsigned short* tg = reinterpret_cast<unsigned short*>(xs + sub_xs_doubles(st.ncols, st.next));
-    uchar2* pu = reinterpret_cast<uchar2*>(tg + st.tgt_count);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double* Ds = Us + st.Ucount;
-    if (tid == 0) {
-        mbar_init(&bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const unsigned nb_pu = (unsigned)(((st.nfr + 7) & ~7) * 2);
-        sub_expect_tx(&bar, (unsigned)(st.Ucount + st.Dcount) * 8u + (unsigned)st.tgt_count * 2u + nb_pu);
-        if (st.Ucount > 0) sub_bulk_g2s(Us, fac + st.Ubeg, (unsigned)st.Ucount * 8u, &bar);
-        sub_bulk_g2s(Ds, dpack + st.Dbeg, (unsigned)st.Dcount * 8u, &bar);
-        if (st.tgt_count > 0) sub_bulk_g2s(tg, tgt_all + st.tgt_beg, (unsigned)st.tgt_count * 2u, &bar);
-        sub_bulk_g2s(pu, pu_all + st.pu_beg, nb_pu, &bar);
-    }
-    for (int i = tid; i < st.ncols; i += B200_SUB_THREADS) xs[i] = zv[st.cbeg + i];
-    for (int i = tid; i < st.next; i += B200_SUB_THREADS) xs[st.ncols + i] = xp[rows_all[st.root_rows + i]];
-    __syncthreads();
-    mbar_wait(&bar, 0);
-    // offsets of the LAST front: the walk runs from the root down to the leaves
-    int Uo = st.Ucount, Do = st.Dcount, c0 = st.ncols, to = 0;
-    for (int fr = 0; fr < st.nfr; fr++) to += pu[fr].y; // (a few hundred fronts at most; every thread keeps its own copy)
-    for (int fr = st.nfr - 1; fr >= 0; fr--) {
-        const uchar2 q = pu[fr];
-        const int p = q.x, u = q.y;
-        Uo -= sub_round4(u * p), Do -= sub_round4(p * p), c0 -= p, to -= u;
-        const double* U = Us + Uo; // u x p, column-major: U[j + k*u] = U12(k, j)
-        const double* D = Ds + Do; // p x p pivot block: upper triangle incl. diagonal = U11
-        // t = z1 - U12 x2: thread (k, part) sums the entries j = part, part + nparts, ... of column k.  Lanes run over k, so a
-        // plain j would make them stride u doubles through shared memory (a 32-way bank conflict for u = 16): every column
-        // starts its walk at a different row (skew) so that the lane stride u + skew is odd
-        int p2 = 1;
-        while (p2 < p) p2 <<= 1;
-        const int nparts = min(B200_SUB_THREADS / p2, 8);
-        const int k = tid & (p2 - 1), part = tid / p2;
-        if (k < p && part < nparts && u > 0) {
-            const int skew = (u & 1) ? 0 : 1;
-            double acc = 0.0;
-            int jj = (part + k * skew) % u;
-            for (int it = part; it < u; it += nparts) {
-                acc += U[jj + k * u] * xs[tg[to + jj]];
-                jj += nparts;
-                if (jj >= u) jj -= u;
-            }
-            red[part][k] = acc;
-        }
-        __syncthreads();
-        if (warp == 0) { // x1 = inv(U11) t by backward substitution: lane = row
-            double tv = 0.0;
-            if (lane < p) {
-                tv = xs[c0 + lane];
-                if (u > 0)
-                    for (int q2 = 0; q2 < nparts; q2++) tv -= red[q2][lane]; // fixed order: deterministic
-            }
-            const double rd = lane < p ? __drcp_rn(D[lane + lane * p]) : 0.0;
-            for (int m = p - 1; m >= 0; m--) {
-                const double xm = __shfl_sync(0xffffffffu, tv * rd, m); // lane m: its row is complete
-                if (lane == m) tv = xm;
-                if (lane < m) tv -= D[lane + m * p] * xm;
-            }
-            if (lane < p) xs[c0 + lane] = tv;
-        }
-        __syncthreads();
-    }
-    for (int i = tid; i < st.ncols; i += B200_SUB_THREADS) xp[st.cbeg + i] = xs[i];
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// v2 (default): ONE WARP per subtree, panels straight from global memory.
-// The bulk-staged kernels above keep a whole subtree (24 KB on average, 45 KB at most) in shared memory: 4-5 CTAs = 8-10
-// warps per SM, and every front is a chain of dependent shared-memory round trips, two block barriers and a p-step
-// substitution -- measured 1.10 ms per sweep at config 2 against 0.92 ms for the round-1 kernels; a smaller subtree budget
-// (more CTAs per SM) was faster, i.e. the walk is bound by the number of fronts in flight per SM, not by bytes.  Here a
-// subtree needs only its solution segment xs in shared memory (<= 8 KB), so 28 warps = 28 subtrees are resident per SM; a
-// warp issues all loads of a front at once (coalesced: lanes = rows), the other warps hide their latency, and nothing but
-// __syncwarp orders the walk.  Per front and warp: ~100 instructions (the round-1 kernels: ~900 on two warps).
-// ---------------------------------------------------------------------------------------------------------------------
 // predicated global load that the compiler cannot sink next to its first use: ncu (profiles/r2e) showed the backward walk
 // issuing load -> multiply -> load -> multiply (eight exposed DRAM latencies per front) because the front end had merged the
 // batched loads back into the loop that consumes them.  asm volatile keeps the loads in program order, back to back.

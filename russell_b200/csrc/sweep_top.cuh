@@ -360,360 +360,4 @@ __global__ void __launch_bounds__(256, 3) k_bwd_top3(const SolveItem* __restrict
     }
 }
 
-
-// =====================================================================================================================
-// LL variants (default): the data IS the flag.
-// k_fwd_top2 / k_bwd_top3 signal through completion counters: producer = stores + __threadfence + atomicAdd, consumer =
-// polling a counter + __threadfence + loads.  The per-item trace (profiles/r02i_trace_top_sweep_3ctas.txt) shows 3.3 us
-// (forward) and 5.2 us (backward) per chain level for ~0.5 us of arithmetic: two device-scope fences and three dependent
-// L2 round trips per hop.  Here every value that crosses CTAs travels as a 16-byte line {lo32 | epoch, hi32 | epoch}
-// written by ONE volatile vector store (each 8-byte half is single-copy atomic; the NCCL "LL" protocol) and the consumer
-// polls the line itself until both tags carry the epoch of the current sweep: no fence, no counter, one L2 round trip per
-// hop.  The epoch (a per-handle counter bumped once per sweep) makes stale lines of earlier sweeps invisible, so nothing is
-// ever reset.  Items are still handed out by atomic tickets in dependency order (see the progress guarantee at the top).
-//   forward : update vectors of the top fronts live in wll (never in wv); children below the region are read from wv
-//   backward: partial dot products live in pll, solution entries of the top columns in xll (+ plain xp for the subtree
-//             kernels and the caller)
-// =====================================================================================================================
-__device__ __forceinline__ bool ll_load(const ulonglong2* p, const unsigned epoch, double& out) {
-    unsigned long long a, b;
-    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
-    if ((unsigned)(a >> 32) != epoch || (unsigned)(b >> 32) != epoch) return false;
-    out = __longlong_as_double((long long)((b << 32) | (a & 0xffffffffull)));
-    return true;
-}
-__device__ __forceinline__ void ll_store(ulonglong2* p, const unsigned epoch, const double v) {
-    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
-    const unsigned long long a = ((unsigned long long)epoch << 32) | (bits & 0xffffffffull);
-    const unsigned long long b = ((unsigned long long)epoch << 32) | (bits >> 32);
-    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
-}
-// bounded poll of one line; sleeps between probes when `relaxed` (the sentinel poll of one thread per CTA)
-__device__ __forceinline__ bool ll_wait(const ulonglong2* p, const unsigned epoch, double& out, int* abort_flag, const bool relaxed) {
-    for (int it = 0; it < (1 << 23); it++) {
-        if (ll_load(p, epoch, out)) return true;
-        if (relaxed && it > 8) __nanosleep(it > 64 ? 200 : 40);
-        if ((it & 1023) == 1023 && *(volatile int*)abort_flag) return false;
-    }
-    atomicExch(abort_flag, 1);
-    return false;
-}
-
-// record layout per (item, child): B200_TOP_REC ints as before; [7] = first line of the child's update vector in wll, or -1
-// when the child lies below the persistent region (its vector is complete in wv before this kernel starts)
-__global__ void __launch_bounds__(256, 3) k_fwd_top_ll(const SolveItem* __restrict__ items, int nitems, const NodeDev* __restrict__ nodes,
-                                                    const int* __restrict__ rel_all, const double* __restrict__ fac,
-                                                    const double* __restrict__ dinv, const int* __restrict__ lperm,
-                                                    const int* __restrict__ ranges, const int* __restrict__ wll_off,
-                                                    const double* __restrict__ y, double* __restrict__ zv, const double* __restrict__ wv,
-                                                    ulonglong2* __restrict__ wll, int* __restrict__ epoch_ptr, int* __restrict__ abort_flag,
-                                                    unsigned long long* __restrict__ trace) {
-    const unsigned epoch = (unsigned)*(volatile int*)epoch_ptr;
-    extern __shared__ double smt[];
-    double* Ps = smt; // this slice of L21: Ps[k * SLICE + r]
-    __shared__ double t1[B200_MAXP], z[B200_MAXP], wloc[B200_SLICE], wpart[B200_SLICE];
-    __shared__ int s_next;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const int gk = tid >> 2, gpart = tid & 3; // GEMV layout: four threads per row
-    int* ticket = epoch_ptr + 1;
-    if (tid == 0) s_next = atomicAdd(ticket, 1);
-    __syncthreads();
-    for (int itx = s_next; itx < nitems; itx = s_next) {
-        int nxt = 0;
-        if (tid == 0) nxt = atomicAdd(ticket, 1); // the next item's ticket is fetched underneath this item's work
-        const SolveItem it = items[itx];
-        const NodeDev nd = nodes[it.node];
-        const int p = nd.p, u = nd.u, nchild = nd.nchild;
-        const long long f = (long long)p + u;
-        {
-            const int r = tid & (B200_SLICE - 1), g = tid >> 7;
-            if (r < it.nrows) {
-                const double* src = fac + nd.Loff + p + it.r0 + r;
-                for (int k = g; k < p; k += 2) cp_async8(Ps + k * B200_SLICE + r, src + (long long)k * f);
-            }
-        }
-        double dreg[16]; // row gk of inv(L11), columns gpart, gpart+4, ... (< gk): loaded before the wait
-        {
-            const double* D = dinv + nd.Doff;
-#pragma unroll
-            for (int q = 0; q < 16; q++) {
-                const int m = gpart + 4 * q;
-                dreg[q] = (gk < p && m < gk) ? D[gk + (long long)m * p] : 0.0;
-            }
-        }
-        if (trace && tid == 0) trace[4 * (long long)itx] = gtime();
-        const int lp = tid < p ? lperm[nd.c0 + tid] : 0;
-        const long long my_out = (long long)wll_off[it.node] + it.r0;
-        if (tid < p) t1[tid] = y[nd.c0 + tid];
-        if (tid < B200_SLICE) wloc[tid] = 0.0;
-        const int lo = p + it.r0;
-        const int* rg0 = ranges + it.rng;
-        // per child: this thread's head entry and slice entry (relative index + where the value comes from)
-        int ih[B200_TOP_EC], is[B200_TOP_EC];
-        const double *ph[B200_TOP_EC], *ps[B200_TOP_EC];   // plain source (child below the region) ...
-        const ulonglong2 *qh[B200_TOP_EC], *qs[B200_TOP_EC]; // ... or LL source
-#pragma unroll
-        for (int e = 0; e < B200_TOP_EC; e++) {
-            ih[e] = -1, is[e] = -1, ph[e] = nullptr, ps[e] = nullptr, qh[e] = nullptr, qs[e] = nullptr;
-            if (e < nchild) {
-                const int* rg = rg0 + B200_TOP_REC * e;
-                const int nhead = rg[0], a = rg[1], b = rg[2], llo = rg[7];
-                const long long wofs = ((long long)rg[5] << 32) | (long long)(unsigned)rg[4];
-                if (tid < nhead) {
-                    ih[e] = rel_all[wofs + tid];
-                    if (llo >= 0) qh[e] = wll + llo + tid;
-                    else ph[e] = wv + wofs + tid;
-                }
-                if (a + tid < b) {
-                    is[e] = rel_all[wofs + a + tid] - lo;
-                    if (llo >= 0) qs[e] = wll + llo + a + tid;
-                    else ps[e] = wv + wofs + a + tid;
-                }
-            }
-        }
-        // ---- stage 1: one thread per child polls that child's first needed line (with back-off): the CTA sleeps cheaply
-        int ok = 1;
-        for (int e = tid; e < nchild; e += nt) {
-            const int* rg = rg0 + B200_TOP_REC * e;
-            if (rg[7] >= 0) {
-                const int first = rg[0] > 0 ? 0 : rg[1];
-                if (rg[0] > 0 || rg[2] > rg[1]) {
-                    double dummy;
-                    ok &= ll_wait(wll + rg[7] + first, epoch, dummy, abort_flag, true) ? 1 : 0;
-                }
-            }
-        }
-        if (!__syncthreads_and(ok)) return;
-        if (trace && tid == 0) trace[4 * (long long)itx + 1] = gtime();
-        // ---- stage 2: every thread fetches its own lines (they are there, or arrive within the same wave)
-        double vh[B200_TOP_EC], vs[B200_TOP_EC];
-#pragma unroll
-        for (int e = 0; e < B200_TOP_EC; e++) {
-            vh[e] = 0.0, vs[e] = 0.0;
-            if (ih[e] >= 0) {
-                if (qh[e]) ok &= ll_wait(qh[e], epoch, vh[e], abort_flag, false) ? 1 : 0;
-                else vh[e] = __ldcg(ph[e]);
-            }
-            if (is[e] >= 0) {
-                if (qs[e]) ok &= ll_wait(qs[e], epoch, vs[e], abort_flag, false) ? 1 : 0;
-                else vs[e] = __ldcg(ps[e]);
-            }
-        }
-#pragma unroll
-        for (int e = 0; e < B200_TOP_EC; e++)
-            if (e < nchild) { // children are applied one after the other (fixed order: deterministic sums)
-                if (ih[e] >= 0) t1[ih[e]] += vh[e];
-                if (is[e] >= 0) wloc[is[e]] += vs[e];
-                __syncthreads();
-            }
-        for (int e = B200_TOP_EC; e < nchild; e++) { // fronts with many children (rare at the top of the tree)
-            const int* rg = rg0 + B200_TOP_REC * e;
-            const int nhead = rg[0], a = rg[1], b = rg[2], llo = rg[7];
-            const long long wofs = ((long long)rg[5] << 32) | (long long)(unsigned)rg[4];
-            const int* rel = rel_all + wofs;
-            for (int i = tid; i < nhead; i += nt) {
-                double val;
-                if (llo >= 0) ok &= ll_wait(wll + llo + i, epoch, val, abort_flag, false) ? 1 : 0;
-                else val = __ldcg(wv + wofs + i);
-                t1[rel[i]] += val;
-            }
-            for (int i = a + tid; i < b; i += nt) {
-                double val;
-                if (llo >= 0) ok &= ll_wait(wll + llo + i, epoch, val, abort_flag, false) ? 1 : 0;
-                else val = __ldcg(wv + wofs + i);
-                wloc[rel[i] - lo] += val;
-            }
-            __syncthreads();
-        }
-        double tp = 0.0;
-        if (tid < p) tp = t1[lp];
-        cp_async_wait_all();
-        if (!__syncthreads_and(ok)) return;
-        if (trace && tid == 0) trace[4 * (long long)itx + 3] = gtime();
-        if (tid < p) t1[tid] = tp;
-        __syncthreads();
-        {   // z = inv(L11) t1: four threads per row (fixed partition + fixed shuffle order: deterministic)
-            double s = 0.0;
-#pragma unroll
-            for (int q = 0; q < 16; q++) {
-                const int m = gpart + 4 * q;
-                if (gk < p && m < gk) s += dreg[q] * t1[m];
-            }
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            if (gk < p && gpart == 0) {
-                s += t1[gk];
-                z[gk] = s;
-                if (it.slice == 0) zv[nd.c0 + gk] = s;
-            }
-        }
-        __syncthreads();
-        {
-            const int r = tid & (B200_SLICE - 1), h = tid >> 7;
-            const int kh = (p + 1) >> 1;
-            const int kbeg = h * kh, kend = min(p, kbeg + kh);
-            double s = 0.0;
-            if (r < it.nrows)
-                for (int k = kbeg; k < kend; k++) s += Ps[k * B200_SLICE + r] * z[k];
-            if (h == 1) wpart[r] = s;
-            if (tid == 0) s_next = nxt; // (every thread read the previous value before this item's first barrier)
-            __syncthreads();
-            if (h == 0 && r < it.nrows) ll_store(wll + my_out + r, epoch, wloc[r] - (s + wpart[r])); // value and flag in one store
-        }
-        if (trace && tid == 0) trace[4 * (long long)itx + 2] = gtime();
-        __syncthreads(); // shared buffers are reused by the next item
-    }
-}
-
-// SolveItem.pad = 1: no child of this front lies in the persistent region, so nobody evaluates its pivot block for it: the
-// last of its slices to finish (ticket on bdone) does, off the critical path.
-__global__ void __launch_bounds__(256, 3) k_bwd_top_ll(const SolveItem* __restrict__ items, int nitems, const NodeDev* __restrict__ nodes,
-                                                    const int* __restrict__ rows_all, const double* __restrict__ fac,
-                                                    const double* __restrict__ dinv, const double* __restrict__ zv,
-                                                    double* __restrict__ xp, ulonglong2* __restrict__ xll, ulonglong2* __restrict__ pll,
-                                                    const int* __restrict__ node_slot, int* __restrict__ bdone,
-                                                    int* __restrict__ epoch_ptr, int* __restrict__ abort_flag,
-                                                    unsigned long long* __restrict__ trace) {
-    const unsigned epoch = (unsigned)*(volatile int*)epoch_ptr;
-    extern __shared__ double smt[];
-    double* Ps = smt; // this slice of the U panel: Ps[k * SLICE + r]
-    __shared__ double t[B200_MAXP], xpar[B200_MAXP], x2[B200_SLICE];
-    __shared__ int s_flag, s_next;
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-    const int gk = tid >> 2, gpart = tid & 3; // GEMV layout: four threads per row
-    int* ticket = epoch_ptr + 2;
-    if (tid == 0) s_next = nitems - 1 - atomicAdd(ticket, 1);
-    __syncthreads();
-    for (int itx = s_next; itx >= 0; itx = s_next) {
-        int nxt = 0;
-        if (tid == 0) nxt = nitems - 1 - atomicAdd(ticket, 1);
-        const SolveItem it = items[itx];
-        const NodeDev nd = nodes[it.node];
-        const int p = nd.p, u = nd.u;
-        const int nsl = slices_of(u);
-        {
-            const int r = tid & (B200_SLICE - 1), g = tid >> 7;
-            if (r < it.nrows) {
-                const double* src = fac + nd.Uoff + it.r0 + r;
-                for (int k = g; k < p; k += 2) cp_async8(Ps + k * B200_SLICE + r, src + (long long)k * u);
-            }
-        }
-        // ---- everything static is loaded before the wait: own row indices and slot, the parent's descriptor, z and inv(U11)
-        const int par = nd.pad;
-        const int rr = tid < it.nrows ? rows_all[nd.rows_ptr + it.r0 + tid] : -1;
-        const int slot = node_slot[it.node];
-        int pp = 0, nslp = 0, slotp = 0, c0p = 0;
-        double dreg[16], zp = 0.0;
-#pragma unroll
-        for (int q = 0; q < 16; q++) dreg[q] = 0.0;
-        if (par >= 0) {
-            const NodeDev pd = nodes[par];
-            pp = pd.p, nslp = slices_of(pd.u), slotp = node_slot[par], c0p = pd.c0;
-            const double* Dp = dinv + pd.Doff;
-#pragma unroll
-            for (int q = 0; q < 16; q++) {
-                const int m = gk + gpart + 4 * q;
-                if (gk < pp && m < pp) dreg[q] = Dp[gk + (long long)m * pp];
-            }
-            if (tid < pp) zp = zv[c0p + tid];
-        }
-        if (trace && tid == 0) trace[4 * (long long)itx] = gtime();
-        // ---- stage 1: one thread polls the first partial line of the parent (with back-off)
-        int ok = 1;
-        if (tid == 0 && par >= 0) {
-            double dummy;
-            ok = ll_wait(pll + (long long)slotp * B200_MAXP, epoch, dummy, abort_flag, true) ? 1 : 0;
-        }
-        if (!__syncthreads_and(ok)) return;
-        if (trace && tid == 0) trace[4 * (long long)itx + 1] = gtime();
-        // ---- stage 2: the parent's partials (one line per slice and pivot) and the solution entries of older ancestors
-        const bool in_par = rr >= c0p && rr < c0p + pp; // (pp == 0 without a parent)
-        double xv = 0.0;
-        if (rr >= 0 && !in_par) ok &= ll_wait(xll + rr, epoch, xv, abort_flag, false) ? 1 : 0;
-        if (par >= 0) {
-            if (tid < pp) {
-                double sacc = zp;
-                const ulonglong2* base = pll + (long long)slotp * B200_MAXP + tid;
-                for (int sl = 0; sl < nslp; sl++) { // subtracted in slice order (deterministic)
-                    double v;
-                    ok &= ll_wait(base + (long long)sl * B200_MAXP, epoch, v, abort_flag, false) ? 1 : 0;
-                    sacc -= v;
-                }
-                t[tid] = sacc;
-            }
-            __syncthreads();
-            {   // x1(parent) = inv(U11) t, four threads per row, inv(U11) from registers
-                double sacc = 0.0;
-#pragma unroll
-                for (int q = 0; q < 16; q++) {
-                    const int m = gk + gpart + 4 * q;
-                    if (gk < pp && m < pp) sacc += dreg[q] * t[m];
-                }
-                sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
-                sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
-                if (gk < pp && gpart == 0) {
-                    xpar[gk] = sacc;
-                    if (it.slice == 0) { // for the descendants (line) and for the subtree kernels / the caller (plain)
-                        ll_store(xll + c0p + gk, epoch, sacc);
-                        xp[c0p + gk] = sacc;
-                    }
-                }
-            }
-        }
-        if (!__syncthreads_and(ok)) return;
-        if (rr >= 0) x2[tid] = in_par ? xpar[rr - c0p] : xv;
-        cp_async_wait_all();
-        __syncthreads();
-        ulonglong2* part = pll + ((long long)slot + it.slice) * B200_MAXP;
-        for (int k = warp; k < p; k += nwarps) {
-            const double* col = Ps + k * B200_SLICE;
-            double sacc = 0.0;
-            for (int j = lane; j < it.nrows; j += 32) sacc += col[j] * x2[j];
-            for (int off = 16; off > 0; off >>= 1) sacc += __shfl_down_sync(0xffffffffu, sacc, off);
-            if (lane == 0) ll_store(part + k, epoch, sacc); // the children of this front may start
-        }
-        if (trace && tid == 0) trace[4 * (long long)itx + 2] = gtime();
-        if (it.pad) { // no child in the region: the last slice of this front evaluates its own pivot block
-            __syncthreads();
-            if (tid == 0) {
-                const int old = atomicAdd(&bdone[it.node], 1);
-                s_flag = (old + 1 == (int)epoch * nsl);
-            }
-            __syncthreads();
-            if (s_flag) {
-                if (tid < p) {
-                    double sacc = zv[nd.c0 + tid];
-                    const ulonglong2* base = pll + (long long)slot * B200_MAXP + tid;
-                    for (int sl = 0; sl < nsl; sl++) {
-                        double v;
-                        ok &= ll_wait(base + (long long)sl * B200_MAXP, epoch, v, abort_flag, false) ? 1 : 0;
-                        sacc -= v;
-                    }
-                    t[tid] = sacc;
-                }
-                const double* Dv = dinv + nd.Doff;
-                double dv[16];
-#pragma unroll
-                for (int q = 0; q < 16; q++) {
-                    const int m = gk + gpart + 4 * q;
-                    dv[q] = (gk < p && m < p) ? Dv[gk + (long long)m * p] : 0.0;
-                }
-                __syncthreads();
-                double sacc = 0.0;
-#pragma unroll
-                for (int q = 0; q < 16; q++) {
-                    const int m = gk + gpart + 4 * q;
-                    if (gk < p && m < p) sacc += dv[q] * t[m];
-                }
-                sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
-                sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
-                if (gk < p && gpart == 0) xp[nd.c0 + gk] = sacc;
-            }
-        }
-        if (tid == 0) s_next = nxt;
-        __syncthreads(); // shared buffers are reused by the next item
-    }
-}
-
 } // namespace b200

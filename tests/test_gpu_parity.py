@@ -256,18 +256,13 @@ def test_factor_panels_match_host_walk_lower_and_saddle():
     _factor_compare(rb.CooMatrix.from_triplets(n, n, ai, aj, ax), {})
 
 
-@pytest.mark.parametrize("opts", [{"diag_variant": 0}, {"diag_variant": 1}, {"diag_variant": 2}, {"use_fused": 0}, {"use_top": 0},
-                                  {"fuse_chain": 0}, {"schur_variant": 0, "use_fused": 0}, {"panel_width": 16, "use_fused": 0},
-                                  {"diag_variant": 2, "use_fused": 0}, {"diag_variant": 2, "panel_width": 20, "use_fused": 0},
-                                  {"diag_variant": 2, "panel_width": 37, "use_fused": 0}, {"panel_variant": 1},
+@pytest.mark.parametrize("opts", [{"diag_variant": 0}, {"use_fused": 0}, {"use_top": 0}, {"fuse_chain": 0}, {"schur_variant": 0, "use_fused": 0},
+                                  {"panel_width": 16, "use_fused": 0}, {"diag_variant": 0, "use_fused": 0}, {"diag_variant": 0, "panel_width": 20, "use_fused": 0},
+                                  {"diag_variant": 0, "panel_width": 37, "use_fused": 0}, {"panel_variant": 1},
                                   {"panel_variant": 1, "use_fused": 0, "panel_width": 37}, {"panel_variant": 1, "use_fused": 0, "panel_width": 8},
-                                  {"overlap_invert": 0}, {"overlap_invert": 1, "use_graph": 0}, {"diag_variant": 3}, {"panel_variant": 2}, {"panel_variant": 0},
-                                  {"lookahead": 0}, {"lookahead": 1, "use_graph": 0}, {"lookahead": 2}, {"diag_variant": 4}, {"fused_variant": 0},
-                                  {"fused_variant": 1, "fused_maxf": 64}, {"fused_variant": 1, "fused_maxf": 20, "panel_width": 13},
-                                  {"diag_variant": 4, "use_fused": 0, "panel_width": 37}, {"diag_variant": 4, "use_fused": 0, "panel_width": 5}, {"lookahead": 1, "overlap_invert": 1}, {"invert_variant": 0},
-                                  {"invert_variant": 1, "use_fused": 0, "panel_width": 37}, {"invert_variant": 1, "use_fused": 0, "panel_width": 5},
-                                  {"panel_variant": 2, "use_fused": 0, "panel_width": 37}, {"panel_variant": 2, "use_fused": 0, "panel_width": 5},
-                                  {"diag_variant": 3, "use_fused": 0, "panel_width": 37}, {"diag_variant": 3, "use_fused": 0, "panel_width": 5},
+                                  {"panel_variant": 0}, {"panel_variant": 0, "use_fused": 0, "panel_width": 37}, {"use_graph": 0}, {"diag_variant": 4},
+                                  {"fused_variant": 0}, {"fused_variant": 1, "fused_maxf": 64}, {"fused_variant": 1, "fused_maxf": 20, "panel_width": 13},
+                                  {"diag_variant": 4, "use_fused": 0, "panel_width": 37}, {"diag_variant": 4, "use_fused": 0, "panel_width": 5},
                                   {"asm_variant": 0}, {"asm_variant": 0, "use_fused": 0, "panel_width": 13}, {"asm_variant": 1, "use_fused": 0, "panel_width": 13},
                                   {"nd_leaf": 96}, {"schur_variant": 2, "ozaki_min_u": 64}, {"schur_variant": 2, "ozaki_min_u": 100, "panel_width": 37},
                                   {"schur_variant": 2, "ozaki_min_u": 1, "use_fused": 0, "panel_width": 20}])
@@ -301,32 +296,26 @@ def _raw_factors(coo, opts):
     return fac, lperm
 
 
-def test_blocked_pivot_block_kernel_is_bit_identical_to_the_rank1_kernel():
-    # k_diag_blk (warp-blocked) performs the same operations per entry in the same order as k_diag_reg: same bits
+def test_register_kernels_are_bit_identical_to_the_shared_memory_fallbacks():
+    # k_diag_w8 (register-resident, one warp per column group) performs the same operations per entry in the same order as
+    # the shared-memory LU k_diag; k_front_fused_w8 vs k_front_fused and k_panel_warp vs k_panel likewise: same bits
     rng = np.random.default_rng(3)
     n, ai, aj, ax = helpers.convection_diffusion_triplets(120)
     ax = ax * (1.0 + 0.3 * rng.standard_normal(len(ax)))
     coo = rb.CooMatrix.from_triplets(n, n, ai, aj, ax)
     for extra in ({}, {"use_fused": 0}, {"use_fused": 0, "panel_width": 29}):
-        f1, p1 = _raw_factors(coo, dict(extra, diag_variant=1))
-        f2, p2 = _raw_factors(coo, dict(extra, diag_variant=2))
-        assert np.array_equal(p1, p2)
-        assert np.array_equal(f1, f2)
-        f5, p5 = _raw_factors(coo, dict(extra, diag_variant=3))
-        assert np.array_equal(p1, p5)
-        assert np.array_equal(f1, f5)
+        f1, p1 = _raw_factors(coo, dict(extra, diag_variant=0))
         f6, p6 = _raw_factors(coo, dict(extra, diag_variant=4))
         assert np.array_equal(p1, p6)
         assert np.array_equal(f1, f6)
-    # register-resident fused fronts against the shared-memory ones
     for extra in ({}, {"fused_maxf": 64}, {"fused_maxf": 30, "panel_width": 11}):
         f7, p7 = _raw_factors(coo, dict(extra, fused_variant=0))
         f8, p8 = _raw_factors(coo, dict(extra, fused_variant=1))
         assert np.array_equal(p7, p8)
         assert np.array_equal(f7, f8)
         # thread-per-row triangular panel solves: same operation order as the tile kernel
-        f3, p3 = _raw_factors(coo, dict(extra, diag_variant=1, panel_variant=0))
-        f4, p4 = _raw_factors(coo, dict(extra, diag_variant=1, panel_variant=1))
+        f3, p3 = _raw_factors(coo, dict(extra, panel_variant=0))
+        f4, p4 = _raw_factors(coo, dict(extra, panel_variant=1))
         assert np.array_equal(p3, p4)
         assert np.array_equal(f3, f4)
 
@@ -346,8 +335,6 @@ def test_round1_kernels_are_bit_identical_to_the_ones_they_replace():
         assert np.array_equal(p0, p2) and np.array_equal(f0, f2)
         f3, p3 = _raw_factors(coo, dict(extra, panel_row_max=0, use_leaf_reg=0, asm_variant=1))  # shared-memory extend-add tile
         assert np.array_equal(p0, p3) and np.array_equal(f0, f3)
-        f4, p4 = _raw_factors(coo, dict(extra, panel_row_max=0, use_leaf_reg=1, small_reg_maxf=32))  # register kernel with children
-        assert np.array_equal(p0, p4) and np.array_equal(f0, f4)
 
 
 @pytest.mark.parametrize("k,lower", [(150, False), (400, True)])

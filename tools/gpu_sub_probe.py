@@ -9,7 +9,7 @@ coo = helpers.laplacian_2d_coo(1000)
 b = np.ones(coo.nrow)
 for variant, budget in cases:
     x = np.zeros(coo.nrow)
-    sol = rb.SolverB200(); sol.set_option("sub_variant", variant); sol.set_option("subtree_budget", budget)
+    sol = rb.SolverB200(); sol.set_option("subtree_budget", budget)
     par = rb.LinSolParams(); par.verbose = True
     sol.factorize(coo, par)
     best = 1e9
