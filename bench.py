@@ -309,8 +309,8 @@ def main():
         rc = lib.solver_b200_solve_device(h, d_x.data_ptr(), d_rhs.data_ptr())
         assert rc == 0, rc
         if world > 1:
-            with torch.cuda.stream(stream):  # ordered after the solve on the solver's own stream: no host synchronisation
-                gatherer.gather()  # system r lives on rank r
+            gatherer.gather()  # system r lives on rank r; (the solve above returned synchronised: x is complete)
+            stream.wait_stream(torch.cuda.current_stream())  # the timing events live on the solver's stream: they must see the gather
 
     def step_e2e():
         rc = lib.solver_b200_factorize(h, ctypes.byref(em), ctypes.byref(ep), 0, ctypes.cast(h_vals.data_ptr(), p_f64))
@@ -318,9 +318,9 @@ def main():
         rc = lib.solver_b200_solve(h, ctypes.cast(h_x.data_ptr(), p_f64), ctypes.cast(h_rhs.data_ptr(), p_f64), 0)
         assert rc == 0, rc
         if world > 1:
-            with torch.cuda.stream(stream):
-                d_x.copy_(h_x, non_blocking=True)
-                gatherer.gather()
+            d_x.copy_(h_x, non_blocking=True)
+            gatherer.gather()
+            stream.wait_stream(torch.cuda.current_stream())
 
     def get_stats():
         out = np.zeros(len(rb.SolverB200.STAT_NAMES))
@@ -432,9 +432,22 @@ def main():
                                               "sequential: %.2f s each (cold, with ordering: %.2f s), rel.residual %.1e; STAND-IN for UMFPACK, which "
                                               "is not installed on the box" % (k, k, t_warm, t_cold, res_cpu)}
         print(json.dumps(line), flush=True)
-    lib.solver_b200_drop(h)
+    # tear down in dependency order: the gather buffers were used on the solver's stream (torch's allocator records an event
+    # on that stream when it frees them), and NCCL's last collectives were enqueued there -- both must go before
+    # solver_b200_drop destroys the stream
+    import gc
+
+    torch.cuda.synchronize()
+    del d_x
+    gatherer.block = gatherer.out = gatherer.index = None
+    del gatherer
+    gc.collect()
+    torch.cuda.synchronize()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    torch.cuda.synchronize()
+    lib.solver_b200_drop(h)
 
 
 if __name__ == "__main__":

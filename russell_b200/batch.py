@@ -39,8 +39,8 @@ class SolutionGatherer:
     """The per-step gather of bench.py without per-step allocations or Python loops (round-1 review: three fresh tensors,
     a list-form all_gather and 2N copies per step cost 0.33 ms of a 9 ms step at N = 8).  Buffers are allocated once;
     `block` is this rank's slot block -- a solver can write its solution straight into `block[slot]` -- and `gather()`
-    issues ONE all_gather_into_tensor on the CURRENT stream (call it under `torch.cuda.stream(solver_stream)` so that it
-    is ordered after the solve without a cross-stream synchronisation).  With one system per rank the gathered tensor is
+    issues ONE all_gather_into_tensor on torch's current stream (the C-ABI solve calls return synchronised, so the block is
+    complete; a caller that times on another stream lets that stream wait for this one).  With one system per rank the gathered tensor is
     already in system order; otherwise a precomputed index restores it."""
 
     def __init__(self, nsys, world, rank, n, dtype=torch.float64, device="cpu"):
