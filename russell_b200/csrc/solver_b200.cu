@@ -72,6 +72,7 @@ struct LevelLists {
     std::vector<size_t> asm_smem;   // per level: largest tile (bytes) of k_assemble_tile
     // schur_variant 2: fronts with u >= ozaki_min_u take the tcgen05 kernel (ozaki_tc.cuh)
     std::vector<int> oz_split_ptr, oz_item_ptr, oz_rows_max; // nlevels+1 / nlevels+1 / nlevels
+    std::vector<int> diag_cnt; // per level: big fronts that need their own pivot-block launch (listed first in their class)
     size_t oz_tile_bytes = 0, oz_scales = 0;                 // arena sizes (largest level)
 };
 
@@ -99,6 +100,7 @@ struct InterfaceB200 {
     int use_fused = 1;     // fronts with f <= B200_FUSED_MAXF go through k_front_fused
     int fused_maxf = 48;   // fronts above this order take the multi-kernel path (measured optimum at config 2)
     int fuse_chain = 1;    // chain links receive their child's Schur complement directly (no k_assemble pass)
+    int fuse_diag = 1;     // ... and the Schur CTA of tile (0, 0) factorizes the parent's pivot block right away (look-ahead)
     int diag_variant = 4;  // 0 = shared-memory LU (k_diag), 1 = register-resident LU with implicit pivoting (k_diag_reg)
     int nrefine = 2;
     double ir_tol = 1e-11;
@@ -331,13 +333,18 @@ void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::ve
             if (f <= SC_MAXF[c]) return c;
         return NSC - 1;
     };
+    std::vector<char> diag_fused(P.nnodes, 0); // pivot block factorized by the chain child's Schur CTA (set at the child's level)
+    lv.diag_cnt.assign(P.nlevels, 0);
     for (int l = 0; l < P.nlevels; l++) {
         size_t lvl_tiles = 0, lvl_scales = 0; // the sliced operands live for one level only
         for (int c = 0; c <= NFC; c++) {
+            for (int pass = 0; pass < (c == NFC ? 2 : 1); pass++) // big fronts: those that need a pivot-block launch first
             for (int e = P.level_ptr[l]; e < P.level_ptr[l + 1]; e++) {
                 const int v = P.level_nodes[e];
                 const int f = P.p[v] + P.u[v];
                 if (fclass(f) != c) continue;
+                if (c == NFC && (diag_fused[v] != 0) != (pass == 1)) continue;
+                if (c == NFC && pass == 0) lv.diag_cnt[l]++;
                 fact_nodes.push_back(v);
                 if (c < NFC) {
                     size_t& sm = lv.fused_smem[(size_t)l * NFC + c];
@@ -415,8 +422,11 @@ void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::ve
                     int nt = (u + B200_TS - 1) / B200_TS;
                     const int par = P.parent[v];
                     const int fuse_into = (par >= 0 && chain_fused(par)) ? par : -1;
+                    const bool la = fuse_into >= 0 && s->fuse_diag && s->diag_variant == 4 && s->schur_variant >= 1;
+                    if (la) diag_fused[par] = 1;
                     for (int tj = 0; tj < nt; tj++)
-                        for (int ti = 0; ti < nt; ti++) schur_items.push_back({v, ti, tj, fuse_into});
+                        for (int ti = 0; ti < nt; ti++)
+                            schur_items.push_back({v, ti, tj, (la && ti == 0 && tj == 0) ? (fuse_into | B200_SCHUR_DIAG) : fuse_into});
                 }
             }
         }
@@ -482,13 +492,16 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
                 k_assemble<<<na, 256, 0, s->stream>>>(s->d_asm + lv.asm_ptr[l], s->d_nodes, s->d_child_idx, s->d_rel, s->d_asm_ranges, s->d_fac, s->d_cb);
             cnt++;
         }
-        if (s->diag_variant == 4)
-            k_diag_w8<<<nbig, 256, 0, s->stream>>>(s->d_fact_nodes + fp[NFC], s->d_nodes, s->d_fac, s->d_lperm, s->d_upiv, s->d_amax,
-                                                   s->pivot_eps, s->d_counters);
-        else
-            k_diag<<<nbig, 512, smem_diag(W), s->stream>>>(s->d_fact_nodes + fp[NFC], s->d_nodes, s->d_fac,
-                                                           s->d_lperm, s->d_upiv, s->d_amax, s->pivot_eps, s->d_counters);
-        cnt++;
+        const int ndiag = lv.diag_cnt[l]; // big fronts whose pivot block was NOT factorized by their chain child's Schur CTA (they come first)
+        if (ndiag > 0) {
+            if (s->diag_variant == 4)
+                k_diag_w8<<<ndiag, 256, 0, s->stream>>>(s->d_fact_nodes + fp[NFC], s->d_nodes, s->d_fac, s->d_lperm, s->d_upiv, s->d_amax,
+                                                        s->pivot_eps, s->d_counters);
+            else
+                k_diag<<<ndiag, 512, smem_diag(W), s->stream>>>(s->d_fact_nodes + fp[NFC], s->d_nodes, s->d_fac,
+                                                                s->d_lperm, s->d_upiv, s->d_amax, s->pivot_eps, s->d_counters);
+            cnt++;
+        }
         int np = lv.panel_ptr[l + 1] - lv.panel_ptr[l];
         if (np > 0) {
             if (s->panel_variant == 1 && np <= s->panel_row_max) // few rows: the launch is latency bound
@@ -510,7 +523,8 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
         int nsch = lv.schur_ptr[l + 1] - lv.schur_ptr[l];
         if (nsch > 0) {
             if (s->schur_variant >= 1)
-                k_schur_dmma<<<nsch, 256, smem_schur_dmma(), s->stream>>>(s->d_schur + lv.schur_ptr[l], s->d_nodes, s->d_fac, s->d_cb);
+                k_schur_dmma<<<nsch, 256, smem_schur_dmma(), s->stream>>>(s->d_schur + lv.schur_ptr[l], s->d_nodes, s->d_fac, s->d_cb, s->d_lperm, s->d_upiv,
+                                                                          s->d_amax, s->pivot_eps, s->d_counters);
             else
                 k_schur_fma<<<nsch, 256, smem_schur_fma(W), s->stream>>>(s->d_schur + lv.schur_ptr[l], s->d_nodes, s->d_fac, s->d_cb);
             cnt++;
@@ -786,6 +800,7 @@ int32_t solver_b200_set_option(struct InterfaceB200* s, const char* key, double 
     else if (k == "subtree_budget") s->subtree_budget = std::max(0, (int)value);
     else if (k == "diag_variant") s->diag_variant = (int)value;
     else if (k == "fuse_chain") s->fuse_chain = value != 0.0;
+    else if (k == "fuse_diag") s->fuse_diag = value != 0.0;
     else if (k == "top_max_nodes") s->top_max_nodes = std::max(1, (int)value);
     else if (k == "fused_maxf") s->fused_maxf = std::max(0, std::min((int)value, B200_FUSED_MAXF));
     else if (k == "force_no_matching") s->force_no_matching = value != 0.0;
