@@ -26,8 +26,9 @@ unsafe extern "C" {
         pivot_epsilon: f64, refinement_nstep: i32, hybrid_memory_factor: f64, verbose: CcBool, general_symmetric: CcBool,
         positive_definite: CcBool, ndim: i32, nnz_coo: i32, indices_i: *const i32, indices_j: *const i32,
         values: *const Complex64) -> i32;
-    fn complex_solver_b200_factorize_coo(solver: *mut InterfaceComplexB200, effective_matching: *mut i32,
-        effective_pivoting: *mut i32, verbose: CcBool, coo_values: *const Complex64) -> i32;
+    fn complex_solver_b200_factorize_coo_checked(solver: *mut InterfaceComplexB200, effective_matching: *mut i32,
+        effective_pivoting: *mut i32, verbose: CcBool, nnz_coo: i32, indices_i: *const i32, indices_j: *const i32,
+        coo_values: *const Complex64) -> i32;
     fn complex_solver_b200_solve(solver: *mut InterfaceComplexB200, x: *mut Complex64, rhs: *const Complex64, verbose: CcBool) -> i32;
 }
 
@@ -107,8 +108,8 @@ impl ComplexLinSolTrait for ComplexSolverB200 {
         self.factorized = false;
         self.stopwatch.reset();
         let status = unsafe {
-            complex_solver_b200_factorize_coo(self.handle, &mut self.effective_matching, &mut self.effective_pivoting, 0,
-                                              mat.values.as_ptr())
+            complex_solver_b200_factorize_coo_checked(self.handle, &mut self.effective_matching, &mut self.effective_pivoting, 0,
+                                                      to_i32(mat.nnz), mat.indices_i.as_ptr(), mat.indices_j.as_ptr(), mat.values.as_ptr())
         };
         if status != SUCCESSFUL_EXIT {
             return Err(handle_b200_error_code(status));

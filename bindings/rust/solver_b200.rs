@@ -29,8 +29,14 @@ unsafe extern "C" {
     fn solver_b200_initialize_coo(solver: *mut InterfaceB200, ordering: i32, matching: i32, pivoting: i32, pivot_epsilon: f64,
         refinement_nstep: i32, hybrid_memory_factor: f64, verbose: CcBool, general_symmetric: CcBool, positive_definite: CcBool,
         ndim: i32, nnz_coo: i32, indices_i: *const i32, indices_j: *const i32, values: *const f64) -> i32;
-    fn solver_b200_factorize_coo(solver: *mut InterfaceB200, effective_matching: *mut i32, effective_pivoting: *mut i32,
-        verbose: CcBool, coo_values: *const f64) -> i32;
+    // the triplet indices travel with the values, like CsrMatrix::update_from_coo sees them on every call
+    // (russell_sparse/src/solver_cudss.rs:209): same indices -> values only; re-ordered triplets -> slot map rebuilt;
+    // another pattern -> 705
+    fn solver_b200_factorize_coo_checked(solver: *mut InterfaceB200, effective_matching: *mut i32, effective_pivoting: *mut i32,
+        verbose: CcBool, nnz_coo: i32, indices_i: *const i32, indices_j: *const i32, coo_values: *const f64) -> i32;
+    fn solver_b200_rcond(solver: *mut InterfaceB200, rcond: *mut f64) -> i32;
+    fn solver_b200_determinant(solver: *mut InterfaceB200, coefficient: *mut f64, exponent: *mut f64) -> i32;
+    fn solver_b200_get_stats(solver: *mut InterfaceB200, out: *mut f64, n_out: i32) -> i32;
     fn solver_b200_solve(solver: *mut InterfaceB200, x: *mut f64, rhs: *const f64, verbose: CcBool) -> i32;
 }
 
@@ -69,6 +75,8 @@ pub(crate) fn handle_b200_error_code(err: i32) -> StrError {
         300 => "cudaStreamSynchronize failed in the C code (B200)",
         701 => "B200 analysis failed: matrix is structurally singular",
         702 => "B200 analysis failed: invalid CSR structure",
+        907 => "B200 solve failed: iterative refinement failed",
+        705 => "subsequent factorizations must use the same matrix (the COO structure differs from the analysed one)",
         703 => "B200 analysis failed: invalid COO structure (index out of range or empty)",
         704 => "B200 analysis failed: Sym::YesLower requires triplets with j <= i",
         801 => "B200 numeric factorization failed: kernel launch failure",
@@ -195,7 +203,8 @@ impl LinSolTrait for SolverB200 {
         self.factorized = false;
         self.stopwatch.reset();
         let status = unsafe {
-            solver_b200_factorize_coo(self.handle, &mut self.effective_matching, &mut self.effective_pivoting, 0, mat.values.as_ptr())
+            solver_b200_factorize_coo_checked(self.handle, &mut self.effective_matching, &mut self.effective_pivoting, 0,
+                to_i32(mat.nnz), mat.indices_i.as_ptr(), mat.indices_j.as_ptr(), mat.values.as_ptr())
         };
         if status != SUCCESSFUL_EXIT {
             return Err(handle_b200_error_code(status));
@@ -234,6 +243,22 @@ impl LinSolTrait for SolverB200 {
         stats.time_nanoseconds.solve_array.push(self.ns_solve);
         stats.output.effective_matching = if self.effective_matching == 5 { "MaxDiagProduct" } else { "None" }.to_string();
         stats.output.effective_pivoting = "LocalBlock".to_string();
+        // what SolverUMFPACK::update_stats fills from UMFPACK's Info array (solver_umfpack.rs:392-422)
+        let mut st = [0.0_f64; 29]; // B200_STAT_COUNT
+        if self.factorized && unsafe { solver_b200_get_stats(self.handle, st.as_mut_ptr(), 29) } == SUCCESSFUL_EXIT {
+            stats.output.effective_ordering = match st[24] as i32 { 3 => "Amd", 5 => "No", _ => "Metis" }.to_string(); // B200_STAT_EFFECTIVE_ORDERING
+            stats.output.effective_scaling = if st[25] != 0.0 { "Max" } else { "No" }.to_string();                      // B200_STAT_EFFECTIVE_SCALING
+            let mut rcond = 0.0;
+            if unsafe { solver_b200_rcond(self.handle, &mut rcond) } == SUCCESSFUL_EXIT {
+                stats.output.umfpack_rcond_estimate = rcond; // UMFPACK's own definition: min|U_kk| / max|U_kk|
+            }
+            let (mut c, mut e) = (0.0, 0.0);
+            if unsafe { solver_b200_determinant(self.handle, &mut c, &mut e) } == SUCCESSFUL_EXIT {
+                stats.determinant.mantissa_real = c;
+                stats.determinant.base = 10.0;
+                stats.determinant.exponent = e;
+            }
+        }
     }
 
     fn get_ns_init(&self) -> u128 {
