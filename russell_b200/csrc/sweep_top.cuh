@@ -18,6 +18,7 @@
 // (russell_sparse/c_code/interface_umfpack.c:229, interface_cudss.cu:530).
 #pragma once
 #include "kernels.cuh"
+#include "sweep_sub.cuh" // warp_reduce8
 
 namespace b200 {
 
@@ -185,8 +186,16 @@ __global__ void __launch_bounds__(256, 3) k_fwd_top2(const SolveItem* __restrict
             const int kh = (p + 1) >> 1;
             const int kbeg = h * kh, kend = min(p, kbeg + kh);
             double s = 0.0;
-            if (r < it.nrows)
-                for (int k = kbeg; k < kend; k++) s += Ps[k * B200_SLICE + r] * z[k];
+            if (r < it.nrows) { // four independent chains (the dependent-add chain of 32 FMAs was the longest leg of an item)
+                double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                int k = kbeg;
+                for (; k + 3 < kend; k += 4) {
+                    s += Ps[k * B200_SLICE + r] * z[k], s1 += Ps[(k + 1) * B200_SLICE + r] * z[k + 1];
+                    s2 += Ps[(k + 2) * B200_SLICE + r] * z[k + 2], s3 += Ps[(k + 3) * B200_SLICE + r] * z[k + 3];
+                }
+                for (; k < kend; k++) s += Ps[k * B200_SLICE + r] * z[k];
+                s = (s + s1) + (s2 + s3);
+            }
             if (h == 1) wpart[r] = s;
             __syncthreads();
             if (h == 0 && r < it.nrows) wv[nd.rows_ptr + it.r0 + r] = wloc[r] - (s + wpart[r]);
@@ -308,12 +317,26 @@ __global__ void __launch_bounds__(256, 3) k_bwd_top3(const SolveItem* __restrict
         cp_async_wait_all();
         __syncthreads();
         double* part = scratch + ((long long)slot + it.slice) * B200_MAXP;
-        for (int k = warp; k < p; k += nwarps) {
-            const double* col = Ps + k * B200_SLICE;
-            double sacc = 0.0;
-            for (int j = lane; j < it.nrows; j += 32) sacc += col[j] * x2[j];
-            for (int off = 16; off > 0; off >>= 1) sacc += __shfl_down_sync(0xffffffffu, sacc, off);
-            if (lane == 0) part[k] = sacc;
+        {   // warp w owns the columns 8w .. 8w+7: lane-local products over its four rows, then ONE 9-shuffle butterfly for the
+            // eight columns (40 shuffles with a reduction per column)
+            double v8[8];
+            const bool ra = lane < it.nrows, rb = lane + 32 < it.nrows, rc = lane + 64 < it.nrows, rd = lane + 96 < it.nrows;
+            const double xa = ra ? x2[lane] : 0.0, xb = rb ? x2[lane + 32] : 0.0, xc = rc ? x2[lane + 64] : 0.0, xd = rd ? x2[lane + 96] : 0.0;
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                const double* col = Ps + (8 * warp + c) * B200_SLICE;
+                double acc8 = 0.0;
+                if (8 * warp + c < p) { // (rows beyond the slice were never staged: they must not be read)
+                    if (ra) acc8 = col[lane] * xa;
+                    if (rb) acc8 += col[lane + 32] * xb;
+                    if (rc) acc8 += col[lane + 64] * xc;
+                    if (rd) acc8 += col[lane + 96] * xd;
+                }
+                v8[c] = acc8;
+            }
+            const double tot = warp_reduce8(v8, lane);
+            const int c = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1); // the column this lane holds
+            if ((lane & 3) == 0 && 8 * warp + c < p) part[8 * warp + c] = tot;
         }
         __threadfence();
         __syncthreads();
