@@ -227,12 +227,17 @@ __global__ void __launch_bounds__(128, 1) k_schur_ozaki(const OzakiItem* __restr
             double acc[16];
 #pragma unroll
             for (int e = 0; e < 16; e++) acc[e] = 0.0;
-            for (int g = OZ_S + 1; g >= 2; g--) { // acc = acc * 2^-7 + G_g  (smallest scale first)
-                int v[16];
-                oz_ld16(lane_base + (unsigned)(g - 2) * OZ_BN + c16 * 16, v);
+            // acc = acc * 2^-7 + G_g, smallest scale first; four groups are read out per tcgen05.wait
+#pragma unroll
+            for (int gb = OZ_S + 1; gb >= 2; gb -= 4) {
+                int v[4][16];
+#pragma unroll
+                for (int h = 0; h < 4; h++) oz_ld16(lane_base + (unsigned)(gb - h - 2) * OZ_BN + c16 * 16, v[h]);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int e = 0; e < 16; e++) acc[e] = fma(acc[e], 0.0078125, (double)v[e]);
+                for (int h = 0; h < 4; h++)
+#pragma unroll
+                    for (int e = 0; e < 16; e++) acc[e] = fma(acc[e], 0.0078125, (double)v[h][e]);
             }
             if (i < it.u) {
 #pragma unroll
