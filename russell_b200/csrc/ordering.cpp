@@ -416,7 +416,14 @@ void nd_component(NdCtx& c, std::vector<int>& verts, int id, int* out, std::vect
     // disjoint slices of `out`.  The first three dissection levels of a large graph are ordered by two threads each
     // (up to 8 concurrent); the resulting permutation does not depend on the schedule (labels are only compared for equality).
     static const bool serial = getenv("B200_ND_SERIAL") != nullptr; // (tests compare the threaded and the serial ordering)
-    if (!serial && depth < 3 && sa + sb > 40000 && std::thread::hardware_concurrency() > 1) {
+    static const int tdepth = []() { // levels that fork: 2^tdepth concurrent halves, about twice the hardware threads
+        if (const char* e = getenv("B200_ND_THREAD_DEPTH")) return atoi(e);
+        const unsigned hc = std::thread::hardware_concurrency();
+        int d = 0;
+        while ((1u << d) < 2 * hc && d < 6) d++;
+        return d;
+    }();
+    if (!serial && depth < tdepth && sa + sb > 20000) {
         std::thread other([&c, &A, idA, out, depth]() { nd_rec(c, A, idA, out, depth + 1); });
         nd_rec(c, B, idB, out + sa, depth + 1);
         other.join();

@@ -16,8 +16,31 @@
 #include <cmath>
 #include <cstdio>
 #include <numeric>
+#include <atomic>
+#include <cstdlib>
+#include <thread>
 
 namespace b200 {
+
+// splits [0, n) into contiguous chunks, one per hardware thread (at most 16); small ranges run inline
+template <class F>
+static void parallel_rows(int n, F fn) {
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt > 16) nt = 16;
+    if (nt < 2 || n < 50000 || getenv("B200_ND_SERIAL")) {
+        fn(0, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    const int chunk = (n + (int)nt - 1) / (int)nt;
+    for (unsigned t = 1; t < nt; t++) {
+        const int a = (int)t * chunk, b = std::min(n, a + chunk);
+        if (a < b) th.emplace_back([=, &fn]() { fn(a, b); });
+    }
+    fn(0, std::min(n, chunk));
+    for (auto& x : th) x.join();
+}
+
 
 namespace {
 double now_s() {
@@ -136,11 +159,13 @@ static void relabel_graph(const Graph& g, const std::vector<int>& perm /*new->ol
     out.ptr.assign(n + 1, 0);
     for (int k = 0; k < n; k++) out.ptr[k + 1] = out.ptr[k] + (g.ptr[perm[k] + 1] - g.ptr[perm[k]]);
     out.adj.resize(g.adj.size());
-    for (int k = 0; k < n; k++) {
-        int o = perm[k], d = out.ptr[k];
-        for (int e = g.ptr[o]; e < g.ptr[o + 1]; e++) out.adj[d++] = inv[g.adj[e]];
-        std::sort(out.adj.begin() + out.ptr[k], out.adj.begin() + out.ptr[k + 1]);
-    }
+    parallel_rows(n, [&](int kbeg, int kend) { // every vertex fills and sorts its own adjacency slice
+        for (int k = kbeg; k < kend; k++) {
+            int o = perm[k], d = out.ptr[k];
+            for (int e = g.ptr[o]; e < g.ptr[o + 1]; e++) out.adj[d++] = inv[g.adj[e]];
+            std::sort(out.adj.begin() + out.ptr[k], out.adj.begin() + out.ptr[k + 1]);
+        }
+    });
 }
 
 int analyze(int n, const int* rowptr, const int* colidx, const double* vals, bool sym_lower,
@@ -734,7 +759,9 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
     P.a_src.resize(fnnz);
     P.a_dst.resize(fnnz);
     if (scaled) P.a_scl.resize(fnnz);
-    for (int i = 0; i < n; i++) {
+    std::atomic<int> scatter_bad{0};
+    parallel_rows(n, [&](int ibeg, int iend) { // rows are independent: every entry writes its own slot of the map
+    for (int i = ibeg; i < iend; i++) {
         const int kr = invq[colmatch[i]];
         for (int k = fptr[i]; k < fptr[i + 1]; k++) {
             const int j = fcol[k];
@@ -748,7 +775,7 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
                 else {
                     const int* r = &P.rows[P.rows_ptr[v]];
                     const int* it = std::lower_bound(r, r + P.u[v], kr);
-                    if (it == r + P.u[v] || *it != kr) return -2;
+                    if (it == r + P.u[v] || *it != kr) { scatter_bad = 1; return; }
                     rpos = P.p[v] + (int)(it - r);
                 }
                 dst = P.Loff[v] + rpos + (int64_t)(kc - P.c0[v]) * f;
@@ -759,7 +786,7 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
                 else {
                     const int* r = &P.rows[P.rows_ptr[v]];
                     const int* it = std::lower_bound(r, r + P.u[v], kc);
-                    if (it == r + P.u[v] || *it != kc) return -2;
+                    if (it == r + P.u[v] || *it != kc) { scatter_bad = 1; return; }
                     dst = P.Uoff[v] + (int64_t)(it - r) + (int64_t)(kr - P.c0[v]) * P.u[v];
                 }
             }
@@ -768,6 +795,8 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
             if (scaled) P.a_scl[k] = P.rscale[i] * P.cscale[j];
         }
     }
+    });
+    if (scatter_bad) return -2;
     if (opt.verbose >= 2) fprintf(stderr, "b200 analyze:   phase scattermap done at %.3f s\n", now_s() - t0);
     P.t_symbolic = now_s() - t0;
     if (opt.verbose) {
