@@ -69,6 +69,13 @@ struct LevelLists {
     std::vector<int> big_ptr; // nlevels+1: slices of the big solve class inside d_big_items
     std::vector<int> inv_ptr; // NIC+1: fronts by pivot-count class inside d_inv_nodes
     std::vector<size_t> fused_smem; // per (level, class): dynamic shared memory of the fused launch
+    // k_front_warp: the fronts of a (level, class) range are sorted by order and cut into size buckets, one launch each
+    // (shared memory per warp follows the bucket's largest front: small fronts get more resident warps)
+    struct FwBatch {
+        int start, count, need; // range inside d_fact_nodes; doubles of shared memory of the largest front ((f | 1) * f)
+    };
+    std::vector<FwBatch> fw_batches;
+    std::vector<int> fw_ptr; // per (level, class) + 1: batches inside fw_batches
     std::vector<size_t> asm_smem;   // per level: largest tile (bytes) of k_assemble_tile
     // schur_variant 2: fronts with u >= ozaki_min_u take the tcgen05 kernel (ozaki_tc.cuh)
     std::vector<int> oz_split_ptr, oz_item_ptr, oz_rows_max; // nlevels+1 / nlevels+1 / nlevels
@@ -178,6 +185,7 @@ struct InterfaceB200 {
     int fused_variant = 2;  // 0 = shared-memory LU (k_front_fused), 1 = register-resident (k_front_fused_w8) for f <= 64,
                             // 2 = register-resident only for launches of at most fused_w8_max fronts (measured crossover)
     int fused_w8_max = 2000;
+    int use_front_warp = 1; // fused launches of more than fused_w8_max fronts of order <= 64: one warp per front (k_front_warp)
 
     // stats
     int n_perturbed = 0;
@@ -304,6 +312,8 @@ void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::ve
     lv.solve_threads.assign(P.nlevels, 32);
     lv.solve_pmax.assign(P.nlevels, 1);
     lv.fused_smem.assign((size_t)P.nlevels * NFC, 0);
+    lv.fw_batches.clear();
+    lv.fw_ptr.assign(1, 0);
     lv.asm_smem.assign(P.nlevels, 0);
     lv.oz_split_ptr.assign(P.nlevels + 1, 0), lv.oz_item_ptr.assign(P.nlevels + 1, 0), lv.oz_rows_max.assign(P.nlevels, 0);
     lv.oz_tile_bytes = 0, lv.oz_scales = 0;
@@ -352,6 +362,28 @@ void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::ve
                 }
             }
             lv.fact_ptr[(size_t)l * (NFC + 1) + c + 1] = (int)fact_nodes.size();
+            if (c < NFC) { // size buckets of the warp-per-front kernel (fronts of one launch are independent: any order will do)
+                const int beg = lv.fact_ptr[(size_t)l * (NFC + 1) + c], end = (int)fact_nodes.size();
+                std::stable_sort(fact_nodes.begin() + beg, fact_nodes.begin() + end,
+                                 [&P](int a, int b) { return P.p[a] + P.u[a] < P.p[b] + P.u[b]; });
+                const size_t first = lv.fw_batches.size();
+                int b0 = beg;
+                while (b0 < end) {
+                    const int f0 = P.p[fact_nodes[b0]] + P.u[fact_nodes[b0]];
+                    const int cap = ((f0 + 3) / 4) * 4 + (f0 > 32 ? 4 : 0); // buckets of 4 (8 above 32)
+                    int b1 = b0, fmax = f0;
+                    while (b1 < end && P.p[fact_nodes[b1]] + P.u[fact_nodes[b1]] <= cap) fmax = P.p[fact_nodes[b1]] + P.u[fact_nodes[b1]], b1++;
+                    // a launch costs the latency of one front (tens of microseconds) however few fronts it has: a sliver joins
+                    // the bucket before it (whose shared memory then follows the sliver's larger fronts)
+                    if (b1 - b0 < 1024 && lv.fw_batches.size() > first) {
+                        lv.fw_batches.back().count += b1 - b0;
+                        lv.fw_batches.back().need = (fmax | 1) * fmax;
+                    } else
+                        lv.fw_batches.push_back({b0, b1 - b0, (fmax | 1) * fmax});
+                    b0 = b1;
+                }
+            }
+            if (c < NFC) lv.fw_ptr.push_back((int)lv.fw_batches.size());
         }
         {
             // solve phase: ONE launch per level for all fronts below the "big" threshold (block size chosen from the
@@ -474,7 +506,26 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
                     k_front_fused_w8<<<nn, 32 * ((FC_MAXF[c] + 7) / 8), lv.fused_smem[(size_t)l * NFC + c], s->stream>>>(
                         s->d_fact_nodes + fp[c], s->d_nodes, s->d_child_idx, s->d_rel, s->d_fac, s->d_cb, s->d_lperm,
                         s->d_upiv, s->d_amax, s->pivot_eps, s->d_counters);
-                else
+                else if (FC_MAXF[c] <= 64 && s->use_front_warp) {
+                    // one warp per front, the front in the warp's slice of shared memory: one launch per size bucket
+                    const int R = FC_MAXF[c] <= 32 ? 1 : 2;
+                    for (int bi = lv.fw_ptr[(size_t)l * NFC + c]; bi < lv.fw_ptr[(size_t)l * NFC + c + 1]; bi++) {
+                        const LevelLists::FwBatch& B = lv.fw_batches[bi];
+                        const int wstride = ((B.need + 1) & ~1) + 32 * R; // front + permutation + one child's relative indices
+                        const int gridw = (B.count + B200_FW_WARPS - 1) / B200_FW_WARPS;
+                        const size_t smw = (size_t)wstride * B200_FW_WARPS * sizeof(double);
+                        if (R == 1)
+                            k_front_warp<1><<<gridw, 32 * B200_FW_WARPS, smw, s->stream>>>(s->d_fact_nodes + B.start, B.count, s->d_nodes, s->d_child_idx,
+                                                                                        s->d_rel, s->d_fac, s->d_cb, s->d_lperm, s->d_upiv, s->d_amax,
+                                                                                        s->pivot_eps, s->d_counters, wstride);
+                        else
+                            k_front_warp<2><<<gridw, 32 * B200_FW_WARPS, smw, s->stream>>>(s->d_fact_nodes + B.start, B.count, s->d_nodes, s->d_child_idx,
+                                                                                        s->d_rel, s->d_fac, s->d_cb, s->d_lperm, s->d_upiv, s->d_amax,
+                                                                                        s->pivot_eps, s->d_counters, wstride);
+                        cnt++;
+                    }
+                    cnt--;
+                } else
                     k_front_fused<<<nn, FC_THREADS[c], lv.fused_smem[(size_t)l * NFC + c], s->stream>>>(
                         s->d_fact_nodes + fp[c], s->d_nodes, s->d_child_idx, s->d_rel, s->d_fac, s->d_cb, s->d_lperm,
                         s->d_upiv, s->d_amax, s->pivot_eps, s->d_counters);
@@ -743,6 +794,9 @@ struct InterfaceB200* solver_b200_new(void) {
     if ((e = getenv("B200_SCHUR_VARIANT"))) s->schur_variant = atoi(e);
     if ((e = getenv("B200_PANEL_VARIANT"))) s->panel_variant = atoi(e);
     if ((e = getenv("B200_PANEL_ROW_MAX"))) s->panel_row_max = atoi(e);
+    if ((e = getenv("B200_USE_FRONT_WARP"))) s->use_front_warp = atoi(e);
+    if ((e = getenv("B200_USE_LEAF_REG"))) s->use_leaf_reg = atoi(e);
+    if ((e = getenv("B200_FUSED_W8_MAX"))) s->fused_w8_max = atoi(e);
     if ((e = getenv("B200_USE_LEAF_REG"))) s->use_leaf_reg = atoi(e);
     if ((e = getenv("B200_ASM_VARIANT"))) s->asm_variant = atoi(e);
     if ((e = getenv("B200_FUSED_VARIANT"))) s->fused_variant = atoi(e);
@@ -792,6 +846,7 @@ int32_t solver_b200_set_option(struct InterfaceB200* s, const char* key, double 
     else if (k == "relax_z3") s->relax_z3 = value;
     else if (k == "fused_variant") s->fused_variant = (int)value;
     else if (k == "fused_w8_max") s->fused_w8_max = (int)value;
+    else if (k == "use_front_warp") s->use_front_warp = value != 0.0;
     else if (k == "use_fused") s->use_fused = value != 0.0;
     else if (k == "use_top") s->use_top = value != 0.0;
     else if (k == "trace") s->want_trace = value != 0.0;
@@ -1180,6 +1235,8 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     CUDA_TRY(cudaFuncSetAttribute(k_invert_col, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_invert(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_front_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused(B200_FUSED_MAXF, B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_front_fused_w8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused(64, B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
+    CUDA_TRY(cudaFuncSetAttribute(k_front_warp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(B200_FW_WARPS * (smem_fused(32, 0) + 32 * 8 + 16))), B200_ERROR_NOT_AVAILABLE);
+    CUDA_TRY(cudaFuncSetAttribute(k_front_warp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(B200_FW_WARPS * (smem_fused(64, 0) + 64 * 8 + 16))), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_panel(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_panel_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_PW_SMEM), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_schur_fma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_schur_fma(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
