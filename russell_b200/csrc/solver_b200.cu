@@ -182,6 +182,14 @@ struct InterfaceB200 {
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaStream_t side = nullptr;          // side stream: the factor arena is cleared there, under the H2D copy of the new values
     cudaEvent_t ev_clr0 = nullptr, ev_clr1 = nullptr; // fork / join of the factor-arena clear that runs under the H2D copy
+    // The launches of one tree level are independent of each other (fused size classes / buckets, and the big-front sequence
+    // assembly -> pivot block -> panels -> Schur): they are enqueued on parallel branches (captured into the graph as a fork /
+    // join per level), so that a launch of a few dozen fronts -- which costs the latency of one front, 15-35 us, however
+    // small it is -- runs beside the large launches of its level instead of in front of them.
+    static const int NLS = 3;
+    cudaStream_t lvl_side[NLS] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[NLS] = {nullptr, nullptr, nullptr};
+    int use_level_fork = 1;
     int fused_variant = 2;  // 0 = shared-memory LU (k_front_fused), 1 = register-resident (k_front_fused_w8) for f <= 64,
                             // 2 = register-resident only for launches of at most fused_w8_max fronts (measured crossover)
     int fused_w8_max = 2000;
@@ -485,6 +493,24 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
     int cnt = 0;
     for (int l = 0; l < P.nlevels; l++) {
         const int* fp = &lv.fact_ptr[(size_t)l * (NFC + 1)];
+        // independent launch groups of this level: fused classes / buckets + the big-front sequence
+        int ngroups = (fp[NFC + 1] - fp[NFC] > 0) ? 1 : 0;
+        for (int c = 0; c < NFC; c++)
+            if (fp[c + 1] - fp[c] > 0) ngroups += std::max(1, lv.fw_ptr[(size_t)l * NFC + c + 1] - lv.fw_ptr[(size_t)l * NFC + c]);
+        const bool fork = s->use_level_fork && ngroups >= 2;
+        unsigned used = 0;
+        int rr = 0;
+        if (fork) cudaEventRecord(s->ev_fork, s->stream);
+        auto fstream = [&]() -> cudaStream_t { // the branch of the next fused launch
+            if (!fork) return s->stream;
+            const int i = rr++ % InterfaceB200::NLS;
+            if (!(used & (1u << i))) cudaStreamWaitEvent(s->lvl_side[i], s->ev_fork, 0), used |= 1u << i;
+            return s->lvl_side[i];
+        };
+        auto join = [&]() {
+            for (int i = 0; i < InterfaceB200::NLS; i++)
+                if (used & (1u << i)) cudaEventRecord(s->ev_join[i], s->lvl_side[i]), cudaStreamWaitEvent(s->stream, s->ev_join[i], 0);
+        };
         for (int c = 0; c < NFC; c++) {
             int nn = fp[c + 1] - fp[c];
             if (nn > 0) {
@@ -492,18 +518,18 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
                     // leaves: the whole front in one warp's registers
                     const int gridw = (nn + B200_LEAF_WARPS - 1) / B200_LEAF_WARPS;
                     if (FC_MAXF[c] <= 16)
-                        k_small_reg<16><<<gridw, 32 * B200_LEAF_WARPS, 0, s->stream>>>(s->d_fact_nodes + fp[c], nn, s->d_nodes, s->d_child_idx,
+                        k_small_reg<16><<<gridw, 32 * B200_LEAF_WARPS, 0, fstream()>>>(s->d_fact_nodes + fp[c], nn, s->d_nodes, s->d_child_idx,
                                                                                       s->d_rel, s->d_fac, s->d_cb, s->d_lperm, s->d_upiv,
                                                                                       s->d_amax, s->pivot_eps, s->d_counters);
                     else
-                        k_small_reg<32><<<gridw, 32 * B200_LEAF_WARPS, 0, s->stream>>>(s->d_fact_nodes + fp[c], nn, s->d_nodes, s->d_child_idx,
+                        k_small_reg<32><<<gridw, 32 * B200_LEAF_WARPS, 0, fstream()>>>(s->d_fact_nodes + fp[c], nn, s->d_nodes, s->d_child_idx,
                                                                                       s->d_rel, s->d_fac, s->d_cb, s->d_lperm, s->d_upiv,
                                                                                       s->d_amax, s->pivot_eps, s->d_counters);
                 }
                 // register-resident LU (one warp per 8 front columns): wins when the launch is latency bound (few fronts),
                 // loses to the leaner shared-memory kernel when tens of thousands of fronts compete for thread slots
                 else if (FC_MAXF[c] <= 64 && (s->fused_variant == 1 || (s->fused_variant == 2 && nn <= s->fused_w8_max)))
-                    k_front_fused_w8<<<nn, 32 * ((FC_MAXF[c] + 7) / 8), lv.fused_smem[(size_t)l * NFC + c], s->stream>>>(
+                    k_front_fused_w8<<<nn, 32 * ((FC_MAXF[c] + 7) / 8), lv.fused_smem[(size_t)l * NFC + c], fstream()>>>(
                         s->d_fact_nodes + fp[c], s->d_nodes, s->d_child_idx, s->d_rel, s->d_fac, s->d_cb, s->d_lperm,
                         s->d_upiv, s->d_amax, s->pivot_eps, s->d_counters);
                 else if (FC_MAXF[c] <= 64 && s->use_front_warp) {
@@ -515,25 +541,28 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
                         const int gridw = (B.count + B200_FW_WARPS - 1) / B200_FW_WARPS;
                         const size_t smw = (size_t)wstride * B200_FW_WARPS * sizeof(double);
                         if (R == 1)
-                            k_front_warp<1><<<gridw, 32 * B200_FW_WARPS, smw, s->stream>>>(s->d_fact_nodes + B.start, B.count, s->d_nodes, s->d_child_idx,
+                            k_front_warp<1><<<gridw, 32 * B200_FW_WARPS, smw, fstream()>>>(s->d_fact_nodes + B.start, B.count, s->d_nodes, s->d_child_idx,
                                                                                         s->d_rel, s->d_fac, s->d_cb, s->d_lperm, s->d_upiv, s->d_amax,
                                                                                         s->pivot_eps, s->d_counters, wstride);
                         else
-                            k_front_warp<2><<<gridw, 32 * B200_FW_WARPS, smw, s->stream>>>(s->d_fact_nodes + B.start, B.count, s->d_nodes, s->d_child_idx,
+                            k_front_warp<2><<<gridw, 32 * B200_FW_WARPS, smw, fstream()>>>(s->d_fact_nodes + B.start, B.count, s->d_nodes, s->d_child_idx,
                                                                                         s->d_rel, s->d_fac, s->d_cb, s->d_lperm, s->d_upiv, s->d_amax,
                                                                                         s->pivot_eps, s->d_counters, wstride);
                         cnt++;
                     }
                     cnt--;
                 } else
-                    k_front_fused<<<nn, FC_THREADS[c], lv.fused_smem[(size_t)l * NFC + c], s->stream>>>(
+                    k_front_fused<<<nn, FC_THREADS[c], lv.fused_smem[(size_t)l * NFC + c], fstream()>>>(
                         s->d_fact_nodes + fp[c], s->d_nodes, s->d_child_idx, s->d_rel, s->d_fac, s->d_cb, s->d_lperm,
                         s->d_upiv, s->d_amax, s->pivot_eps, s->d_counters);
                 cnt++;
             }
         }
         int nbig = fp[NFC + 1] - fp[NFC];
-        if (nbig == 0) continue;
+        if (nbig == 0) {
+            join();
+            continue;
+        }
         int na = lv.asm_ptr[l + 1] - lv.asm_ptr[l];
         if (na > 0) {
             if (s->asm_variant == 1 && lv.asm_smem[l] <= (size_t)B200_ASM_SMEM_MAX) // tile in shared memory
@@ -580,6 +609,7 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
                 k_schur_fma<<<nsch, 256, smem_schur_fma(W), s->stream>>>(s->d_schur + lv.schur_ptr[l], s->d_nodes, s->d_fac, s->d_cb);
             cnt++;
         }
+        join();
     }
     // explicit inverses of the pivot blocks, all fronts outside the subtree region in one batched launch per size class:
     // only the solve phase needs them
@@ -757,11 +787,21 @@ static bool create_streams(InterfaceB200* s) {
     if (cudaStreamCreateWithPriority(&s->side, cudaStreamNonBlocking, lo) != cudaSuccess) return false;
     if (cudaEventCreateWithFlags(&s->ev_clr0, cudaEventDisableTiming) != cudaSuccess) return false;
     if (cudaEventCreateWithFlags(&s->ev_clr1, cudaEventDisableTiming) != cudaSuccess) return false;
+    if (cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) != cudaSuccess) return false;
+    for (int i = 0; i < InterfaceB200::NLS; i++) {
+        if (cudaStreamCreateWithPriority(&s->lvl_side[i], cudaStreamNonBlocking, hi) != cudaSuccess) return false;
+        if (cudaEventCreateWithFlags(&s->ev_join[i], cudaEventDisableTiming) != cudaSuccess) return false;
+    }
     return true;
 }
 static void destroy_streams(InterfaceB200* s) {
     if (s->ev_clr0) cudaEventDestroy(s->ev_clr0), s->ev_clr0 = nullptr;
     if (s->ev_clr1) cudaEventDestroy(s->ev_clr1), s->ev_clr1 = nullptr;
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork), s->ev_fork = nullptr;
+    for (int i = 0; i < InterfaceB200::NLS; i++) {
+        if (s->ev_join[i]) cudaEventDestroy(s->ev_join[i]), s->ev_join[i] = nullptr;
+        if (s->lvl_side[i]) cudaStreamDestroy(s->lvl_side[i]), s->lvl_side[i] = nullptr;
+    }
     if (s->side) cudaStreamDestroy(s->side), s->side = nullptr;
     if (s->stream) cudaStreamDestroy(s->stream), s->stream = nullptr;
 }
@@ -796,6 +836,7 @@ struct InterfaceB200* solver_b200_new(void) {
     if ((e = getenv("B200_PANEL_ROW_MAX"))) s->panel_row_max = atoi(e);
     if ((e = getenv("B200_USE_FRONT_WARP"))) s->use_front_warp = atoi(e);
     if ((e = getenv("B200_USE_LEAF_REG"))) s->use_leaf_reg = atoi(e);
+    if ((e = getenv("B200_USE_LEVEL_FORK"))) s->use_level_fork = atoi(e);
     if ((e = getenv("B200_FUSED_W8_MAX"))) s->fused_w8_max = atoi(e);
     if ((e = getenv("B200_USE_LEAF_REG"))) s->use_leaf_reg = atoi(e);
     if ((e = getenv("B200_ASM_VARIANT"))) s->asm_variant = atoi(e);
@@ -847,6 +888,7 @@ int32_t solver_b200_set_option(struct InterfaceB200* s, const char* key, double 
     else if (k == "fused_variant") s->fused_variant = (int)value;
     else if (k == "fused_w8_max") s->fused_w8_max = (int)value;
     else if (k == "use_front_warp") s->use_front_warp = value != 0.0;
+    else if (k == "use_level_fork") s->use_level_fork = value != 0.0;
     else if (k == "use_fused") s->use_fused = value != 0.0;
     else if (k == "use_top") s->use_top = value != 0.0;
     else if (k == "trace") s->want_trace = value != 0.0;
