@@ -272,6 +272,39 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
     t0 = now_s();
     Graph g0;
     g0.n = n;
+    // Fast path (the usual case: PDE / Jacobian patterns): without a row matching and with a structurally symmetric pattern
+    // the graph is the pattern itself minus the diagonal -- checked and copied by row-parallel threads.
+    bool pattern_is_graph = !P.matched;
+    if (pattern_is_graph)
+        for (int j = 0; j < n && pattern_is_graph; j++) pattern_is_graph = rowmatch[j] == j;
+    if (pattern_is_graph) {
+        std::atomic<int> asym{0};
+        g0.ptr.assign(n + 1, 0);
+        parallel_rows(n, [&](int ibeg, int iend) {
+            for (int i = ibeg; i < iend && !asym.load(std::memory_order_relaxed); i++) {
+                int cnt = 0;
+                for (int k = fptr[i]; k < fptr[i + 1]; k++) {
+                    const int j = fcol[k];
+                    if (j == i) continue;
+                    cnt++;
+                    if (!std::binary_search(fcol.begin() + fptr[j], fcol.begin() + fptr[j + 1], i)) { asym = 1; break; }
+                }
+                g0.ptr[i + 1] = cnt;
+            }
+        });
+        pattern_is_graph = asym == 0;
+    }
+    if (pattern_is_graph) {
+        for (int v = 0; v < n; v++) g0.ptr[v + 1] += g0.ptr[v];
+        g0.adj.resize(g0.ptr[n]);
+        parallel_rows(n, [&](int ibeg, int iend) {
+            for (int i = ibeg; i < iend; i++) {
+                int d = g0.ptr[i];
+                for (int k = fptr[i]; k < fptr[i + 1]; k++)
+                    if (fcol[k] != i) g0.adj[d++] = fcol[k]; // (rows are sorted and duplicate-free: checked above)
+            }
+        });
+    } else
     {
         std::vector<int> deg(n + 1, 0);
         for (int i = 0; i < n; i++) {
@@ -291,16 +324,21 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
                 if (j != ip) adj[fill[ip]++] = j, adj[fill[j]++] = ip;
             }
         }
+        // every vertex sorts its own slice and counts its distinct neighbours; a prefix sum places the compacted lists
         g0.ptr.assign(n + 1, 0);
-        g0.adj.reserve(adj.size());
-        for (int v = 0; v < n; v++) {
-            std::sort(adj.begin() + deg[v], adj.begin() + deg[v + 1]);
-            int prev = -1;
-            for (int e = deg[v]; e < deg[v + 1]; e++)
-                if (adj[e] != prev) g0.adj.push_back(prev = adj[e]);
-            g0.ptr[v + 1] = (int)g0.adj.size();
-        }
+        parallel_rows(n, [&](int vbeg, int vend) {
+            for (int v = vbeg; v < vend; v++) {
+                std::sort(adj.begin() + deg[v], adj.begin() + deg[v + 1]);
+                g0.ptr[v + 1] = (int)(std::unique(adj.begin() + deg[v], adj.begin() + deg[v + 1]) - (adj.begin() + deg[v]));
+            }
+        });
+        for (int v = 0; v < n; v++) g0.ptr[v + 1] += g0.ptr[v];
+        g0.adj.resize(g0.ptr[n]);
+        parallel_rows(n, [&](int vbeg, int vend) {
+            for (int v = vbeg; v < vend; v++) std::copy(adj.begin() + deg[v], adj.begin() + deg[v] + (g0.ptr[v + 1] - g0.ptr[v]), g0.adj.begin() + g0.ptr[v]);
+        });
     }
+    if (opt.verbose >= 3) fprintf(stderr, "b200 analyze:     .g0 at %.3f s\n", now_s() - t0);
 
     // ---- fill-reducing ordering ----------------------------------------------------------------------
     std::vector<int> q; // new -> old
@@ -321,16 +359,22 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
     {
         Graph g1;
         relabel_graph(g0, q, g1);
+    if (opt.verbose >= 3) fprintf(stderr, "b200 analyze:     .relabel1 at %.3f s\n", now_s() - t0);
         std::vector<int> par1, cc1, post1, none;
         etree_symmetric(g1, par1);
+    if (opt.verbose >= 3) fprintf(stderr, "b200 analyze:     .etree1 at %.3f s\n", now_s() - t0);
         postorder_tree(par1, none, post1);
+    if (opt.verbose >= 3) fprintf(stderr, "b200 analyze:     .post1 at %.3f s\n", now_s() - t0);
         column_counts_post(g1, par1, post1, cc1);
+    if (opt.verbose >= 3) fprintf(stderr, "b200 analyze:     .cc1 at %.3f s\n", now_s() - t0);
         std::vector<int> post;
         postorder_tree(par1, cc1, post);
+    if (opt.verbose >= 3) fprintf(stderr, "b200 analyze:     .post2 at %.3f s\n", now_s() - t0);
         std::vector<int> q2(n);
         for (int k = 0; k < n; k++) q2[k] = q[post[k]];
         q.swap(q2);
         relabel_graph(g0, q, g);
+    if (opt.verbose >= 3) fprintf(stderr, "b200 analyze:     .relabel2 at %.3f s\n", now_s() - t0);
         // A postorder only renames the vertices of the elimination tree: parents and column counts of the final
         // labelling follow from the first pass by renaming (no second etree / column-count computation).
         std::vector<int> newid(n);
@@ -388,6 +432,7 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
             for (int s = 0; s < nf; s++)
                 if (fpar[s] >= 0) cidx[fill[fpar[s]]++] = s;
         }
+    if (opt.verbose >= 3) fprintf(stderr, "b200 analyze:     .fundtree at %.3f s\n", now_s() - t0);
         // bottom-up greedy merging; nc/ff/zz describe the merged group rooted at s
         std::vector<int64_t> nc(nf), ff(nf), zz(nf, 0);
         std::vector<char> merged_into_parent(nf, 0);
@@ -416,6 +461,7 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
                 nc[s] = nm, ff[s] = fm, zz[s] = z;
             }
         }
+    if (opt.verbose >= 3) fprintf(stderr, "b200 analyze:     .merge at %.3f s\n", now_s() - t0);
         // new elimination order: for every group, first the (unmerged) child groups, then the group's columns
         // (merged children's columns before their parent's columns)
         std::vector<int> order;
@@ -477,6 +523,7 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
                     if (!merged_into_parent[cidx[e]]) tmp.push_back(cidx[e]);
             for (auto it = tmp.rbegin(); it != tmp.rend(); ++it) st.push_back({*it, 0});
         }
+    if (opt.verbose >= 3) fprintf(stderr, "b200 analyze:     .emit at %.3f s\n", now_s() - t0);
         // relabel everything to the new order
         bool identity = true;
         for (int k = 0; k < n; k++)
@@ -574,47 +621,6 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
             P.rows_ptr[v + 1] = P.rows_ptr[v] + P.u[v];
         }
     }
-    P.rows.resize(P.rows_ptr[nnodes]);
-    P.rel.assign(P.rows_ptr[nnodes], -1);
-    for (int s = 0; s < ns; s++) {
-        const int K = sn_npieces[s];
-        const int lastcol = grp[s].first + grp[s].ncols - 1;
-        for (int k = 0; k < K; k++) {
-            int v = sn_firstnode[s] + k;
-            int* r = &P.rows[P.rows_ptr[v]];
-            int t = 0;
-            for (int j = P.c0[v] + P.p[v]; j <= lastcol; j++) r[t++] = j; // remaining columns of the supernode
-            for (int i : srows[s]) r[t++] = i;
-            assert(t == P.u[v]);
-        }
-    }
-    // relative indices into the parent front
-    for (int s = 0; s < ns; s++) {
-        const int K = sn_npieces[s];
-        for (int k = 0; k < K; k++) {
-            int v = sn_firstnode[s] + k;
-            int* rel = &P.rel[P.rows_ptr[v]];
-            if (k + 1 < K) {
-                for (int i = 0; i < P.u[v]; i++) rel[i] = i; // the next panel's front is exactly this update set
-            } else if (sparent[s] >= 0) {
-                int t = sparent[s];
-                const int tfirst = grp[t].first, tn = grp[t].ncols;
-                const std::vector<int>& tr = srows[t];
-                size_t w = 0;
-                const int* r = &P.rows[P.rows_ptr[v]];
-                for (int i = 0; i < P.u[v]; i++) {
-                    int gi = r[i];
-                    if (gi < tfirst + tn) {
-                        rel[i] = gi - tfirst;
-                    } else {
-                        while (w < tr.size() && tr[w] < gi) w++;
-                        if (w >= tr.size() || tr[w] != gi) return -2; // structure inconsistency (should not happen)
-                        rel[i] = tn + (int)w;
-                    }
-                }
-            }
-        }
-    }
     // children lists + levels
     P.child_ptr.assign(nnodes + 1, 0);
     P.child_idx.resize(nnodes);
@@ -641,63 +647,11 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
         std::vector<int> fill(P.level_ptr.begin(), P.level_ptr.end() - 1);
         for (int v = 0; v < nnodes; v++) P.level_nodes[fill[P.level[v]]++] = v;
     }
-    // storage offsets + stats
-    if (opt.verbose >= 2) fprintf(stderr, "b200 analyze:   phase fronttree done at %.3f s\n", now_s() - t0);
-    // ---- solve-phase subtrees: maximal subtrees whose fronts are all small (nodes are in postorder: the subtree rooted at
-    //      v is the contiguous range [v - size + 1, v])
-    P.in_sub.assign(nnodes, 0);
-    if (opt.st_enable) {
-        std::vector<int64_t> ent(nnodes, 0);
-        std::vector<int> size(nnodes, 1), cols(nnodes, 0);
-        std::vector<char> elig(nnodes, 1);
-        for (int v = 0; v < nnodes; v++) { // children precede parents: the sums of v are final when v is visited
-            ent[v] += round_up4((int64_t)P.p[v] * (P.p[v] + P.u[v]));
-            cols[v] += P.p[v];
-            if (P.p[v] + P.u[v] > opt.st_maxf || P.p[v] > opt.st_pmax || ent[v] > opt.st_budget || cols[v] + P.u[v] > opt.st_maxcols)
-                elig[v] = 0;
-            const int par = P.parent[v];
-            if (par >= 0) {
-                ent[par] += ent[v], size[par] += size[v], cols[par] += cols[v];
-                if (!elig[v]) elig[par] = 0;
-            }
-        }
-        int count = 0;
-        for (int v = 0; v < nnodes; v++)
-            if (elig[v] && (P.parent[v] < 0 || !elig[P.parent[v]])) count++;
-        if (count >= opt.st_min_count)
-            for (int v = 0; v < nnodes; v++)
-                if (elig[v] && (P.parent[v] < 0 || !elig[P.parent[v]])) {
-                    P.st_first.push_back(v - size[v] + 1), P.st_root.push_back(v);
-                    for (int w = v - size[v] + 1; w <= v; w++) P.in_sub[w] = 1;
-                }
-    }
-    int64_t fo = 0, co = 0, dof = 0;
-    {
-        size_t si = 0;
-        for (int v = 0; v < nnodes;) {
-            if (si < P.st_first.size() && P.st_first[si] == v) { // a subtree: all L panels, then all U panels
-                const int r = P.st_root[si++];
-                for (int w = v; w <= r; w++) P.Loff[w] = fo, fo = round_up4(fo + (int64_t)(P.p[w] + P.u[w]) * P.p[w]);
-                for (int w = v; w <= r; w++) P.Uoff[w] = fo, fo = round_up4(fo + (int64_t)P.u[w] * P.p[w]);
-                v = r + 1;
-            } else {
-                const int64_t p = P.p[v], u = P.u[v];
-                P.Loff[v] = fo, fo = round_up4(fo + (p + u) * p);
-                P.Uoff[v] = fo, fo = round_up4(fo + u * p);
-                v++;
-            }
-        }
-    }
-    for (int v = 0; v < nnodes; v++) {
-        int64_t p = P.p[v], u = P.u[v], f = p + u;
-        if (!opt.cb_reuse) P.Coff[v] = co, co = round_up4(co + u * u);
-        P.Doff[v] = dof, dof = round_up4(dof + p * p);
-        P.nnz_L += f * p;
-        P.nnz_U += u * p;
-        P.flops += (2.0 / 3.0) * p * p * p + 2.0 * p * p * u + 2.0 * (double)p * u * u;
-        P.max_front = std::max<int>(P.max_front, (int)f);
-    }
-    if (opt.cb_reuse) {
+    // The contribution-block allocator needs only the tree (levels, u, children): it runs on a helper thread underneath the
+    // row lists, relative indices, subtree layout and scatter map (it was 0.1 s of a 0.55 s symbolic phase at 1M dof).
+    int64_t co_reuse = 0;
+    P.Coff.assign(nnodes, 0);
+    auto alloc_cb = [&]() {
         // Contribution blocks live only from the level that first writes them to the level of their parent, and the
         // device executes the tree level by level: blocks whose lifetimes do not overlap share storage.  (One block per
         // front for the whole factorization costs sum(u^2): 159 GB for a 64^3 27-point grid, TBs at 115^3.)
@@ -738,20 +692,131 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
                     if (size > need) release(off + need, size - need);
                 } else {
                     // grow the arena: a free block that ends at the top is extended instead of wasted
-                    int64_t off = co;
+                    int64_t off = co_reuse;
                     if (!free_by_off.empty()) {
                         auto last = std::prev(free_by_off.end());
-                        if (last->first + last->second == co) { off = last->first; free_by_size.erase({last->second, last->first}); free_by_off.erase(last); }
+                        if (last->first + last->second == co_reuse) { off = last->first; free_by_size.erase({last->second, last->first}); free_by_off.erase(last); }
                     }
                     P.Coff[v] = off;
-                    co = off + need;
+                    co_reuse = off + need;
                 }
             }
             for (int v : dies_at[l]) // reusable from the NEXT level on
                 release(P.Coff[v], round_up4((int64_t)P.u[v] * P.u[v]));
         }
+    };
+    std::thread cb_thread;
+    struct Joiner { // (early error returns below must not leave a running thread behind)
+        std::thread& t;
+        void finish() { if (t.joinable()) t.join(); }
+        ~Joiner() { finish(); }
+    } cb_join{cb_thread};
+    if (opt.cb_reuse) {
+        if (nnodes >= 20000 && !getenv("B200_ND_SERIAL")) cb_thread = std::thread(alloc_cb);
+        else alloc_cb();
     }
-    P.fac_size = fo, P.cb_size = co, P.dinv_size = dof;
+    P.rows.resize(P.rows_ptr[nnodes]);
+    P.rel.assign(P.rows_ptr[nnodes], -1);
+    for (int s = 0; s < ns; s++) {
+        const int K = sn_npieces[s];
+        const int lastcol = grp[s].first + grp[s].ncols - 1;
+        for (int k = 0; k < K; k++) {
+            int v = sn_firstnode[s] + k;
+            int* r = &P.rows[P.rows_ptr[v]];
+            int t = 0;
+            for (int j = P.c0[v] + P.p[v]; j <= lastcol; j++) r[t++] = j; // remaining columns of the supernode
+            for (int i : srows[s]) r[t++] = i;
+            assert(t == P.u[v]);
+        }
+    }
+    if (opt.verbose >= 3) fprintf(stderr, "b200 analyze:     .rows at %.3f s\n", now_s() - t0);
+    // relative indices into the parent front
+    for (int s = 0; s < ns; s++) {
+        const int K = sn_npieces[s];
+        for (int k = 0; k < K; k++) {
+            int v = sn_firstnode[s] + k;
+            int* rel = &P.rel[P.rows_ptr[v]];
+            if (k + 1 < K) {
+                for (int i = 0; i < P.u[v]; i++) rel[i] = i; // the next panel's front is exactly this update set
+            } else if (sparent[s] >= 0) {
+                int t = sparent[s];
+                const int tfirst = grp[t].first, tn = grp[t].ncols;
+                const std::vector<int>& tr = srows[t];
+                size_t w = 0;
+                const int* r = &P.rows[P.rows_ptr[v]];
+                for (int i = 0; i < P.u[v]; i++) {
+                    int gi = r[i];
+                    if (gi < tfirst + tn) {
+                        rel[i] = gi - tfirst;
+                    } else {
+                        while (w < tr.size() && tr[w] < gi) w++;
+                        if (w >= tr.size() || tr[w] != gi) return -2; // structure inconsistency (should not happen)
+                        rel[i] = tn + (int)w;
+                    }
+                }
+            }
+        }
+    }
+    if (opt.verbose >= 3) fprintf(stderr, "b200 analyze:     .rel at %.3f s\n", now_s() - t0);
+    // storage offsets + stats
+    if (opt.verbose >= 2) fprintf(stderr, "b200 analyze:   phase fronttree done at %.3f s\n", now_s() - t0);
+    // ---- solve-phase subtrees: maximal subtrees whose fronts are all small (nodes are in postorder: the subtree rooted at
+    //      v is the contiguous range [v - size + 1, v])
+    P.in_sub.assign(nnodes, 0);
+    if (opt.st_enable) {
+        std::vector<int64_t> ent(nnodes, 0);
+        std::vector<int> size(nnodes, 1), cols(nnodes, 0);
+        std::vector<char> elig(nnodes, 1);
+        for (int v = 0; v < nnodes; v++) { // children precede parents: the sums of v are final when v is visited
+            ent[v] += round_up4((int64_t)P.p[v] * (P.p[v] + P.u[v]));
+            cols[v] += P.p[v];
+            if (P.p[v] + P.u[v] > opt.st_maxf || P.p[v] > opt.st_pmax || ent[v] > opt.st_budget || cols[v] + P.u[v] > opt.st_maxcols)
+                elig[v] = 0;
+            const int par = P.parent[v];
+            if (par >= 0) {
+                ent[par] += ent[v], size[par] += size[v], cols[par] += cols[v];
+                if (!elig[v]) elig[par] = 0;
+            }
+        }
+        int count = 0;
+        for (int v = 0; v < nnodes; v++)
+            if (elig[v] && (P.parent[v] < 0 || !elig[P.parent[v]])) count++;
+        if (count >= opt.st_min_count)
+            for (int v = 0; v < nnodes; v++)
+                if (elig[v] && (P.parent[v] < 0 || !elig[P.parent[v]])) {
+                    P.st_first.push_back(v - size[v] + 1), P.st_root.push_back(v);
+                    for (int w = v - size[v] + 1; w <= v; w++) P.in_sub[w] = 1;
+                }
+    }
+    if (opt.verbose >= 3) fprintf(stderr, "b200 analyze:     .subtrees at %.3f s\n", now_s() - t0);
+    int64_t fo = 0, co = 0, dof = 0;
+    {
+        size_t si = 0;
+        for (int v = 0; v < nnodes;) {
+            if (si < P.st_first.size() && P.st_first[si] == v) { // a subtree: all L panels, then all U panels
+                const int r = P.st_root[si++];
+                for (int w = v; w <= r; w++) P.Loff[w] = fo, fo = round_up4(fo + (int64_t)(P.p[w] + P.u[w]) * P.p[w]);
+                for (int w = v; w <= r; w++) P.Uoff[w] = fo, fo = round_up4(fo + (int64_t)P.u[w] * P.p[w]);
+                v = r + 1;
+            } else {
+                const int64_t p = P.p[v], u = P.u[v];
+                P.Loff[v] = fo, fo = round_up4(fo + (p + u) * p);
+                P.Uoff[v] = fo, fo = round_up4(fo + u * p);
+                v++;
+            }
+        }
+    }
+    for (int v = 0; v < nnodes; v++) {
+        int64_t p = P.p[v], u = P.u[v], f = p + u;
+        if (!opt.cb_reuse) P.Coff[v] = co, co = round_up4(co + u * u);
+        P.Doff[v] = dof, dof = round_up4(dof + p * p);
+        P.nnz_L += f * p;
+        P.nnz_U += u * p;
+        P.flops += (2.0 / 3.0) * p * p * p + 2.0 * p * p * u + 2.0 * (double)p * u * u;
+        P.max_front = std::max<int>(P.max_front, (int)f);
+    }
+    if (opt.verbose >= 3) fprintf(stderr, "b200 analyze:     .layout at %.3f s\n", now_s() - t0);
+    P.fac_size = fo, P.dinv_size = dof;
 
     if (opt.verbose >= 2) fprintf(stderr, "b200 analyze:   phase subtrees+layout+cb done at %.3f s\n", now_s() - t0);
     // ---- value scatter map ---------------------------------------------------------------------------
@@ -796,6 +861,8 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
         }
     }
     });
+    cb_join.finish();
+    P.cb_size = opt.cb_reuse ? co_reuse : co;
     if (scatter_bad) return -2;
     if (opt.verbose >= 2) fprintf(stderr, "b200 analyze:   phase scattermap done at %.3f s\n", now_s() - t0);
     P.t_symbolic = now_s() - t0;

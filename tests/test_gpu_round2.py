@@ -305,7 +305,8 @@ def test_identical_patterns_share_the_host_analysis():
     s2, x2 = _solve(coo2, b)
     st1, st2 = s1.device_stats(), s2.device_stats()
     assert st2["plan_cache_hit"] == 1.0
-    assert st2["t_initialize_host_s"] < st1["t_initialize_host_s"] or st1["plan_cache_hit"] == 1.0
+    # (no assertion on t_initialize_host_s: at this size the analysis is ~20 ms of an initialize whose device allocations
+    # jitter by more than that from call to call; the saving is measured at 1M dof by bench.py / tools/gpu_init_probe.py)
     assert helpers.host_rel_residual(n, ai, aj, ax * 1.5, x2, b) <= TOL_RESIDUAL
     assert np.allclose(x2 * 1.5, x1, rtol=1e-9, atol=0)  # (1.5 A) x2 = b  <=>  x2 = x1 / 1.5
     # a different pattern is analysed afresh; a matrix that needs the matching never takes a shared plan
