@@ -115,7 +115,8 @@ struct InterfaceB200 {
     int force_no_matching = 0;
     int strict_residual = 0; // 1: solve returns B200_ERROR_SOLVE+7 whenever ||b-Ax||/||b|| > 10 ir_tol after refinement
 
-    Plan plan;
+    std::shared_ptr<Plan> plan_sp = std::make_shared<Plan>(); // shared (read-only) with the plan cache and with other handles of the same pattern
+    bool plan_shared = false;
     LevelLists lv;
     int n = 0, nnz_in = 0, fnnz = 0;
     bool sym_lower = false;
@@ -310,7 +311,7 @@ size_t smem_fused(int f, int p) { return ((size_t)(f | 1) * f) * sizeof(double) 
 void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::vector<PanelItem>& panel_items,
                       std::vector<SchurItem>& schur_items, std::vector<int>& fact_nodes, std::vector<int>& solve_nodes,
                       std::vector<int>& asm_ranges, std::vector<OzakiSplitItem>& oz_split, std::vector<OzakiItem>& oz_items) {
-    const Plan& P = s->plan;
+    const Plan& P = (*s->plan_sp);
     LevelLists& lv = s->lv;
     lv.asm_ptr.assign(P.nlevels + 1, 0);
     lv.panel_ptr.assign(P.nlevels + 1, 0);
@@ -487,7 +488,7 @@ size_t smem_schur_dmma() { return (size_t)2 * B200_MAXP * (B200_TS + 8) * sizeof
 // enqueue the per-level numeric kernels: fused fronts (one launch per size class), then the big-front path
 // (assembly -> pivot block -> panels -> Schur complement)
 int enqueue_levels(InterfaceB200* s, int* launches) {
-    const Plan& P = s->plan;
+    const Plan& P = (*s->plan_sp);
     const LevelLists& lv = s->lv;
     const int W = s->opt_panel_width;
     int cnt = 0;
@@ -658,7 +659,7 @@ void k_bwd_top_launch(InterfaceB200* s) {
 }
 
 int enqueue_sweep_levels(InterfaceB200* s, int* launches) {
-    const Plan& P = s->plan;
+    const Plan& P = (*s->plan_sp);
     const LevelLists& lv = s->lv;
     int cnt = 0;
     const int lsplit = s->n_top_items > 0 ? s->ltop : P.nlevels; // levels >= lsplit run in the persistent kernels
@@ -971,24 +972,27 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
                 if (e.h1 == h1 && e.h2 == h2 && e.n == ndim && e.nnz == row_pointers[ndim] && e.sym_lower == want_sym && same_options(e.opt, opt)) hit = e.plan;
         }
         if (hit) {
-            s->plan = *hit; // (a copy: the handle releases parts of its plan after the upload)
+            s->plan_sp = std::const_pointer_cast<Plan>(hit); // no copy: a shared plan is never written again
+            s->plan_shared = true;
             s->plan_cache_hit = 1;
             if (verbose) fprintf(stderr, "solver_b200_initialize:   plan served from the cache (identical pattern analysed before)\n");
         } else {
-            rc = analyze(ndim, row_pointers, col_indices, values, want_sym, opt, s->plan);
-            if (rc == 0 && cache_on && !s->plan.matched && s->plan.rscale.empty()) {
+            s->plan_sp = std::make_shared<Plan>();
+            s->plan_shared = false;
+            rc = analyze(ndim, row_pointers, col_indices, values, want_sym, opt, *s->plan_sp);
+            if (rc == 0 && cache_on && !s->plan_sp->matched && s->plan_sp->rscale.empty()) {
                 if (h1 == 0 && h2 == 0) hash_pattern(ndim, row_pointers, col_indices, h1, h2);
-                auto copy = std::make_shared<const Plan>(s->plan);
+                s->plan_shared = true; // the cache and this handle hold the same object (copying ~150 MB at 1M dof cost tens of ms)
                 std::lock_guard<std::mutex> lock(g_plan_mu);
                 if (g_plan_cache.size() >= 3) g_plan_cache.erase(g_plan_cache.begin());
-                g_plan_cache.push_back({h1, h2, ndim, row_pointers[ndim], want_sym, opt, copy});
+                g_plan_cache.push_back({h1, h2, ndim, row_pointers[ndim], want_sym, opt, s->plan_sp});
             }
         }
     }
     if (rc == -1) return B200_ERROR_SINGULAR;
     if (rc != 0) return B200_ERROR_ANALYSIS + 2;
     if (verbose) fprintf(stderr, "solver_b200_initialize:   analysis done at %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_host0).count());
-    Plan& P = s->plan;
+    Plan& P = (*s->plan_sp);
     s->n = P.n;
     s->nnz_in = P.nnz_in;
     s->sym_lower = P.sym_lower;
@@ -1209,10 +1213,8 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     s->cdone_init = cdone_init;
     s->n_slots = nslots;
     UP(d_a_src, P.a_src);
-    {
-        std::vector<long long> dst(P.a_dst.begin(), P.a_dst.end());
-        UP(d_a_dst, dst);
-    }
+    static_assert(sizeof(long long) == sizeof(int64_t), "a_dst is uploaded as it is");
+    CUDA_TRY(upload(reinterpret_cast<int64_t**>(&s->d_a_dst), P.a_dst), B200_ERROR_CUDA_MALLOC);
     if (!P.a_scl.empty()) UP(d_a_scl, P.a_scl);
     UP(d_rowperm, P.rowperm);
     UP(d_colperm, P.colperm);
@@ -1303,13 +1305,15 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     s->sptrsv_bytes = 8.0 * ((double)P.nnz_L + (double)P.nnz_U) + 16.0 * P.n;
     s->spmv_bytes = 12.0 * s->fnnz + 4.0 * (P.n + 1) + 16.0 * P.n;
 
-    // host-side plan arrays that are no longer needed
-    std::vector<int>().swap(P.a_src);
-    std::vector<int64_t>().swap(P.a_dst);
-    std::vector<double>().swap(P.a_scl);
-    std::vector<int>().swap(P.full_col);
-    std::vector<int>().swap(P.full_src);
-    std::vector<int>().swap(P.rel);
+    // host-side plan arrays that are no longer needed (a plan that lives in the cache keeps them for the next handle)
+    if (!s->plan_shared) {
+        std::vector<int>().swap(P.a_src);
+        std::vector<int64_t>().swap(P.a_dst);
+        std::vector<double>().swap(P.a_scl);
+        std::vector<int>().swap(P.full_col);
+        std::vector<int>().swap(P.full_src);
+        std::vector<int>().swap(P.rel);
+    }
 
     CUDA_TRY(cudaStreamSynchronize(s->stream), B200_ERROR_CUDA_SYNCHRONIZE);
     if (verbose) {
@@ -1332,7 +1336,7 @@ int32_t solver_b200_factorize_device(struct InterfaceB200* s, const double* d_va
     if (!s->initialized) return B200_ERROR_NEED_INITIALIZATION;
     if (!d_values) return B200_ERROR_NULL_POINTER;
     CUDA_TRY(cudaSetDevice(s->device), B200_ERROR_NOT_AVAILABLE);
-    const Plan& P = s->plan;
+    const Plan& P = (*s->plan_sp);
     s->factorized = false;
     s->rcond = -1.0;
     if (s->sweep_dirty) { // re-arm the dependency counters of the persistent sweep after an aborted solve
@@ -1392,7 +1396,7 @@ static void clear_fac_under_h2d(InterfaceB200* s) {
     if (!s->side || !s->ev_clr0 || !s->ev_clr1) return;
     if (cudaEventRecord(s->ev_clr0, s->stream) != cudaSuccess) return; // (orders the clear after the previous solve's reads)
     cudaStreamWaitEvent(s->side, s->ev_clr0, 0);
-    if (cudaMemsetAsync(s->d_fac, 0, (size_t)s->plan.fac_size * sizeof(double), s->side) != cudaSuccess) return;
+    if (cudaMemsetAsync(s->d_fac, 0, (size_t)(*s->plan_sp).fac_size * sizeof(double), s->side) != cudaSuccess) return;
     cudaEventRecord(s->ev_clr1, s->side);
     s->fac_cleared = true;
 }
@@ -1619,7 +1623,7 @@ int32_t solver_b200_determinant(struct InterfaceB200* s, double* coefficient, do
     if (!s || !coefficient || !exponent) return B200_ERROR_NULL_POINTER;
     if (!s->factorized) return B200_ERROR_NEED_FACTORIZATION;
     CUDA_TRY(cudaSetDevice(s->device), B200_ERROR_NOT_AVAILABLE);
-    const Plan& P = s->plan;
+    const Plan& P = (*s->plan_sp);
     const int n = s->n;
     std::vector<double> up(n);
     std::vector<int> lp(n);
@@ -1741,7 +1745,7 @@ int32_t solver_b200_rcond(struct InterfaceB200* s, double* rcond) {
 int32_t solver_b200_get_stats(struct InterfaceB200* s, double* out, int32_t n_out) {
     if (!s || !out) return B200_ERROR_NULL_POINTER;
     if (!s->initialized) return B200_ERROR_NEED_INITIALIZATION;
-    const Plan& P = s->plan;
+    const Plan& P = (*s->plan_sp);
     double v[B200_STAT_COUNT];
     v[B200_STAT_NNODES] = P.nnodes;
     v[B200_STAT_NLEVELS] = P.nlevels;
@@ -1792,7 +1796,7 @@ int32_t solver_b200_debug_trace(struct InterfaceB200* s, unsigned long long* out
         std::vector<SolveItem> items(s->n_top_items);
         cudaMemcpy(items.data(), s->d_top_items, items.size() * sizeof(SolveItem), cudaMemcpyDeviceToHost);
         for (int i = 0; i < n; i++) {
-            desc[4 * i] = items[i].node, desc[4 * i + 1] = s->plan.level[items[i].node];
+            desc[4 * i] = items[i].node, desc[4 * i + 1] = (*s->plan_sp).level[items[i].node];
             desc[4 * i + 2] = items[i].slice, desc[4 * i + 3] = items[i].nrows;
         }
     }
@@ -1814,14 +1818,14 @@ int32_t solver_b200_debug_copy_factors(struct InterfaceB200* s, double* fac, int
         CUDA_TRY(cudaStreamSynchronize(s->stream), B200_ERROR_CUDA_SYNCHRONIZE);
     }
     if (dinv) {
-        CUDA_TRY(cudaMemcpy(dinv, s->d_dinv, std::min<int64_t>(dinv_len, s->plan.dinv_size) * sizeof(double), cudaMemcpyDeviceToHost), B200_ERROR_CUDA_MEMCPY);
+        CUDA_TRY(cudaMemcpy(dinv, s->d_dinv, std::min<int64_t>(dinv_len, (*s->plan_sp).dinv_size) * sizeof(double), cudaMemcpyDeviceToHost), B200_ERROR_CUDA_MEMCPY);
         if (s->n_subtrees > 0 && !s->inv_skip_ptr.empty() && s->inv_skip_ptr[NIC] > 0) { // give the subtree fronts their packed pivot blocks back
             const int nn = s->inv_skip_ptr[NIC];
             k_pack_pivot_blocks<<<std::min((nn + 7) / 8, 148 * 8), 256, 0, s->stream>>>(s->d_inv_skip, nn, s->d_nodes, s->d_fac, s->d_dinv);
             CUDA_TRY(cudaStreamSynchronize(s->stream), B200_ERROR_CUDA_SYNCHRONIZE);
         }
     }
-    if (fac) CUDA_TRY(cudaMemcpy(fac, s->d_fac, std::min<int64_t>(fac_len, s->plan.fac_size) * sizeof(double), cudaMemcpyDeviceToHost), B200_ERROR_CUDA_MEMCPY);
+    if (fac) CUDA_TRY(cudaMemcpy(fac, s->d_fac, std::min<int64_t>(fac_len, (*s->plan_sp).fac_size) * sizeof(double), cudaMemcpyDeviceToHost), B200_ERROR_CUDA_MEMCPY);
     if (lperm) CUDA_TRY(cudaMemcpy(lperm, s->d_lperm, std::min<int64_t>(n, s->n) * sizeof(int), cudaMemcpyDeviceToHost), B200_ERROR_CUDA_MEMCPY);
     return B200_SUCCESSFUL_EXIT;
 }

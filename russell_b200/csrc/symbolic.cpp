@@ -178,16 +178,23 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
     const int nnz = rowptr[n];
     P.nnz_in = nnz;
     if (rowptr[0] != 0 || nnz < 1) return -2;
-    for (int i = 0; i < n; i++) {
+    for (int i = 0; i < n; i++)
         if (rowptr[i + 1] < rowptr[i]) return -2;
-        for (int k = rowptr[i]; k < rowptr[i + 1]; k++) {
-            int j = colidx[k];
-            if (j < 0 || j >= n) return -2;
-            if (sym_lower && j > i) return -2;
-            // the CSR contract (csr_matrix.rs:359-480): columns ascending, duplicates already summed.  A duplicate would make
-            // the value scatter last-writer-wins while the SpMV sums it, so it is rejected rather than tolerated.
-            if (!sym_lower && k > rowptr[i] && j <= colidx[k - 1]) return -2;
-        }
+    {
+        std::atomic<int> bad{0};
+        parallel_rows(n, [&](int ibeg, int iend) {
+            for (int i = ibeg; i < iend; i++)
+                for (int k = rowptr[i]; k < rowptr[i + 1]; k++) {
+                    const int j = colidx[k];
+                    // the CSR contract (csr_matrix.rs:359-480): columns ascending, duplicates already summed.  A duplicate would make
+                    // the value scatter last-writer-wins while the SpMV sums it, so it is rejected rather than tolerated.
+                    if (j < 0 || j >= n || (sym_lower && j > i) || (!sym_lower && k > rowptr[i] && j <= colidx[k - 1])) {
+                        bad = 1;
+                        return;
+                    }
+                }
+        });
+        if (bad) return -2;
     }
     const int W = std::max(4, std::min(opt.panel_width, 128));
 
@@ -536,7 +543,14 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
             relabel_graph(g, order, g2);
             g.ptr.swap(g2.ptr);
             g.adj.swap(g2.adj);
-            etree_symmetric(g, parent);
+            // `order` lists every vertex before its elimination-tree parent (merged children before their parent's columns,
+            // child groups before parent groups): an equivalent reordering, so the tree of the new labelling is the old one renamed
+            {
+                std::vector<int> newid(n), par2(n);
+                for (int k = 0; k < n; k++) newid[order[k]] = k;
+                for (int k = 0; k < n; k++) par2[k] = parent[order[k]] < 0 ? -1 : newid[parent[order[k]]];
+                parent.swap(par2);
+            }
             for (int k = 0; k < n; k++) invq[q[k]] = k;
             P.colperm = q;
             for (int k = 0; k < n; k++) P.rowperm[k] = rowmatch[q[k]];
@@ -678,6 +692,7 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
             free_by_off[off] = size;
             free_by_size.insert({size, off});
         };
+        std::vector<std::pair<int64_t, int64_t>> dying;
         for (int l = 0; l < nlev; l++) {
             // largest first: big blocks take the big holes
             std::sort(born_at[l].begin(), born_at[l].end(), [&](int a, int b) { return P.u[a] != P.u[b] ? P.u[a] > P.u[b] : a < b; });
@@ -701,8 +716,19 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
                     co_reuse = off + need;
                 }
             }
-            for (int v : dies_at[l]) // reusable from the NEXT level on
-                release(P.Coff[v], round_up4((int64_t)P.u[v] * P.u[v]));
+            // reusable from the NEXT level on.  The blocks that die together are merged among themselves first (sorted by
+            // offset, one linear pass): the free set after a batch of releases does not depend on their order, and the
+            // balanced trees then see one operation per run instead of one per block (the bottom levels free ~80k blocks each)
+            dying.clear();
+            for (int v : dies_at[l]) dying.push_back({P.Coff[v], round_up4((int64_t)P.u[v] * P.u[v])});
+            std::sort(dying.begin(), dying.end());
+            for (size_t i = 0; i < dying.size();) {
+                int64_t off = dying[i].first, size = dying[i].second;
+                size_t j = i + 1;
+                while (j < dying.size() && dying[j].first == off + size) size += dying[j].second, j++;
+                release(off, size);
+                i = j;
+            }
         }
     };
     std::thread cb_thread;
