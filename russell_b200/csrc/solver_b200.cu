@@ -68,6 +68,7 @@ struct LevelLists {
     std::vector<int> solve_threads, solve_pmax; // per level: block size and largest pivot count of the small launch
     std::vector<int> big_ptr; // nlevels+1: slices of the big solve class inside d_big_items
     std::vector<int> inv_ptr; // NIC+1: fronts by pivot-count class inside d_inv_nodes
+    std::vector<int> inv_mid; // NIC: first front of the class that waits for the end of the level loop (the ones before it lie below inv_split_level)
     std::vector<size_t> fused_smem; // per (level, class): dynamic shared memory of the fused launch
     // k_front_warp: the fronts of a (level, class) range are sorted by order and cut into size buckets, one launch each
     // (shared memory per warp follows the bucket's largest front: small fronts get more resident warps)
@@ -191,6 +192,15 @@ struct InterfaceB200 {
     cudaStream_t lvl_side[NLS] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[NLS] = {nullptr, nullptr, nullptr};
     int use_level_fork = 1;
+    // The explicit pivot-block inverses (and the packed pivot blocks of the subtree fronts) are needed by the solve phase
+    // only.  Those of the fronts below `inv_split_level` -- the level from which every level holds just a few big fronts, the
+    // latency-bound chain at the top of the tree -- are computed on a low-priority branch forked at that level, in the
+    // shadow of the chain; the fronts of the chain itself follow after the level loop as before.
+    cudaStream_t inv_side = nullptr;
+    cudaEvent_t ev_inv0 = nullptr, ev_inv1 = nullptr;
+    int inv_overlap = 1;      // option "inv_overlap" / B200_INV_OVERLAP
+    int inv_split_level = -1; // -1: no early branch
+    bool pack_early = false;  // the subtree fronts all lie below the split level
     int fused_variant = 2;  // 0 = shared-memory LU (k_front_fused), 1 = register-resident (k_front_fused_w8) for f <= 64,
                             // 2 = register-resident only for launches of at most fused_w8_max fronts (measured crossover)
     int fused_w8_max = 2000;
@@ -492,7 +502,31 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
     const LevelLists& lv = s->lv;
     const int W = s->opt_panel_width;
     int cnt = 0;
+    auto invert_range = [&](int c, int a, int b, cudaStream_t st) {
+        if (b > a) {
+            k_invert_col<<<b - a, 2 * IC_MAXP[c], smem_invert(IC_MAXP[c]), st>>>(s->d_inv_nodes + a, s->d_nodes, s->d_fac, s->d_dinv, IC_MAXP[c], b - a);
+            cnt++;
+        }
+    };
+    auto pack_blocks = [&](cudaStream_t st) {
+        if (s->n_subtrees > 0 && !s->inv_skip_ptr.empty() && s->inv_skip_ptr[NIC] > 0) {
+            // pivot blocks of the subtree fronts, packed for the subtree solve kernels (they keep no explicit inverses)
+            const int nn = s->inv_skip_ptr[NIC];
+            k_pack_pivot_blocks<<<std::min((nn + 7) / 8, 148 * 8), 256, 0, st>>>(s->d_inv_skip, nn, s->d_nodes, s->d_fac, s->d_dinv);
+            cnt++;
+        }
+    };
+    const bool early = s->inv_split_level > 0 && s->inv_split_level < P.nlevels && (int)lv.inv_mid.size() == NIC;
     for (int l = 0; l < P.nlevels; l++) {
+        if (early && l == s->inv_split_level) {
+            // every front below this level is final (a pivot block is factorized at its own level at the latest): their
+            // inverses run on a low-priority branch while the chain levels above proceed
+            cudaEventRecord(s->ev_inv0, s->stream);
+            cudaStreamWaitEvent(s->inv_side, s->ev_inv0, 0);
+            for (int c = NIC - 1; c >= 0; c--) invert_range(c, lv.inv_ptr[c], lv.inv_mid[c], s->inv_side); // the long class first
+            if (s->pack_early) pack_blocks(s->inv_side);
+            cudaEventRecord(s->ev_inv1, s->inv_side);
+        }
         const int* fp = &lv.fact_ptr[(size_t)l * (NFC + 1)];
         // independent launch groups of this level: fused classes / buckets + the big-front sequence
         int ngroups = (fp[NFC + 1] - fp[NFC] > 0) ? 1 : 0;
@@ -613,21 +647,10 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
         join();
     }
     // explicit inverses of the pivot blocks, all fronts outside the subtree region in one batched launch per size class:
-    // only the solve phase needs them
-    for (int c = 0; c < NIC; c++) {
-        int nn = lv.inv_ptr[c + 1] - lv.inv_ptr[c];
-        if (nn > 0) {
-            k_invert_col<<<nn, 2 * IC_MAXP[c], smem_invert(IC_MAXP[c]), s->stream>>>(s->d_inv_nodes + lv.inv_ptr[c], s->d_nodes, s->d_fac, s->d_dinv,
-                                                                                      IC_MAXP[c], nn);
-            cnt++;
-        }
-    }
-    if (s->n_subtrees > 0 && !s->inv_skip_ptr.empty() && s->inv_skip_ptr[NIC] > 0) {
-        // pivot blocks of the subtree fronts, packed for the subtree solve kernels (they keep no explicit inverses)
-        const int nn = s->inv_skip_ptr[NIC];
-        k_pack_pivot_blocks<<<std::min((nn + 7) / 8, 148 * 8), 256, 0, s->stream>>>(s->d_inv_skip, nn, s->d_nodes, s->d_fac, s->d_dinv);
-        cnt++;
-    }
+    // only the solve phase needs them (with the early branch: the fronts of the top levels only)
+    for (int c = 0; c < NIC; c++) invert_range(c, early ? lv.inv_mid[c] : lv.inv_ptr[c], lv.inv_ptr[c + 1], s->stream);
+    if (!(early && s->pack_early)) pack_blocks(s->stream);
+    if (early) cudaStreamWaitEvent(s->stream, s->ev_inv1, 0); // join
     if (launches) *launches = cnt;
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
@@ -789,6 +812,9 @@ static bool create_streams(InterfaceB200* s) {
     if (cudaEventCreateWithFlags(&s->ev_clr0, cudaEventDisableTiming) != cudaSuccess) return false;
     if (cudaEventCreateWithFlags(&s->ev_clr1, cudaEventDisableTiming) != cudaSuccess) return false;
     if (cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) != cudaSuccess) return false;
+    if (cudaStreamCreateWithPriority(&s->inv_side, cudaStreamNonBlocking, lo) != cudaSuccess) return false;
+    if (cudaEventCreateWithFlags(&s->ev_inv0, cudaEventDisableTiming) != cudaSuccess) return false;
+    if (cudaEventCreateWithFlags(&s->ev_inv1, cudaEventDisableTiming) != cudaSuccess) return false;
     for (int i = 0; i < InterfaceB200::NLS; i++) {
         if (cudaStreamCreateWithPriority(&s->lvl_side[i], cudaStreamNonBlocking, hi) != cudaSuccess) return false;
         if (cudaEventCreateWithFlags(&s->ev_join[i], cudaEventDisableTiming) != cudaSuccess) return false;
@@ -799,6 +825,9 @@ static void destroy_streams(InterfaceB200* s) {
     if (s->ev_clr0) cudaEventDestroy(s->ev_clr0), s->ev_clr0 = nullptr;
     if (s->ev_clr1) cudaEventDestroy(s->ev_clr1), s->ev_clr1 = nullptr;
     if (s->ev_fork) cudaEventDestroy(s->ev_fork), s->ev_fork = nullptr;
+    if (s->ev_inv0) cudaEventDestroy(s->ev_inv0), s->ev_inv0 = nullptr;
+    if (s->ev_inv1) cudaEventDestroy(s->ev_inv1), s->ev_inv1 = nullptr;
+    if (s->inv_side) cudaStreamDestroy(s->inv_side), s->inv_side = nullptr;
     for (int i = 0; i < InterfaceB200::NLS; i++) {
         if (s->ev_join[i]) cudaEventDestroy(s->ev_join[i]), s->ev_join[i] = nullptr;
         if (s->lvl_side[i]) cudaStreamDestroy(s->lvl_side[i]), s->lvl_side[i] = nullptr;
@@ -838,6 +867,7 @@ struct InterfaceB200* solver_b200_new(void) {
     if ((e = getenv("B200_USE_FRONT_WARP"))) s->use_front_warp = atoi(e);
     if ((e = getenv("B200_USE_LEAF_REG"))) s->use_leaf_reg = atoi(e);
     if ((e = getenv("B200_USE_LEVEL_FORK"))) s->use_level_fork = atoi(e);
+    if ((e = getenv("B200_INV_OVERLAP"))) s->inv_overlap = atoi(e);
     if ((e = getenv("B200_FUSED_W8_MAX"))) s->fused_w8_max = atoi(e);
     if ((e = getenv("B200_USE_LEAF_REG"))) s->use_leaf_reg = atoi(e);
     if ((e = getenv("B200_ASM_VARIANT"))) s->asm_variant = atoi(e);
@@ -890,6 +920,7 @@ int32_t solver_b200_set_option(struct InterfaceB200* s, const char* key, double 
     else if (k == "fused_w8_max") s->fused_w8_max = (int)value;
     else if (k == "use_front_warp") s->use_front_warp = value != 0.0;
     else if (k == "use_level_fork") s->use_level_fork = value != 0.0;
+    else if (k == "inv_overlap") s->inv_overlap = value != 0.0;
     else if (k == "use_fused") s->use_fused = value != 0.0;
     else if (k == "use_top") s->use_top = value != 0.0;
     else if (k == "trace") s->want_trace = value != 0.0;
@@ -1167,15 +1198,34 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     UP(d_fact_nodes, fact_nodes);
     UP(d_solve_nodes, solve_nodes);
     {
-        // fronts that need explicit pivot-block inverses (everything outside the subtree region), by pivot-count class
+        // fronts that need explicit pivot-block inverses (everything outside the subtree region), by pivot-count class;
+        // within a class first the fronts below the split level (inverted on the early branch), then the rest
+        s->inv_split_level = -1;
+        s->pack_early = false;
+        if (s->inv_overlap) {
+            std::vector<int> nbig(P.nlevels, 0); // fronts per level outside the subtree region
+            int sub_top = -1;
+            for (int v = 0; v < P.nnodes; v++) {
+                if (s->in_sub[v]) sub_top = std::max(sub_top, P.level[v]);
+                else nbig[P.level[v]]++;
+            }
+            int l = P.nlevels;
+            while (l > 0 && nbig[l - 1] <= 16) l--;
+            if (l >= 1 && P.nlevels - l >= 8) s->inv_split_level = l, s->pack_early = sub_top < l;
+        }
         std::vector<int> inv_nodes;
         s->lv.inv_ptr.assign(NIC + 1, 0);
+        s->lv.inv_mid.assign(NIC, 0);
         for (int c = 0; c < NIC; c++) {
-            for (int v = 0; v < P.nnodes; v++) {
-                int cls = 0;
-                while (cls < NIC - 1 && P.p[v] > IC_MAXP[cls]) cls++;
-                if (s->in_sub[v]) continue; // the subtree kernels substitute with L11 / U11 directly (their slots hold the packed pivot blocks)
-                if (cls == c) inv_nodes.push_back(v);
+            for (int pass = 0; pass < 2; pass++) {
+                if (pass == 1) s->lv.inv_mid[c] = (int)inv_nodes.size();
+                for (int v = 0; v < P.nnodes; v++) {
+                    int cls = 0;
+                    while (cls < NIC - 1 && P.p[v] > IC_MAXP[cls]) cls++;
+                    if (s->in_sub[v]) continue; // the subtree kernels substitute with L11 / U11 directly (their slots hold the packed pivot blocks)
+                    const bool is_early = s->inv_split_level > 0 && P.level[v] < s->inv_split_level;
+                    if (cls == c && is_early == (pass == 0)) inv_nodes.push_back(v);
+                }
             }
             s->lv.inv_ptr[c + 1] = (int)inv_nodes.size();
         }
