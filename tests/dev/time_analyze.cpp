@@ -34,6 +34,23 @@ int main(int argc, char** argv) {
             if (i < k - 1) col.push_back(r + k), val.push_back(-1);
             ptr[r + 1] = (int)col.size();
         }
+    if (getenv("G3")) { // 7-point Laplacian on a k^3 grid instead
+        const int k3 = atoi(getenv("G3"));
+        ptr.assign(1, 0), col.clear(), val.clear();
+        for (int z = 0; z < k3; z++)
+            for (int y = 0; y < k3; y++)
+                for (int x = 0; x < k3; x++) {
+                    const int r = (z * k3 + y) * k3 + x;
+                    if (z > 0) col.push_back(r - k3 * k3), val.push_back(-1);
+                    if (y > 0) col.push_back(r - k3), val.push_back(-1);
+                    if (x > 0) col.push_back(r - 1), val.push_back(-1);
+                    col.push_back(r), val.push_back(6);
+                    if (x < k3 - 1) col.push_back(r + 1), val.push_back(-1);
+                    if (y < k3 - 1) col.push_back(r + k3), val.push_back(-1);
+                    if (z < k3 - 1) col.push_back(r + k3 * k3), val.push_back(-1);
+                    ptr.push_back((int)col.size());
+                }
+    }
     if (getenv("SKEW")) { // unsymmetric pattern: drop the west neighbour of every third row (exercises the A+A^T graph)
         std::vector<int> p2(n + 1, 0), c2;
         std::vector<double> v2;
@@ -47,10 +64,12 @@ int main(int argc, char** argv) {
     for (int rep = 0; rep < (argc > 2 ? atoi(argv[2]) : 2); rep++) {
         b200::AnalyzeOptions opt;
         opt.matching = 2;
+        if (getenv("NDLEAF")) opt.nd_leaf = atoi(getenv("NDLEAF"));
+        if (getenv("Z2")) opt.relax_z2 = atof(getenv("Z2"));
         opt.verbose = getenv("V") ? atoi(getenv("V")) : 2;
         b200::Plan P;
         auto t0 = std::chrono::steady_clock::now();
-        int rc = b200::analyze(n, ptr.data(), col.data(), val.data(), false, opt, P);
+        int rc = b200::analyze((int)ptr.size() - 1, ptr.data(), col.data(), val.data(), false, opt, P);
         double t = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         printf("analyze rc=%d: %.3f s (match %.3f, order %.3f, symbolic %.3f), fronts %d, nnz %lld, flops %.3e\n", rc, t, P.t_match, P.t_order,
                P.t_symbolic, P.nnodes, (long long)(P.nnz_L + P.nnz_U), P.flops);
