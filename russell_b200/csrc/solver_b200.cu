@@ -61,7 +61,6 @@ static const int SC_MAXP[NSC] = {32, B200_MAXP, B200_MAXP};
 struct LevelLists {
     // offsets (nlevels+1) into the concatenated device item arrays (big fronts only)
     std::vector<int> asm_ptr, panel_ptr, schur_ptr;
-    std::vector<int> asm_mid; // per level: first extend-add tile without pivot columns (the tiles before it feed the pivot-block LU)
     // fact_ptr[l*(NFC+1)+c .. +1]: nodes of level l and factorization class c inside d_fact_nodes (class NFC = big)
     std::vector<int> fact_ptr;
     // solve_ptr[l*NSC+c .. +1] inside d_solve_nodes
@@ -197,12 +196,6 @@ struct InterfaceB200 {
     // only.  Those of the fronts below `inv_split_level` -- the level from which every level holds just a few big fronts, the
     // latency-bound chain at the top of the tree -- are computed on a low-priority branch forked at that level, in the
     // shadow of the chain; the fronts of the chain itself follow after the level loop as before.
-    // Extend-add tiles that hold no pivot column (the U-panel rows and the contribution block: most of a front) are not read by
-    // the pivot-block LU: they run on a branch beside it ("asm_split"); the panels wait for both.
-    cudaStream_t asm_side = nullptr;
-    cudaEvent_t ev_asm0 = nullptr, ev_asm1 = nullptr;
-    int asm_split = 1;
-    int top_occ = 0; // > 0: at most this many CTAs per SM for the persistent sweep kernels (option "top_occ"; 0 = what fits)
     cudaStream_t inv_side = nullptr;
     cudaEvent_t ev_inv0 = nullptr, ev_inv1 = nullptr;
     int inv_overlap = 1;      // option "inv_overlap" / B200_INV_OVERLAP
@@ -331,7 +324,6 @@ void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::ve
     const Plan& P = (*s->plan_sp);
     LevelLists& lv = s->lv;
     lv.asm_ptr.assign(P.nlevels + 1, 0);
-    lv.asm_mid.assign(P.nlevels, 0);
     lv.panel_ptr.assign(P.nlevels + 1, 0);
     lv.schur_ptr.assign(P.nlevels + 1, 0);
     lv.fact_ptr.assign((size_t)P.nlevels * (NFC + 1) + 1, 0);
@@ -489,9 +481,6 @@ void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::ve
                 }
             }
         }
-        // tiles that hold pivot columns first: the pivot-block LU waits for them only (the items of a level are independent)
-        lv.asm_mid[l] = (int)(std::stable_partition(asm_items.begin() + lv.asm_ptr[l], asm_items.end(),
-                                                    [&P](const AsmItem& a) { return a.t0 < P.p[a.node]; }) - asm_items.begin());
         lv.asm_ptr[l + 1] = (int)asm_items.size();
         lv.panel_ptr[l + 1] = (int)panel_items.size();
         lv.schur_ptr[l + 1] = (int)schur_items.size();
@@ -609,27 +598,14 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
             join();
             continue;
         }
-        const int na = lv.asm_ptr[l + 1] - lv.asm_ptr[l];
-        bool asm_forked = false;
+        int na = lv.asm_ptr[l + 1] - lv.asm_ptr[l];
         if (na > 0) {
-            auto assemble = [&](int a, int b, cudaStream_t st) {
-                if (s->asm_variant == 1 && lv.asm_smem[l] <= (size_t)B200_ASM_SMEM_MAX) // tile in shared memory
-                    k_assemble_tile<<<b - a, 256, lv.asm_smem[l], st>>>(s->d_asm + a, s->d_nodes, s->d_child_idx, s->d_rel, s->d_asm_ranges, s->d_fac, s->d_cb);
-                else
-                    k_assemble<<<b - a, 256, 0, st>>>(s->d_asm + a, s->d_nodes, s->d_child_idx, s->d_rel, s->d_asm_ranges, s->d_fac, s->d_cb);
-                cnt++;
-            };
-            const int a0 = lv.asm_ptr[l], am = lv.asm_mid[l], a1 = lv.asm_ptr[l + 1];
-            if (s->asm_split && lv.diag_cnt[l] > 0 && am > a0 && am < a1) {
-                // the tiles without pivot columns run beside the pivot-block LU; the panels wait for both
-                cudaEventRecord(s->ev_asm0, s->stream);
-                cudaStreamWaitEvent(s->asm_side, s->ev_asm0, 0);
-                assemble(am, a1, s->asm_side);
-                cudaEventRecord(s->ev_asm1, s->asm_side);
-                assemble(a0, am, s->stream);
-                asm_forked = true;
-            } else
-                assemble(a0, a1, s->stream);
+            if (s->asm_variant == 1 && lv.asm_smem[l] <= (size_t)B200_ASM_SMEM_MAX) // tile in shared memory
+                k_assemble_tile<<<na, 256, lv.asm_smem[l], s->stream>>>(s->d_asm + lv.asm_ptr[l], s->d_nodes, s->d_child_idx, s->d_rel,
+                                                                      s->d_asm_ranges, s->d_fac, s->d_cb);
+            else
+                k_assemble<<<na, 256, 0, s->stream>>>(s->d_asm + lv.asm_ptr[l], s->d_nodes, s->d_child_idx, s->d_rel, s->d_asm_ranges, s->d_fac, s->d_cb);
+            cnt++;
         }
         const int ndiag = lv.diag_cnt[l]; // big fronts whose pivot block was NOT factorized by their chain child's Schur CTA (they come first)
         if (ndiag > 0) {
@@ -641,7 +617,6 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
                                                                 s->d_lperm, s->d_upiv, s->d_amax, s->pivot_eps, s->d_counters);
             cnt++;
         }
-        if (asm_forked) cudaStreamWaitEvent(s->stream, s->ev_asm1, 0); // join: panels and Schur tiles read the whole front
         int np = lv.panel_ptr[l + 1] - lv.panel_ptr[l];
         if (np > 0) {
             if (s->panel_variant == 1 && np <= s->panel_row_max) // few rows: the launch is latency bound
@@ -838,9 +813,6 @@ static bool create_streams(InterfaceB200* s) {
     if (cudaEventCreateWithFlags(&s->ev_clr1, cudaEventDisableTiming) != cudaSuccess) return false;
     if (cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) != cudaSuccess) return false;
     if (cudaStreamCreateWithPriority(&s->inv_side, cudaStreamNonBlocking, lo) != cudaSuccess) return false;
-    if (cudaStreamCreateWithPriority(&s->asm_side, cudaStreamNonBlocking, hi) != cudaSuccess) return false;
-    if (cudaEventCreateWithFlags(&s->ev_asm0, cudaEventDisableTiming) != cudaSuccess) return false;
-    if (cudaEventCreateWithFlags(&s->ev_asm1, cudaEventDisableTiming) != cudaSuccess) return false;
     if (cudaEventCreateWithFlags(&s->ev_inv0, cudaEventDisableTiming) != cudaSuccess) return false;
     if (cudaEventCreateWithFlags(&s->ev_inv1, cudaEventDisableTiming) != cudaSuccess) return false;
     for (int i = 0; i < InterfaceB200::NLS; i++) {
@@ -856,9 +828,6 @@ static void destroy_streams(InterfaceB200* s) {
     if (s->ev_inv0) cudaEventDestroy(s->ev_inv0), s->ev_inv0 = nullptr;
     if (s->ev_inv1) cudaEventDestroy(s->ev_inv1), s->ev_inv1 = nullptr;
     if (s->inv_side) cudaStreamDestroy(s->inv_side), s->inv_side = nullptr;
-    if (s->ev_asm0) cudaEventDestroy(s->ev_asm0), s->ev_asm0 = nullptr;
-    if (s->ev_asm1) cudaEventDestroy(s->ev_asm1), s->ev_asm1 = nullptr;
-    if (s->asm_side) cudaStreamDestroy(s->asm_side), s->asm_side = nullptr;
     for (int i = 0; i < InterfaceB200::NLS; i++) {
         if (s->ev_join[i]) cudaEventDestroy(s->ev_join[i]), s->ev_join[i] = nullptr;
         if (s->lvl_side[i]) cudaStreamDestroy(s->lvl_side[i]), s->lvl_side[i] = nullptr;
@@ -899,7 +868,6 @@ struct InterfaceB200* solver_b200_new(void) {
     if ((e = getenv("B200_USE_LEAF_REG"))) s->use_leaf_reg = atoi(e);
     if ((e = getenv("B200_USE_LEVEL_FORK"))) s->use_level_fork = atoi(e);
     if ((e = getenv("B200_INV_OVERLAP"))) s->inv_overlap = atoi(e);
-    if ((e = getenv("B200_ASM_SPLIT"))) s->asm_split = atoi(e);
     if ((e = getenv("B200_FUSED_W8_MAX"))) s->fused_w8_max = atoi(e);
     if ((e = getenv("B200_USE_LEAF_REG"))) s->use_leaf_reg = atoi(e);
     if ((e = getenv("B200_ASM_VARIANT"))) s->asm_variant = atoi(e);
@@ -953,8 +921,6 @@ int32_t solver_b200_set_option(struct InterfaceB200* s, const char* key, double 
     else if (k == "use_front_warp") s->use_front_warp = value != 0.0;
     else if (k == "use_level_fork") s->use_level_fork = value != 0.0;
     else if (k == "inv_overlap") s->inv_overlap = value != 0.0;
-    else if (k == "asm_split") s->asm_split = value != 0.0;
-    else if (k == "top_occ") s->top_occ = std::max(0, (int)value);
     else if (k == "use_fused") s->use_fused = value != 0.0;
     else if (k == "use_top") s->use_top = value != 0.0;
     else if (k == "trace") s->want_trace = value != 0.0;
@@ -1378,7 +1344,6 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_fwd_top2, 256, B200_TOP3_SMEM), B200_ERROR_NOT_AVAILABLE);
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_bwd_top3, 256, B200_TOP3_SMEM), B200_ERROR_NOT_AVAILABLE);
         CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device), B200_ERROR_NOT_AVAILABLE);
-        if (s->top_occ > 0) occ_f = std::min(occ_f, s->top_occ), occ_b = std::min(occ_b, s->top_occ);
         int occ = std::min(occ_f, occ_b);
         if (occ < 1) s->n_top_items = 0; // the kernels cannot run at all: fall back to per-level launches
         s->top_grid = std::max(1, std::min(s->n_top_items, occ_f * nsm)); // (a performance choice only: items are handed out by ticket)
