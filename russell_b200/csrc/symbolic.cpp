@@ -378,28 +378,31 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
         postorder_tree(par1, cc1, post);
     if (opt.verbose >= 3) fprintf(stderr, "b200 analyze:     .post2 at %.3f s\n", now_s() - t0);
         std::vector<int> q2(n);
-        for (int k = 0; k < n; k++) q2[k] = q[post[k]];
+        parallel_rows(n, [&](int a, int b) { for (int k = a; k < b; k++) q2[k] = q[post[k]]; });
         q.swap(q2);
         relabel_graph(g0, q, g);
     if (opt.verbose >= 3) fprintf(stderr, "b200 analyze:     .relabel2 at %.3f s\n", now_s() - t0);
         // A postorder only renames the vertices of the elimination tree: parents and column counts of the final
         // labelling follow from the first pass by renaming (no second etree / column-count computation).
         std::vector<int> newid(n);
-        for (int k = 0; k < n; k++) newid[post[k]] = k;
+        parallel_rows(n, [&](int a, int b) { for (int k = a; k < b; k++) newid[post[k]] = k; });
         parent.assign(n, -1);
         cc.assign(n, 0);
-        for (int k = 0; k < n; k++) {
-            const int old = post[k];
-            parent[k] = par1[old] < 0 ? -1 : newid[par1[old]];
-            cc[k] = cc1[old];
-        }
+        parallel_rows(n, [&](int a, int b) {
+            for (int k = a; k < b; k++) {
+                const int old = post[k];
+                parent[k] = par1[old] < 0 ? -1 : newid[par1[old]];
+                cc[k] = cc1[old];
+            }
+        });
     }
     g0 = Graph();
     std::vector<int> invq(n);
-    for (int k = 0; k < n; k++) invq[q[k]] = k;
     P.colperm = q;
     P.rowperm.resize(n);
-    for (int k = 0; k < n; k++) P.rowperm[k] = rowmatch[q[k]];
+    parallel_rows(n, [&](int a, int b) {
+        for (int k = a; k < b; k++) invq[q[k]] = k, P.rowperm[k] = rowmatch[q[k]];
+    });
 
     if (opt.verbose >= 2) fprintf(stderr, "b200 analyze:   phase etree done at %.3f s\n", now_s() - t0);
     // ---- fundamental supernodes, then amalgamation over the supernode tree -------------------------------
@@ -482,10 +485,13 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
         };
         std::vector<Frame> st;
         std::vector<int> members; // supernodes of the current group in emission order
+        std::vector<int> mem_store, mem_off(nf, 0), mem_end(nf, 0); // the member lists, kept from phase 0 for phase 1
+        mem_store.reserve(nf);
         // collect(s): members of the group rooted at s = collect(merged children)... + s
+        std::vector<std::pair<int, int>> stack;
         auto collect = [&](int root, std::vector<int>& out) {
             // post-order over merged-children edges only
-            std::vector<std::pair<int, int>> stack;
+            stack.clear();
             stack.push_back({root, cptr[root]});
             while (!stack.empty()) {
                 auto& top = stack.back();
@@ -510,12 +516,12 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
         while (!st.empty()) {
             Frame fr = st.back();
             st.pop_back();
-            if (fr.phase == 1) {
-                members.clear();
-                collect(fr.s, members);
+            if (fr.phase == 1) { // the members were listed when the group was scheduled (phase 0)
                 Grp gnew{(int)order.size(), 0, ff[fr.s], zz[fr.s]};
-                for (int m : members)
+                for (int q2 = mem_off[fr.s]; q2 < mem_end[fr.s]; q2++) {
+                    const int m = mem_store[q2];
                     for (int j = fund[m].first; j < fund[m].first + fund[m].ncols; j++) order.push_back(j);
+                }
                 gnew.ncols = (int)order.size() - gnew.first;
                 grp.push_back(gnew);
                 continue;
@@ -524,6 +530,9 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
             st.push_back({fr.s, 1});
             members.clear();
             collect(fr.s, members);
+            mem_off[fr.s] = (int)mem_store.size();
+            mem_store.insert(mem_store.end(), members.begin(), members.end());
+            mem_end[fr.s] = (int)mem_store.size();
             tmp.clear();
             for (int m : members)
                 for (int e = cptr[m]; e < cptr[m + 1]; e++)
@@ -537,7 +546,7 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
             if (order[k] != k) identity = false;
         if (!identity) {
             std::vector<int> q2(n);
-            for (int k = 0; k < n; k++) q2[k] = q[order[k]];
+            parallel_rows(n, [&](int a, int b) { for (int k = a; k < b; k++) q2[k] = q[order[k]]; });
             q.swap(q2);
             Graph g2;
             relabel_graph(g, order, g2);
@@ -547,13 +556,16 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
             // child groups before parent groups): an equivalent reordering, so the tree of the new labelling is the old one renamed
             {
                 std::vector<int> newid(n), par2(n);
-                for (int k = 0; k < n; k++) newid[order[k]] = k;
-                for (int k = 0; k < n; k++) par2[k] = parent[order[k]] < 0 ? -1 : newid[parent[order[k]]];
+                parallel_rows(n, [&](int a, int b) { for (int k = a; k < b; k++) newid[order[k]] = k; });
+                parallel_rows(n, [&](int a, int b) {
+                    for (int k = a; k < b; k++) par2[k] = parent[order[k]] < 0 ? -1 : newid[parent[order[k]]];
+                });
                 parent.swap(par2);
             }
-            for (int k = 0; k < n; k++) invq[q[k]] = k;
             P.colperm = q;
-            for (int k = 0; k < n; k++) P.rowperm[k] = rowmatch[q[k]];
+            parallel_rows(n, [&](int a, int b) {
+                for (int k = a; k < b; k++) invq[q[k]] = k, P.rowperm[k] = rowmatch[q[k]];
+            });
         }
     }
     const int ns = (int)grp.size();
@@ -581,18 +593,19 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
             for (int s = 0; s < ns; s++)
                 if (sparent[s] >= 0) scidx[fill[sparent[s]]++] = s;
         }
-        for (int s = 0; s < ns; s++) {
+        // one supernode: union of the adjacency of its columns and of its children's rows, beyond its last column
+        auto row_struct = [&](int s, std::vector<int>& mk) {
             const int first = grp[s].first, last = first + grp[s].ncols - 1;
             std::vector<int>& r = srows[s];
             for (int j = first; j <= last; j++)
                 for (int e = g.ptr[j]; e < g.ptr[j + 1]; e++) {
                     int i = g.adj[e];
-                    if (i > last && mark[i] != s) mark[i] = s, r.push_back(i);
+                    if (i > last && mk[i] != s) mk[i] = s, r.push_back(i);
                 }
             for (int e = scptr[s]; e < scptr[s + 1]; e++) {
                 int c = scidx[e];
                 for (int i : srows[c])
-                    if (i > last && mark[i] != s) mark[i] = s, r.push_back(i);
+                    if (i > last && mk[i] != s) mk[i] = s, r.push_back(i);
             }
             std::sort(r.begin(), r.end());
             if ((int64_t)r.size() + grp[s].ncols != grp[s].f) {
@@ -601,7 +614,43 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
                             (long long)grp[s].f, (long long)(r.size() + grp[s].ncols));
                 grp[s].f = (int64_t)r.size() + grp[s].ncols; // the enumerated structure is authoritative
             }
+        };
+        // A supernode needs its children only: disjoint subtrees (contiguous ranges, the supernodes are in postorder) are
+        // independent tasks for a pool of threads, each with its own mark array; the few supernodes above them follow serially.
+        unsigned nt = std::thread::hardware_concurrency();
+        if (nt > 16) nt = 16;
+        std::vector<char> done(ns, 0);
+        if (nt >= 2 && ns >= 20000 && !getenv("B200_ND_SERIAL")) {
+            std::vector<int64_t> wsub(ns);
+            std::vector<int> cnt(ns, 1);
+            for (int s = 0; s < ns; s++) wsub[s] = grp[s].f;
+            for (int s = 0; s < ns; s++)
+                if (sparent[s] >= 0) wsub[sparent[s]] += wsub[s], cnt[sparent[s]] += cnt[s];
+            int64_t total = 0;
+            for (int s = 0; s < ns; s++)
+                if (sparent[s] < 0) total += wsub[s];
+            const int64_t target = std::max<int64_t>(total / (8 * (int64_t)nt), 1);
+            std::vector<std::pair<int64_t, int>> tasks; // (weight, root)
+            for (int s = 0; s < ns; s++)
+                if (wsub[s] <= target && (sparent[s] < 0 || wsub[sparent[s]] > target)) tasks.push_back({wsub[s], s});
+            std::sort(tasks.begin(), tasks.end(), [](const std::pair<int64_t, int>& x, const std::pair<int64_t, int>& y) {
+                return x.first != y.first ? x.first > y.first : x.second < y.second;
+            });
+            std::atomic<size_t> next{0};
+            auto worker = [&]() {
+                std::vector<int> mk(n, -1);
+                for (size_t t = next++; t < tasks.size(); t = next++) {
+                    const int root = tasks[t].second;
+                    for (int s2 = root - cnt[root] + 1; s2 <= root; s2++) row_struct(s2, mk), done[s2] = 1;
+                }
+            };
+            std::vector<std::thread> th;
+            for (unsigned t = 1; t < nt; t++) th.emplace_back(worker);
+            worker();
+            for (auto& x : th) x.join();
         }
+        for (int s = 0; s < ns; s++)
+            if (!done[s]) row_struct(s, mark);
     }
     g = Graph();
 
