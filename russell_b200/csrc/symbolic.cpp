@@ -22,12 +22,19 @@
 
 namespace b200 {
 
+// problem sizes below which the threaded variants of the analysis run inline; B200_PAR_FLOOR overrides them (the tests force
+// the threaded code paths on small matrices and compare the plan with the serial one)
+static int par_floor(int dflt) {
+    static const int forced = getenv("B200_PAR_FLOOR") ? atoi(getenv("B200_PAR_FLOOR")) : -1;
+    return forced >= 0 ? forced : dflt;
+}
+
 // splits [0, n) into contiguous chunks, one per hardware thread (at most 16); small ranges run inline
 template <class F>
 static void parallel_rows(int n, F fn) {
     unsigned nt = std::thread::hardware_concurrency();
     if (nt > 16) nt = 16;
-    if (nt < 2 || n < 50000 || getenv("B200_ND_SERIAL")) {
+    if (nt < 2 || n < par_floor(50000) || getenv("B200_ND_SERIAL")) {
         fn(0, n);
         return;
     }
@@ -620,7 +627,7 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
         unsigned nt = std::thread::hardware_concurrency();
         if (nt > 16) nt = 16;
         std::vector<char> done(ns, 0);
-        if (nt >= 2 && ns >= 20000 && !getenv("B200_ND_SERIAL")) {
+        if (nt >= 2 && ns >= par_floor(20000) && !getenv("B200_ND_SERIAL")) {
             std::vector<int64_t> wsub(ns);
             std::vector<int> cnt(ns, 1);
             for (int s = 0; s < ns; s++) wsub[s] = grp[s].f;
@@ -787,7 +794,7 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
         ~Joiner() { finish(); }
     } cb_join{cb_thread};
     if (opt.cb_reuse) {
-        if (nnodes >= 20000 && !getenv("B200_ND_SERIAL")) cb_thread = std::thread(alloc_cb);
+        if (nnodes >= par_floor(20000) && !getenv("B200_ND_SERIAL")) cb_thread = std::thread(alloc_cb);
         else alloc_cb();
     }
     P.rows.resize(P.rows_ptr[nnodes]);

@@ -436,7 +436,9 @@ def test_threaded_nested_dissection_equals_serial():
             "print(rc, float(x.sum()).hex(), float(np.abs(x).max()).hex(), int(st['nnz_l']), int(st['nlevels']))\n"
             % (ROOT, HERE))
     outs = []
-    for env_extra in ({}, {"B200_ND_SERIAL": "1"}, {}):
+    # B200_PAR_FLOOR = 0 forces every threaded stage of symbolic.cpp (row-parallel loops, subtree tasks of the row structures,
+    # the helper thread of the contribution-block allocator) at this size
+    for env_extra in ({}, {"B200_ND_SERIAL": "1"}, {"B200_PAR_FLOOR": "0"}):
         env = dict(os.environ, **env_extra)
         outs.append(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout.strip())
     assert outs[0] == outs[1] == outs[2], outs
