@@ -267,13 +267,21 @@ bool values_need_matching(int matching, int n, const int* rp, const int* ci, con
     return false;
 }
 
+// time spent in the allocations / copies of upload() by the calling thread (printed by initialize when verbose)
+thread_local double g_up_malloc_s = 0.0, g_up_copy_s = 0.0, g_up_bytes = 0.0;
+
 template <typename T>
 cudaError_t upload(T** dptr, const std::vector<T>& h) {
     *dptr = nullptr;
     size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+    const auto t0 = std::chrono::steady_clock::now();
     cudaError_t e = cudaMalloc((void**)dptr, bytes);
+    const auto t1 = std::chrono::steady_clock::now();
+    g_up_malloc_s += std::chrono::duration<double>(t1 - t0).count();
     if (e != cudaSuccess) return e;
     if (!h.empty()) e = cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+    g_up_copy_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
+    g_up_bytes += (double)bytes;
     return e;
 }
 
@@ -1190,6 +1198,7 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
 
 
     if (verbose) fprintf(stderr, "solver_b200_initialize:   top items built at %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_host0).count());
+    g_up_malloc_s = g_up_copy_s = g_up_bytes = 0.0;
 #define UP(dst, vec) CUDA_TRY(upload(&s->dst, vec), B200_ERROR_CUDA_MALLOC)
     UP(d_nodes, nodes);
     UP(d_rows, P.rows);
@@ -1277,7 +1286,9 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     if (!P.full_src.empty()) UP(d_full_src, P.full_src);
     UP(d_rowblk, rowblk);
 #undef UP
-    if (verbose) fprintf(stderr, "solver_b200_initialize:   plan uploaded at %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_host0).count());
+    if (verbose)
+        fprintf(stderr, "solver_b200_initialize:   plan uploaded at %.3f s (%.1f MB: cudaMalloc %.3f s, cudaMemcpy %.3f s)\n",
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t_host0).count(), g_up_bytes * 1e-6, g_up_malloc_s, g_up_copy_s);
 #define DM(ptr, count, type) CUDA_TRY(cudaMalloc((void**)&s->ptr, std::max<size_t>((size_t)(count), 1) * sizeof(type)), B200_ERROR_CUDA_MALLOC)
     DM(d_vals, P.nnz_in, double);
     if (P.sym_lower) DM(d_fullvals, s->fnnz, double);
