@@ -58,6 +58,51 @@ static const int SC_MAXF[NSC] = {32, 256, 1 << 30};
 static const int SC_THREADS[NSC] = {32, 128, 256};
 static const int SC_MAXP[NSC] = {32, B200_MAXP, B200_MAXP};
 
+// Device memory of a handle comes from a few large chunks instead of ~70 separate cudaMalloc calls: on the B200 boxes a
+// cudaMalloc costs 0.1 ms on a quiet device but ~5-10 ms next to live handles / instantiated graphs (profiles/r4f_init_probe.txt:
+// 0.28-0.41 s of a 0.9 s initialize went into cudaMalloc alone).  A request that does not fit the chunk being filled gets a chunk
+// of its own when it is at least half a chunk, a fresh chunk otherwise.
+struct SlabSet {
+    struct Chunk {
+        char* base;
+        size_t cap, used;
+    };
+    std::vector<Chunk> chunks; // the chunk that is being filled is the last one
+    size_t chunk_default = (size_t)1 << 20;
+    int n_malloc = 0;
+    cudaError_t alloc(void** out, size_t bytes) {
+        bytes = (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255;
+        const bool fits = !chunks.empty() && chunks.back().used + bytes <= chunks.back().cap;
+        const bool own = !fits && 2 * bytes >= chunk_default;
+        if (!fits) {
+            const size_t cap = own ? bytes : chunk_default;
+            char* b = nullptr;
+            cudaError_t e = cudaMalloc((void**)&b, cap);
+            n_malloc++;
+            if (e != cudaSuccess) return e;
+            if (own) { // full from the start: goes in front of the chunk that is being filled
+                chunks.insert(chunks.empty() ? chunks.end() : chunks.end() - 1, Chunk{b, cap, cap});
+                *out = b;
+                return cudaSuccess;
+            }
+            chunks.push_back(Chunk{b, cap, 0});
+        }
+        Chunk& c = chunks.back();
+        *out = c.base + c.used;
+        c.used += bytes;
+        return cudaSuccess;
+    }
+    bool owns(const void* p) const {
+        for (const Chunk& c : chunks)
+            if ((const char*)p >= c.base && (const char*)p < c.base + c.cap) return true;
+        return false;
+    }
+    void release() {
+        for (Chunk& c : chunks) cudaFree(c.base);
+        chunks.clear();
+    }
+};
+
 struct LevelLists {
     // offsets (nlevels+1) into the concatenated device item arrays (big fronts only)
     std::vector<int> asm_ptr, panel_ptr, schur_ptr;
@@ -116,6 +161,7 @@ struct InterfaceB200 {
     int force_no_matching = 0;
     int strict_residual = 0; // 1: solve returns B200_ERROR_SOLVE+7 whenever ||b-Ax||/||b|| > 10 ir_tol after refinement
 
+    SlabSet slabs; // device memory of the plan arrays, work vectors and arenas (released as a whole)
     std::shared_ptr<Plan> plan_sp = std::make_shared<Plan>(); // shared (read-only) with the plan cache and with other handles of the same pattern
     bool plan_shared = false;
     LevelLists lv;
@@ -269,13 +315,20 @@ bool values_need_matching(int matching, int n, const int* rp, const int* ci, con
 
 // time spent in the allocations / copies of upload() by the calling thread (printed by initialize when verbose)
 thread_local double g_up_malloc_s = 0.0, g_up_copy_s = 0.0, g_up_bytes = 0.0;
+// the slab set device allocations of the calling thread go to (set for the duration of solver_b200_initialize / release_device)
+thread_local SlabSet* g_slab = nullptr;
+struct SlabScope {
+    explicit SlabScope(SlabSet* sl) { g_slab = sl; }
+    ~SlabScope() { g_slab = nullptr; }
+};
+cudaError_t device_alloc(void** out, size_t bytes) { return g_slab ? g_slab->alloc(out, bytes) : cudaMalloc(out, bytes); }
 
 template <typename T>
 cudaError_t upload(T** dptr, const std::vector<T>& h) {
     *dptr = nullptr;
     size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
     const auto t0 = std::chrono::steady_clock::now();
-    cudaError_t e = cudaMalloc((void**)dptr, bytes);
+    cudaError_t e = device_alloc((void**)dptr, bytes);
     const auto t1 = std::chrono::steady_clock::now();
     g_up_malloc_s += std::chrono::duration<double>(t1 - t0).count();
     if (e != cudaSuccess) return e;
@@ -287,11 +340,12 @@ cudaError_t upload(T** dptr, const std::vector<T>& h) {
 
 template <typename T>
 void dfree(T*& p) {
-    if (p) cudaFree(p);
+    if (p && !(g_slab && g_slab->owns(p))) cudaFree(p); // (chunk memory is released as a whole)
     p = nullptr;
 }
 
 void release_device(InterfaceB200* s) {
+    SlabScope scope(&s->slabs);
     if (s->g_fact) cudaGraphExecDestroy(s->g_fact), s->g_fact = nullptr;
     if (s->g_sweep) cudaGraphExecDestroy(s->g_sweep), s->g_sweep = nullptr;
     dfree(s->d_nodes), dfree(s->d_rows), dfree(s->d_rel), dfree(s->d_child_idx), dfree(s->d_fact_nodes), dfree(s->d_solve_nodes), dfree(s->d_inv_nodes);
@@ -314,6 +368,7 @@ void release_device(InterfaceB200* s) {
     dfree(s->d_partial), dfree(s->d_norms);
     if (s->h_norms) cudaFreeHost(s->h_norms), s->h_norms = nullptr;
     if (s->h_counters) cudaFreeHost(s->h_counters), s->h_counters = nullptr;
+    s->slabs.release();
 }
 
 int grid_for(long long work, int block = 256, int cap = 148 * 16) {
@@ -1199,6 +1254,13 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
 
     if (verbose) fprintf(stderr, "solver_b200_initialize:   top items built at %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_host0).count());
     g_up_malloc_s = g_up_copy_s = g_up_bytes = 0.0;
+    SlabScope slab_scope(&s->slabs);
+    {   // one chunk for everything but the big arenas: plan arrays (~28 B per matrix entry, ~26 B per front row) + work vectors
+        const double est = 36.0 * (double)s->fnnz + 28.0 * (double)P.rows_ptr[P.nnodes] + 96.0 * (double)P.n + 256.0 * (double)P.nnodes +
+                           16.0 * (double)(asm_items.size() + panel_items.size() + schur_items.size() + top_items.size() + big_items.size()) +
+                           4.0 * (double)(asm_ranges.size() + big_ranges.size() + top_ranges.size()) + 8.0 * (double)P.dinv_size * 0.0;
+        s->slabs.chunk_default = (size_t)std::min(std::max(est * 1.1, 1048576.0), 1024.0 * 1048576.0);
+    }
 #define UP(dst, vec) CUDA_TRY(upload(&s->dst, vec), B200_ERROR_CUDA_MALLOC)
     UP(d_nodes, nodes);
     UP(d_rows, P.rows);
@@ -1289,7 +1351,7 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     if (verbose)
         fprintf(stderr, "solver_b200_initialize:   plan uploaded at %.3f s (%.1f MB: cudaMalloc %.3f s, cudaMemcpy %.3f s)\n",
                 std::chrono::duration<double>(std::chrono::steady_clock::now() - t_host0).count(), g_up_bytes * 1e-6, g_up_malloc_s, g_up_copy_s);
-#define DM(ptr, count, type) CUDA_TRY(cudaMalloc((void**)&s->ptr, std::max<size_t>((size_t)(count), 1) * sizeof(type)), B200_ERROR_CUDA_MALLOC)
+#define DM(ptr, count, type) CUDA_TRY(device_alloc((void**)&s->ptr, std::max<size_t>((size_t)(count), 1) * sizeof(type)), B200_ERROR_CUDA_MALLOC)
     DM(d_vals, P.nnz_in, double);
     if (P.sym_lower) DM(d_fullvals, s->fnnz, double);
     DM(d_fac, P.fac_size, double);
@@ -1333,7 +1395,9 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     CUDA_TRY(cudaMallocHost((void**)&s->h_norms, 4 * sizeof(double)), B200_ERROR_MALLOC);
     CUDA_TRY(cudaMallocHost((void**)&s->h_counters, 16 * sizeof(int)), B200_ERROR_MALLOC);
 
-    if (verbose) fprintf(stderr, "solver_b200_initialize:   arenas allocated at %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_host0).count());
+    if (verbose)
+        fprintf(stderr, "solver_b200_initialize:   arenas allocated at %.3f s (%d cudaMalloc calls for this handle)\n",
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t_host0).count(), s->slabs.n_malloc);
     // kernels that need more than 48 KB of dynamic shared memory
     const int W = s->opt_panel_width;
     CUDA_TRY(cudaFuncSetAttribute(k_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_diag(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
@@ -1505,10 +1569,15 @@ int32_t solver_b200_initialize_coo(struct InterfaceB200* s, int32_t ordering, in
     if (rc != B200_SUCCESSFUL_EXIT) return rc;
     const int nslots = ptr[ndim];
     s->nnz_coo = nnz_coo;
-    cudaError_t e = cudaMalloc(&s->d_seg_ptr, ((size_t)nslots + 1) * sizeof(int));
-    if (e == cudaSuccess) e = cudaMalloc(&s->d_seg_idx, (size_t)nnz_coo * sizeof(int));
-    if (e == cudaSuccess) e = cudaMalloc(&s->d_coo_vals, (size_t)nnz_coo * sizeof(double));
-    if (e != cudaSuccess) return B200_ERROR_CUDA_MALLOC;
+    {
+        SlabScope slab_scope(&s->slabs); // (one chunk for the three arrays)
+        s->slabs.chunk_default = std::max<size_t>((size_t)1 << 20, ((size_t)nslots + 1) * sizeof(int) + (size_t)nnz_coo * (sizeof(int) + sizeof(double)) + 1024);
+        if (!s->slabs.chunks.empty()) s->slabs.chunks.back().used = s->slabs.chunks.back().cap; // start a fresh chunk of that size
+        cudaError_t e = device_alloc((void**)&s->d_seg_ptr, ((size_t)nslots + 1) * sizeof(int));
+        if (e == cudaSuccess) e = device_alloc((void**)&s->d_seg_idx, (size_t)nnz_coo * sizeof(int));
+        if (e == cudaSuccess) e = device_alloc((void**)&s->d_coo_vals, (size_t)nnz_coo * sizeof(double));
+        if (e != cudaSuccess) return B200_ERROR_CUDA_MALLOC;
+    }
     CUDA_TRY(cudaMemcpyAsync(s->d_seg_ptr, seg_ptr.data(), ((size_t)nslots + 1) * sizeof(int), cudaMemcpyHostToDevice, s->stream), B200_ERROR_CUDA_MEMCPY);
     CUDA_TRY(cudaMemcpyAsync(s->d_seg_idx, seg_idx.data(), (size_t)nnz_coo * sizeof(int), cudaMemcpyHostToDevice, s->stream), B200_ERROR_CUDA_MEMCPY);
     CUDA_TRY(cudaStreamSynchronize(s->stream), B200_ERROR_CUDA_SYNCHRONIZE);
