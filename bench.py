@@ -369,6 +369,29 @@ def main():
     ms_e2e, wall_e2e, parts_e2e = timed(step_e2e, K)
     res_e2e = get_stats()["last_rel_residual"]
 
+    # the same five-call loop with PAGEABLE host buffers (plain numpy arrays -- what a Rust Vec<f64> is): with the library's
+    # striped staging through pinned buffers (default) and with plain cudaMemcpyAsync from the caller's pages
+    pageable = None
+    if world == 1:
+        pv, pr, px = vals.copy(), np.ones(n), np.zeros(n)
+
+        def step_pageable():
+            rc = lib.solver_b200_factorize(h, ctypes.byref(em), ctypes.byref(ep), 0, ptr(pv, p_f64))
+            assert rc == 0, rc
+            rc = lib.solver_b200_solve(h, ptr(px, p_f64), ptr(pr, p_f64), 0)
+            assert rc == 0, rc
+
+        pageable = {"unit": "systems/s", "what": "e2e loop with pageable (numpy) host buffers; staged = striped copies through the "
+                                                 "handle's pinned staging buffers (default), plain = cudaMemcpyAsync from the caller's pages"}
+        for label, flag in (("staged", 1.0), ("plain", 0.0)):
+            assert lib.solver_b200_set_option(h, b"staged_copy", flag) == 0
+            for _ in range(2):
+                step_pageable()
+            ms_p, wall_p, _ = timed(step_pageable, min(K, 10))
+            pageable[label] = {"value": min(K, 10) / (wall_p * 1e-3), "wall_ms_per_step": wall_p / min(K, 10), "ms_per_step": ms_p / min(K, 10)}
+        assert lib.solver_b200_set_option(h, b"staged_copy", 1.0) == 0
+        pageable["x_equals_pinned_run"] = bool(np.array_equal(px, h_x.numpy()))
+
     # accuracy (north star): ||b - A x|| / ||b|| of the last device-resident solve, evaluated in f64 by the SpMV kernel
     rel_res = st["last_rel_residual"]
     t_res = torch.tensor([rel_res, res_e2e], dtype=torch.float64, device="cuda")
@@ -400,6 +423,7 @@ def main():
             "e2e": {"value": world * K / (ms_e2e * 1e-3), "unit": "systems/s", "h2d_bytes_per_step": 8 * nnz + 8 * n,
                     "d2h_bytes_per_step": 8 * n, "ms_per_step": ms_e2e / K, "wall_ms_per_step": wall_e2e / K,
                     "rel_residual": res_e2e, "api": "solver_b200_factorize + solver_b200_solve (pinned host buffers)"},
+            "e2e_pageable": pageable,
             "e2e_cold": {"value": world / (t_init + t_first), "unit": "systems/s", "initialize_s": t_init, "first_factorize_solve_s": t_first,
                          "what": "initialize (host analysis + plan upload) + first factorize + solve, one shot per system; compare with the reference arm's `cold`"},
             "gpu_launches": int(K * (st["launches_factorize"] + st["launches_solve"])),

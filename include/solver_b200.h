@@ -180,6 +180,13 @@ int32_t solver_b200_debug_trace(struct InterfaceB200 *solver, unsigned long long
 /* the CUDA stream (cudaStream_t) every kernel of this handle is launched on, and its device ordinal: lets a
  * caller bracket calls with its own CUDA events (bench.py) or order its own work after ours */
 void *solver_b200_get_stream(struct InterfaceB200 *solver);
+
+/* extension: transfers between a caller's host buffer and device memory on the handle's stream.  Pinned host memory goes
+ * straight to the copy engine (asynchronous, like cudaMemcpyAsync); large pageable buffers -- what a Rust Vec<f64> or a numpy
+ * array is -- are striped over a few threads and staged through pinned buffers of the handle (H2D: ordered on the stream;
+ * D2H: complete on return).  solver_b200_factorize / _factorize_coo / _solve and the complex twins use it for values, rhs and x. */
+int32_t solver_b200_copy_h2d(struct InterfaceB200 *solver, void *dst_device, const void *src_host, int64_t bytes);
+int32_t solver_b200_copy_d2h(struct InterfaceB200 *solver, void *dst_host, const void *src_device, int64_t bytes);
 int32_t solver_b200_get_device(struct InterfaceB200 *solver);
 
 /* ---- Complex64 twin ---------------------------------------------------------------------

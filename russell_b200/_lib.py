@@ -44,6 +44,8 @@ SIGNATURES = {
     "solver_b200_debug_trace": (c_i32, [p_void, ctypes.POINTER(ctypes.c_uint64), p_i32, c_i32]),
     "solver_b200_version": (ctypes.c_char_p, []),
     "solver_b200_get_stream": (p_void, [p_void]),
+    "solver_b200_copy_h2d": (c_i32, [p_void, p_void, p_void, ctypes.c_int64]),
+    "solver_b200_copy_d2h": (c_i32, [p_void, p_void, p_void, ctypes.c_int64]),
     "solver_b200_get_device": (c_i32, [p_void]),
     # Complex64 twin (russell_b200/csrc/complex_b200.cu)
     "complex_solver_b200_new": (p_void, []),

@@ -186,7 +186,7 @@ int32_t complex_solver_b200_factorize(struct InterfaceComplexB200* s, int32_t* e
     if (!values) return B200_ERROR_NULL_POINTER;
     CB_CUDA_TRY(cudaSetDevice(solver_b200_get_device(s->real)), B200_ERROR_NOT_AVAILABLE);
     cudaStream_t st = (cudaStream_t)solver_b200_get_stream(s->real);
-    CB_CUDA_TRY(cudaMemcpyAsync(s->d_cvals, values, (size_t)s->nnz * sizeof(double2), cudaMemcpyHostToDevice, st), B200_ERROR_CUDA_MEMCPY);
+    if (solver_b200_copy_h2d(s->real, s->d_cvals, values, (int64_t)s->nnz * (int64_t)sizeof(double2)) != 0) return B200_ERROR_CUDA_MEMCPY; // (staged when pageable)
     int32_t rc = complex_solver_b200_factorize_device(s, (const double*)s->d_cvals);
     double st8[B200_STAT_COUNT];
     if (solver_b200_get_stats(s->real, st8, B200_STAT_COUNT) == 0) {
@@ -244,7 +244,7 @@ int32_t complex_solver_b200_factorize_coo(struct InterfaceComplexB200* s, int32_
     if (!coo_values) return B200_ERROR_NULL_POINTER;
     CB_CUDA_TRY(cudaSetDevice(solver_b200_get_device(s->real)), B200_ERROR_NOT_AVAILABLE);
     cudaStream_t st = (cudaStream_t)solver_b200_get_stream(s->real);
-    CB_CUDA_TRY(cudaMemcpyAsync(s->d_coo_cvals, coo_values, (size_t)s->nnz_coo * sizeof(double2), cudaMemcpyHostToDevice, st), B200_ERROR_CUDA_MEMCPY);
+    if (solver_b200_copy_h2d(s->real, s->d_coo_cvals, coo_values, (int64_t)s->nnz_coo * (int64_t)sizeof(double2)) != 0) return B200_ERROR_CUDA_MEMCPY;
     int blocks = (s->nnz + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     k_complex_coo_to_csr_values<<<blocks, 256, 0, st>>>(s->nnz, s->d_seg_ptr, s->d_seg_idx, s->d_coo_cvals, s->d_cvals);

@@ -161,6 +161,15 @@ struct InterfaceB200 {
     int force_no_matching = 0;
     int strict_residual = 0; // 1: solve returns B200_ERROR_SOLVE+7 whenever ||b-Ax||/||b|| > 10 ir_tol after refinement
 
+    // Host buffers of the callers (Rust Vec<f64>, numpy arrays) are pageable: a plain cudaMemcpyAsync from them is staged by the
+    // driver at a fraction of the PCIe rate.  Large pageable transfers are striped over a few threads, each copying its stripe
+    // through its own pair of pinned staging buffers (memcpy of piece k+1 overlaps the DMA of piece k); pinned buffers (the
+    // benchmark's) go straight to the copy engine.  Option "staged_copy" / B200_STAGED_COPY = 0 restores the plain copies.
+    static const int NST = 4;                     // stripes (threads)
+    static const size_t STAGE_PIECE = (size_t)2 << 20; // bytes per staging buffer
+    char* h_stage = nullptr;                      // NST x 2 pinned buffers
+    cudaEvent_t ev_stage[2 * NST] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int staged_copy = 1;
     SlabSet slabs; // device memory of the plan arrays, work vectors and arenas (released as a whole)
     std::shared_ptr<Plan> plan_sp = std::make_shared<Plan>(); // shared (read-only) with the plan cache and with other handles of the same pattern
     bool plan_shared = false;
@@ -369,6 +378,9 @@ void release_device(InterfaceB200* s) {
     if (s->h_norms) cudaFreeHost(s->h_norms), s->h_norms = nullptr;
     if (s->h_counters) cudaFreeHost(s->h_counters), s->h_counters = nullptr;
     s->slabs.release();
+    if (s->h_stage) cudaFreeHost(s->h_stage), s->h_stage = nullptr;
+    for (int i = 0; i < 2 * InterfaceB200::NST; i++)
+        if (s->ev_stage[i]) cudaEventDestroy(s->ev_stage[i]), s->ev_stage[i] = nullptr;
 }
 
 int grid_for(long long work, int block = 256, int cap = 148 * 16) {
@@ -931,6 +943,7 @@ struct InterfaceB200* solver_b200_new(void) {
     if ((e = getenv("B200_USE_LEAF_REG"))) s->use_leaf_reg = atoi(e);
     if ((e = getenv("B200_USE_LEVEL_FORK"))) s->use_level_fork = atoi(e);
     if ((e = getenv("B200_INV_OVERLAP"))) s->inv_overlap = atoi(e);
+    if ((e = getenv("B200_STAGED_COPY"))) s->staged_copy = atoi(e);
     if ((e = getenv("B200_FUSED_W8_MAX"))) s->fused_w8_max = atoi(e);
     if ((e = getenv("B200_USE_LEAF_REG"))) s->use_leaf_reg = atoi(e);
     if ((e = getenv("B200_ASM_VARIANT"))) s->asm_variant = atoi(e);
@@ -965,6 +978,7 @@ int32_t solver_b200_set_option(struct InterfaceB200* s, const char* key, double 
     if (k == "ir_tol") { s->ir_tol = value; return 0; }
     if (k == "refinement_nstep") { s->nrefine = (int)value; return 0; }
     if (k == "strict_residual") { s->strict_residual = value != 0.0; return 0; }
+    if (k == "staged_copy") { s->staged_copy = value != 0.0; return 0; }
     if (s->initialized) return B200_ERROR_ALREADY_INITIALIZED;
     if (k == "panel_width") s->opt_panel_width = std::max(4, std::min((int)value, B200_MAXP));
     else if (k == "nd_leaf") s->opt_nd_leaf = std::max(4, (int)value);
@@ -1258,7 +1272,7 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     {   // one chunk for everything but the big arenas: plan arrays (~28 B per matrix entry, ~26 B per front row) + work vectors
         const double est = 36.0 * (double)s->fnnz + 28.0 * (double)P.rows_ptr[P.nnodes] + 96.0 * (double)P.n + 256.0 * (double)P.nnodes +
                            16.0 * (double)(asm_items.size() + panel_items.size() + schur_items.size() + top_items.size() + big_items.size()) +
-                           4.0 * (double)(asm_ranges.size() + big_ranges.size() + top_ranges.size()) + 8.0 * (double)P.dinv_size * 0.0;
+                           4.0 * (double)(asm_ranges.size() + big_ranges.size() + top_ranges.size());
         s->slabs.chunk_default = (size_t)std::min(std::max(est * 1.1, 1048576.0), 1024.0 * 1048576.0);
     }
 #define UP(dst, vec) CUDA_TRY(upload(&s->dst, vec), B200_ERROR_CUDA_MALLOC)
@@ -1526,6 +1540,109 @@ static void clear_fac_under_h2d(InterfaceB200* s) {
     s->fac_cleared = true;
 }
 
+// ---- host <-> device transfers of the callers' buffers ------------------------------------------------------------
+namespace {
+bool host_pointer_is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+bool staging_ready(InterfaceB200* s) {
+    if (s->h_stage) return true;
+    if (cudaMallocHost((void**)&s->h_stage, 2 * InterfaceB200::NST * InterfaceB200::STAGE_PIECE) != cudaSuccess) {
+        cudaGetLastError();
+        s->h_stage = nullptr;
+        return false;
+    }
+    for (int i = 0; i < 2 * InterfaceB200::NST; i++)
+        if (cudaEventCreateWithFlags(&s->ev_stage[i], cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            cudaFreeHost(s->h_stage), s->h_stage = nullptr;
+            s->staged_copy = 0; // plain copies from now on
+            return false;
+        }
+    return true;
+}
+// one stripe [lo, hi) of a transfer between pageable host memory and the device, through the stripe's two staging buffers
+cudaError_t stripe_copy(InterfaceB200* s, int t, char* dev, char* host, size_t lo, size_t hi, bool to_device) {
+    cudaError_t e = cudaSetDevice(s->device);
+    const size_t piece = InterfaceB200::STAGE_PIECE;
+    char* buf[2] = {s->h_stage + (size_t)(2 * t) * piece, s->h_stage + (size_t)(2 * t + 1) * piece};
+    cudaEvent_t ev[2] = {s->ev_stage[2 * t], s->ev_stage[2 * t + 1]};
+    size_t prev_off = 0, prev_n = 0;
+    int k = 0;
+    for (size_t off = lo; off < hi && e == cudaSuccess; off += piece, k++) {
+        const size_t n = std::min(piece, hi - off);
+        const int b = k & 1;
+        if (to_device) {
+            e = cudaEventSynchronize(ev[b]); // the DMA that last read this buffer is done (a fresh event is complete)
+            if (e != cudaSuccess) break;
+            memcpy(buf[b], host + off, n);
+            e = cudaMemcpyAsync(dev + off, buf[b], n, cudaMemcpyHostToDevice, s->stream);
+            if (e == cudaSuccess) e = cudaEventRecord(ev[b], s->stream);
+        } else {
+            e = cudaMemcpyAsync(buf[b], dev + off, n, cudaMemcpyDeviceToHost, s->stream);
+            if (e == cudaSuccess) e = cudaEventRecord(ev[b], s->stream);
+            if (e == cudaSuccess && k > 0) { // unload the previous piece while this one is in flight
+                e = cudaEventSynchronize(ev[b ^ 1]);
+                if (e == cudaSuccess) memcpy(host + prev_off, buf[b ^ 1], prev_n);
+            }
+            prev_off = off, prev_n = n;
+        }
+    }
+    if (!to_device && e == cudaSuccess && k > 0) {
+        e = cudaEventSynchronize(ev[(k - 1) & 1]);
+        if (e == cudaSuccess) memcpy(host + prev_off, buf[(k - 1) & 1], prev_n);
+    }
+    return e;
+}
+// H2D: enqueued on the handle's stream (ordered like a cudaMemcpyAsync).  D2H: pinned destination -> enqueued; pageable
+// destination -> complete when the call returns.
+cudaError_t transfer(InterfaceB200* s, void* dev, void* host, size_t bytes, bool to_device) {
+    const bool plain = !s->staged_copy || bytes < 2 * InterfaceB200::STAGE_PIECE || host_pointer_is_pinned(host) || !staging_ready(s);
+    if (plain)
+        return to_device ? cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, s->stream)
+                         : cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, s->stream);
+    const int nt = InterfaceB200::NST;
+    const size_t stripe = ((bytes + nt - 1) / nt + 255) & ~(size_t)255;
+    cudaError_t err[InterfaceB200::NST];
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) {
+        const size_t lo = std::min(bytes, (size_t)t * stripe), hi = std::min(bytes, lo + stripe);
+        err[t] = cudaSuccess;
+        if (lo >= hi) continue;
+        if (t == nt - 1 || hi == bytes) { // the calling thread takes the last stripe
+            err[t] = stripe_copy(s, t, (char*)dev, (char*)host, lo, hi, to_device);
+            break;
+        }
+        th.emplace_back([=, &err]() { err[t] = stripe_copy(s, t, (char*)dev, (char*)host, lo, hi, to_device); });
+    }
+    for (auto& x : th) x.join();
+    for (int t = 0; t < nt; t++)
+        if (err[t] != cudaSuccess) return err[t];
+    return cudaSuccess;
+}
+} // namespace
+
+int32_t solver_b200_copy_h2d(struct InterfaceB200* s, void* dst_device, const void* src_host, int64_t bytes) {
+    if (!s || !dst_device || !src_host) return B200_ERROR_NULL_POINTER;
+    if (bytes <= 0) return B200_SUCCESSFUL_EXIT;
+    CUDA_TRY(cudaSetDevice(s->device), B200_ERROR_NOT_AVAILABLE);
+    CUDA_TRY(transfer(s, dst_device, const_cast<void*>(src_host), (size_t)bytes, true), B200_ERROR_CUDA_MEMCPY);
+    return B200_SUCCESSFUL_EXIT;
+}
+
+int32_t solver_b200_copy_d2h(struct InterfaceB200* s, void* dst_host, const void* src_device, int64_t bytes) {
+    if (!s || !dst_host || !src_device) return B200_ERROR_NULL_POINTER;
+    if (bytes <= 0) return B200_SUCCESSFUL_EXIT;
+    CUDA_TRY(cudaSetDevice(s->device), B200_ERROR_NOT_AVAILABLE);
+    CUDA_TRY(transfer(s, const_cast<void*>(src_device), dst_host, (size_t)bytes, false), B200_ERROR_CUDA_MEMCPY);
+    return B200_SUCCESSFUL_EXIT;
+}
+
 int32_t solver_b200_factorize(struct InterfaceB200* s, int32_t* effective_matching, int32_t* effective_pivoting,
                               int32_t verbose, const double* values) {
     if (!s) return B200_ERROR_NULL_POINTER;
@@ -1535,7 +1652,7 @@ int32_t solver_b200_factorize(struct InterfaceB200* s, int32_t* effective_matchi
     s->factorized = false; // the factor arena is about to be cleared: a failed copy must not leave a "factorized" handle
     CUDA_TRY(cudaSetDevice(s->device), B200_ERROR_NOT_AVAILABLE);
     clear_fac_under_h2d(s);
-    CUDA_TRY(cudaMemcpyAsync(s->d_vals, values, (size_t)s->nnz_in * sizeof(double), cudaMemcpyHostToDevice, s->stream), B200_ERROR_CUDA_MEMCPY);
+    CUDA_TRY(transfer(s, s->d_vals, const_cast<double*>(values), (size_t)s->nnz_in * sizeof(double), true), B200_ERROR_CUDA_MEMCPY);
     int32_t rc = solver_b200_factorize_device(s, s->d_vals);
     if (effective_matching) *effective_matching = s->effective_matching;
     if (effective_pivoting) *effective_pivoting = s->effective_pivoting;
@@ -1603,7 +1720,7 @@ int32_t solver_b200_factorize_coo(struct InterfaceB200* s, int32_t* effective_ma
     s->factorized = false;
     CUDA_TRY(cudaSetDevice(s->device), B200_ERROR_NOT_AVAILABLE);
     clear_fac_under_h2d(s);
-    CUDA_TRY(cudaMemcpyAsync(s->d_coo_vals, coo_values, (size_t)s->nnz_coo * sizeof(double), cudaMemcpyHostToDevice, s->stream), B200_ERROR_CUDA_MEMCPY);
+    CUDA_TRY(transfer(s, s->d_coo_vals, const_cast<double*>(coo_values), (size_t)s->nnz_coo * sizeof(double), true), B200_ERROR_CUDA_MEMCPY);
     int32_t rc = solver_b200_factorize_coo_device(s, s->d_coo_vals);
     if (effective_matching) *effective_matching = s->effective_matching;
     if (effective_pivoting) *effective_pivoting = s->effective_pivoting;
@@ -1710,10 +1827,10 @@ int32_t solver_b200_solve(struct InterfaceB200* s, double* x, const double* rhs,
     if (!x || !rhs) return B200_ERROR_NULL_POINTER;
     s->verbose = verbose;
     CUDA_TRY(cudaSetDevice(s->device), B200_ERROR_NOT_AVAILABLE);
-    CUDA_TRY(cudaMemcpyAsync(s->d_b, rhs, (size_t)s->n * sizeof(double), cudaMemcpyHostToDevice, s->stream), B200_ERROR_CUDA_MEMCPY);
+    CUDA_TRY(transfer(s, s->d_b, const_cast<double*>(rhs), (size_t)s->n * sizeof(double), true), B200_ERROR_CUDA_MEMCPY);
     int32_t rc = solver_b200_solve_device(s, s->d_x, s->d_b);
     if (rc != 0) return rc;
-    CUDA_TRY(cudaMemcpyAsync(x, s->d_x, (size_t)s->n * sizeof(double), cudaMemcpyDeviceToHost, s->stream), B200_ERROR_CUDA_MEMCPY);
+    CUDA_TRY(transfer(s, s->d_x, x, (size_t)s->n * sizeof(double), false), B200_ERROR_CUDA_MEMCPY);
     CUDA_TRY(cudaStreamSynchronize(s->stream), B200_ERROR_CUDA_SYNCHRONIZE);
     if (verbose)
         printf("solver_b200_solve: solution completed: %d refinement step(s), ||b-Ax||/||b|| = %.3e, %.3f ms (device)\n",

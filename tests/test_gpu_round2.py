@@ -314,3 +314,40 @@ def test_identical_patterns_share_the_host_analysis():
     s3 = rb.SolverB200()
     s3.factorize(rb.CooMatrix.from_triplets(n3, n3, ai3, aj3, ax3, rb.Sym.No))
     assert s3.device_stats()["plan_cache_hit"] == 0.0
+
+
+# ---- pageable host buffers: striped staging through pinned memory must move the same bytes as the plain copies --------------
+def test_staged_transfers_of_pageable_buffers_are_exact():
+    import ctypes
+
+    import torch
+
+    coo = helpers.laplacian_2d_coo(760)  # n = 577,600: values (23 MB), rhs and x (4.6 MB each) all take the staged path
+    n = coo.nrow
+    b = np.sin(0.01 * np.arange(n)) + 2.0
+    xs = {}
+    for staged in (1.0, 0.0):
+        sol = rb.SolverB200()
+        sol.set_option("staged_copy", staged)
+        sol.factorize(coo)
+        x = np.zeros(n)
+        sol.solve(x, b)
+        sol.factorize(coo)  # a second round trip reuses the staging buffers and their events
+        x2 = np.full(n, np.nan)
+        sol.solve(x2, b)
+        assert np.array_equal(x, x2)
+        xs[staged] = x
+        if staged:
+            # an odd size that divides neither into stripes nor into pieces, straight through the extension entry points
+            src = np.random.default_rng(3).standard_normal(1_234_567)
+            dst = np.zeros_like(src)
+            dev = torch.empty(src.size, dtype=torch.float64, device="cuda")
+            vp = ctypes.c_void_p
+            assert sol._lib.solver_b200_copy_h2d(sol.solver, vp(dev.data_ptr()), vp(src.ctypes.data), src.nbytes) == 0
+            assert sol._lib.solver_b200_copy_d2h(sol.solver, vp(dst.ctypes.data), vp(dev.data_ptr()), dst.nbytes) == 0
+            assert np.array_equal(src, dst)
+            torch.cuda.synchronize()
+            assert np.array_equal(dev.cpu().numpy(), src)
+    assert np.array_equal(xs[1.0], xs[0.0])
+    n2, ai, aj, ax = helpers.laplacian_2d_triplets(760)
+    assert helpers.host_rel_residual(n2, ai, aj, ax, xs[1.0], b) <= TOL_RESIDUAL
