@@ -32,6 +32,8 @@
 #include <thread>
 #include <memory>
 #include <mutex>
+#include <condition_variable>
+#include <functional>
 
 using namespace b200;
 
@@ -57,6 +59,66 @@ static const int NSC = 3;
 static const int SC_MAXF[NSC] = {32, 256, 1 << 30};
 static const int SC_THREADS[NSC] = {32, 128, 256};
 static const int SC_MAXP[NSC] = {32, B200_MAXP, B200_MAXP};
+
+// A few persistent helper threads per handle for the striped host <-> device transfers (spawning threads per transfer cost
+// ~0.15 ms, three times per step).  run(n, f) executes f(0) .. f(n-1): f(n-1) on the calling thread, the rest on the workers.
+struct StripePool {
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv_go, cv_done;
+    std::function<void(int)> job;
+    int generation = 0, njobs = 0, pending = 0;
+    bool stop = false;
+    void ensure(int n) {
+        while ((int)workers.size() < n) {
+            const int t = (int)workers.size();
+            workers.emplace_back([this, t]() {
+                int seen = 0;
+                for (;;) {
+                    std::function<void(int)> f;
+                    {
+                        std::unique_lock<std::mutex> lk(mu);
+                        cv_go.wait(lk, [&]() { return stop || generation != seen; });
+                        if (stop) return;
+                        seen = generation;
+                        if (t >= njobs) continue;
+                        f = job;
+                    }
+                    f(t);
+                    {
+                        std::lock_guard<std::mutex> lk(mu);
+                        if (--pending == 0) cv_done.notify_all();
+                    }
+                }
+            });
+        }
+    }
+    void run(int n, const std::function<void(int)>& f) {
+        if (n > 1) {
+            ensure(n - 1);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                job = f, njobs = n - 1, pending = n - 1, generation++;
+            }
+            cv_go.notify_all();
+        }
+        f(n - 1);
+        if (n > 1) {
+            std::unique_lock<std::mutex> lk(mu);
+            cv_done.wait(lk, [&]() { return pending == 0; });
+        }
+    }
+    void shutdown() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv_go.notify_all();
+        for (auto& w : workers) w.join();
+        workers.clear();
+        stop = false;
+    }
+};
 
 // Device memory of a handle comes from a few large chunks instead of ~70 separate cudaMalloc calls: on the B200 boxes a
 // cudaMalloc costs 0.1 ms on a quiet device but ~5-10 ms next to live handles / instantiated graphs (profiles/r4f_init_probe.txt:
@@ -162,13 +224,14 @@ struct InterfaceB200 {
     int strict_residual = 0; // 1: solve returns B200_ERROR_SOLVE+7 whenever ||b-Ax||/||b|| > 10 ir_tol after refinement
 
     // Host buffers of the callers (Rust Vec<f64>, numpy arrays) are pageable: a plain cudaMemcpyAsync from them is staged by the
-    // driver at a fraction of the PCIe rate.  Large pageable transfers are striped over a few threads, each copying its stripe
+    // driver at a fraction of the PCIe rate.  Large pageable transfers are striped over a few (pooled) threads, each copying its stripe
     // through its own pair of pinned staging buffers (memcpy of piece k+1 overlaps the DMA of piece k); pinned buffers (the
     // benchmark's) go straight to the copy engine.  Option "staged_copy" / B200_STAGED_COPY = 0 restores the plain copies.
-    static const int NST = 4;                     // stripes (threads)
+    static const int NST = 8;                     // stripes (threads)
     static const size_t STAGE_PIECE = (size_t)2 << 20; // bytes per staging buffer
     char* h_stage = nullptr;                      // NST x 2 pinned buffers
-    cudaEvent_t ev_stage[2 * NST] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_stage[2 * NST] = {};
+    StripePool stripe_pool;
     int staged_copy = 1;
     SlabSet slabs; // device memory of the plan arrays, work vectors and arenas (released as a whole)
     std::shared_ptr<Plan> plan_sp = std::make_shared<Plan>(); // shared (read-only) with the plan cache and with other handles of the same pattern
@@ -378,6 +441,7 @@ void release_device(InterfaceB200* s) {
     if (s->h_norms) cudaFreeHost(s->h_norms), s->h_norms = nullptr;
     if (s->h_counters) cudaFreeHost(s->h_counters), s->h_counters = nullptr;
     s->slabs.release();
+    s->stripe_pool.shutdown();
     if (s->h_stage) cudaFreeHost(s->h_stage), s->h_stage = nullptr;
     for (int i = 0; i < 2 * InterfaceB200::NST; i++)
         if (s->ev_stage[i]) cudaEventDestroy(s->ev_stage[i]), s->ev_stage[i] = nullptr;
@@ -1606,21 +1670,15 @@ cudaError_t transfer(InterfaceB200* s, void* dev, void* host, size_t bytes, bool
     if (plain)
         return to_device ? cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, s->stream)
                          : cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, s->stream);
-    const int nt = InterfaceB200::NST;
+    // stripes of at least one piece (small vectors use fewer threads), 256-byte aligned
+    const int nt = (int)std::max<size_t>(1, std::min<size_t>(InterfaceB200::NST, bytes / InterfaceB200::STAGE_PIECE));
     const size_t stripe = ((bytes + nt - 1) / nt + 255) & ~(size_t)255;
     cudaError_t err[InterfaceB200::NST];
-    std::vector<std::thread> th;
-    for (int t = 0; t < nt; t++) {
+    for (int t = 0; t < InterfaceB200::NST; t++) err[t] = cudaSuccess;
+    s->stripe_pool.run(nt, [&](int t) {
         const size_t lo = std::min(bytes, (size_t)t * stripe), hi = std::min(bytes, lo + stripe);
-        err[t] = cudaSuccess;
-        if (lo >= hi) continue;
-        if (t == nt - 1 || hi == bytes) { // the calling thread takes the last stripe
-            err[t] = stripe_copy(s, t, (char*)dev, (char*)host, lo, hi, to_device);
-            break;
-        }
-        th.emplace_back([=, &err]() { err[t] = stripe_copy(s, t, (char*)dev, (char*)host, lo, hi, to_device); });
-    }
-    for (auto& x : th) x.join();
+        if (lo < hi) err[t] = stripe_copy(s, t, (char*)dev, (char*)host, lo, hi, to_device);
+    });
     for (int t = 0; t < nt; t++)
         if (err[t] != cudaSuccess) return err[t];
     return cudaSuccess;
