@@ -227,8 +227,9 @@ struct InterfaceB200 {
     // driver at a fraction of the PCIe rate.  Large pageable transfers are striped over a few (pooled) threads, each copying its stripe
     // through its own pair of pinned staging buffers (memcpy of piece k+1 overlaps the DMA of piece k); pinned buffers (the
     // benchmark's) go straight to the copy engine.  Option "staged_copy" / B200_STAGED_COPY = 0 restores the plain copies.
-    static const int NST = 8;                     // stripes (threads)
-    static const size_t STAGE_PIECE = (size_t)2 << 20; // bytes per staging buffer
+    static const int NST = 4;                     // stripes (threads): the host's memcpy rate, not the thread count, bounds the staged path
+                                                  // (8 stripes: 10.0 ms per step, 4: 10.1 ms, plain cudaMemcpyAsync: 10.9-11.6 ms; pinned: 7.7 ms)
+    static const size_t STAGE_PIECE = (size_t)1 << 20; // bytes per staging buffer (8 MB of pinned memory per handle, allocated at the first staged transfer)
     char* h_stage = nullptr;                      // NST x 2 pinned buffers
     cudaEvent_t ev_stage[2 * NST] = {};
     StripePool stripe_pool;
@@ -1666,7 +1667,7 @@ cudaError_t stripe_copy(InterfaceB200* s, int t, char* dev, char* host, size_t l
 // H2D: enqueued on the handle's stream (ordered like a cudaMemcpyAsync).  D2H: pinned destination -> enqueued; pageable
 // destination -> complete when the call returns.
 cudaError_t transfer(InterfaceB200* s, void* dev, void* host, size_t bytes, bool to_device) {
-    const bool plain = !s->staged_copy || bytes < 2 * InterfaceB200::STAGE_PIECE || host_pointer_is_pinned(host) || !staging_ready(s);
+    const bool plain = !s->staged_copy || bytes < 4 * InterfaceB200::STAGE_PIECE || host_pointer_is_pinned(host) || !staging_ready(s);
     if (plain)
         return to_device ? cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, s->stream)
                          : cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, s->stream);
