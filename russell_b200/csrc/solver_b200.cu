@@ -318,7 +318,6 @@ struct InterfaceB200 {
     cudaStream_t inv_side = nullptr;
     cudaEvent_t ev_inv0 = nullptr, ev_inv1 = nullptr;
     int inv_overlap = 1;      // option "inv_overlap" / B200_INV_OVERLAP
-    int bwd_sub_occ = 4;      // option "bwd_sub_occ": register cap of the backward subtree kernel, in CTAs per SM (4 = none)
     int inv_split_level = -1; // -1: no early branch
     bool pack_early = false;  // the subtree fronts all lie below the split level
     int fused_variant = 2;  // 0 = shared-memory LU (k_front_fused), 1 = register-resident (k_front_fused_w8) for f <= 64,
@@ -870,13 +869,8 @@ int enqueue_sweep_levels(InterfaceB200* s, int* launches) {
         }
     }
     if (s->n_subtrees > 0) {
-        const int gsub = (s->n_subtrees + B200_SUBW_WARPS - 1) / B200_SUBW_WARPS;
-        if (s->bwd_sub_occ >= 6)
-            k_bwd_stree_w<6><<<gsub, 32 * B200_SUBW_WARPS, 0, s->stream>>>(s->d_subtrees, s->n_subtrees, s->d_fac, s->d_dinv, s->d_st_tgt, s->d_st_pu, s->d_rows, s->d_z, s->d_xp);
-        else if (s->bwd_sub_occ == 5)
-            k_bwd_stree_w<5><<<gsub, 32 * B200_SUBW_WARPS, 0, s->stream>>>(s->d_subtrees, s->n_subtrees, s->d_fac, s->d_dinv, s->d_st_tgt, s->d_st_pu, s->d_rows, s->d_z, s->d_xp);
-        else
-            k_bwd_stree_w<4><<<gsub, 32 * B200_SUBW_WARPS, 0, s->stream>>>(s->d_subtrees, s->n_subtrees, s->d_fac, s->d_dinv, s->d_st_tgt, s->d_st_pu, s->d_rows, s->d_z, s->d_xp);
+        k_bwd_stree_w<<<(s->n_subtrees + B200_SUBW_WARPS - 1) / B200_SUBW_WARPS, 32 * B200_SUBW_WARPS, 0, s->stream>>>(
+            s->d_subtrees, s->n_subtrees, s->d_fac, s->d_dinv, s->d_st_tgt, s->d_st_pu, s->d_rows, s->d_z, s->d_xp);
         cnt++;
     }
     if (launches) *launches = cnt;
@@ -1069,7 +1063,6 @@ int32_t solver_b200_set_option(struct InterfaceB200* s, const char* key, double 
     else if (k == "use_front_warp") s->use_front_warp = value != 0.0;
     else if (k == "use_level_fork") s->use_level_fork = value != 0.0;
     else if (k == "inv_overlap") s->inv_overlap = value != 0.0;
-    else if (k == "bwd_sub_occ") s->bwd_sub_occ = (int)value;
     else if (k == "use_fused") s->use_fused = value != 0.0;
     else if (k == "use_top") s->use_top = value != 0.0;
     else if (k == "trace") s->want_trace = value != 0.0;

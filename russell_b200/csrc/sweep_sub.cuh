@@ -169,8 +169,7 @@ __global__ void __launch_bounds__(32 * B200_SUBW_WARPS) k_fwd_stree_w(const Subt
     }
 }
 
-template <int MINB> // CTAs per SM the register allocation aims at (1: no cap = 108 registers, 4 CTAs; 5: 96; 6: 80 with a few spills)
-__global__ void __launch_bounds__(32 * B200_SUBW_WARPS, MINB) k_bwd_stree_w(const SubtreeDev* __restrict__ trees, int ntrees,
+__global__ void __launch_bounds__(32 * B200_SUBW_WARPS) k_bwd_stree_w(const SubtreeDev* __restrict__ trees, int ntrees,
                                                                        const double* __restrict__ fac, const double* __restrict__ dpack,
                                                                        const unsigned short* __restrict__ tgt_all, const uchar2* __restrict__ pu_all,
                                                                        const int* __restrict__ rows_all, const double* __restrict__ zv,
