@@ -87,11 +87,31 @@ void postorder_tree(const std::vector<int>& parent, const std::vector<int>& weig
         for (int v = 0; v < n; v++) cidx[fill[parent[v] < 0 ? n : parent[v]]++] = v;
     }
     if (!weight.empty()) {
-        for (int v = 0; v <= n; v++) {
-            int a = cptr[v], b = cptr[v + 1];
-            if (b - a > 1)
-                std::stable_sort(cidx.begin() + a, cidx.begin() + b, [&](int x, int y) { return weight[x] < weight[y]; });
+        parallel_rows(n + 1, [&](int v0, int v1) { // every vertex sorts its own child list
+            for (int v = v0; v < v1; v++) {
+                int a = cptr[v], b = cptr[v + 1];
+                if (b - a > 1)
+                    std::stable_sort(cidx.begin() + a, cidx.begin() + b, [&](int x, int y) { return weight[x] < weight[y]; });
+            }
+        });
+    }
+    // No traversal is needed: a vertex is emitted right after its subtree, so its position is (start of its subtree) + (size
+    // of its subtree) - 1, and the subtrees of the children of one vertex follow each other in list order.  Sizes bottom-up
+    // and starts top-down are plain loops because parents carry larger indices than their children (elimination trees,
+    // supernode trees); the general case falls back to an explicit depth-first traversal.
+    bool increasing = true;
+    for (int v = 0; v < n && increasing; v++) increasing = parent[v] < 0 || parent[v] > v;
+    post.assign(n, 0);
+    if (increasing) {
+        std::vector<int> size(n + 1, 1), start(n + 1, 0);
+        size[n] = 0;
+        for (int v = 0; v < n; v++) size[parent[v] < 0 ? n : parent[v]] += size[v];
+        for (int v = n; v >= 0; v--) {
+            int at = start[v];
+            for (int e = cptr[v]; e < cptr[v + 1]; e++) start[cidx[e]] = at, at += size[cidx[e]];
         }
+        parallel_rows(n, [&](int a, int b) { for (int v = a; v < b; v++) post[start[v] + size[v] - 1] = v; });
+        return;
     }
     post.clear();
     post.reserve(n);
@@ -432,13 +452,17 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
         const int nf = (int)fund.size();
         P.nsuper_fundamental = nf;
         std::vector<int> c2s(n);
-        for (int s = 0; s < nf; s++)
-            for (int j = fund[s].first; j < fund[s].first + fund[s].ncols; j++) c2s[j] = s;
+        parallel_rows(nf, [&](int s0, int s1) {
+            for (int s = s0; s < s1; s++)
+                for (int j = fund[s].first; j < fund[s].first + fund[s].ncols; j++) c2s[j] = s;
+        });
         std::vector<int> fpar(nf, -1);
-        for (int s = 0; s < nf; s++) {
-            int lastc = fund[s].first + fund[s].ncols - 1;
-            fpar[s] = parent[lastc] < 0 ? -1 : c2s[parent[lastc]];
-        }
+        parallel_rows(nf, [&](int s0, int s1) {
+            for (int s = s0; s < s1; s++) {
+                int lastc = fund[s].first + fund[s].ncols - 1;
+                fpar[s] = parent[lastc] < 0 ? -1 : c2s[parent[lastc]];
+            }
+        });
         // children lists of the fundamental supernode tree
         std::vector<int> cptr(nf + 1, 0), cidx(nf);
         for (int s = 0; s < nf; s++)
@@ -578,13 +602,17 @@ int analyze(int n, const int* rowptr, const int* colidx, const double* vals, boo
     const int ns = (int)grp.size();
     P.nsuper_relaxed = ns;
     std::vector<int> col2sn(n);
-    for (int s = 0; s < ns; s++)
-        for (int j = grp[s].first; j < grp[s].first + grp[s].ncols; j++) col2sn[j] = s;
+    parallel_rows(ns, [&](int s0, int s1) {
+        for (int s = s0; s < s1; s++)
+            for (int j = grp[s].first; j < grp[s].first + grp[s].ncols; j++) col2sn[j] = s;
+    });
     std::vector<int> sparent(ns, -1);
-    for (int s = 0; s < ns; s++) {
-        int lastc = grp[s].first + grp[s].ncols - 1;
-        sparent[s] = parent[lastc] < 0 ? -1 : col2sn[parent[lastc]];
-    }
+    parallel_rows(ns, [&](int s0, int s1) {
+        for (int s = s0; s < s1; s++) {
+            int lastc = grp[s].first + grp[s].ncols - 1;
+            sparent[s] = parent[lastc] < 0 ? -1 : col2sn[parent[lastc]];
+        }
+    });
 
     if (opt.verbose >= 2) fprintf(stderr, "b200 analyze:   phase amalgamation done at %.3f s\n", now_s() - t0);
     // ---- row structure of every supernode (rows beyond its last column, ascending) ----------------------
