@@ -318,8 +318,6 @@ struct InterfaceB200 {
     cudaStream_t inv_side = nullptr;
     cudaEvent_t ev_inv0 = nullptr, ev_inv1 = nullptr;
     int inv_overlap = 1;      // option "inv_overlap" / B200_INV_OVERLAP
-    int schur_ca = 0;         // option "schur_ca": Schur launches of at least schur_ca_min tiles use the cp.async / 3-CTA build
-    int schur_ca_min = 600;
     int inv_split_level = -1; // -1: no early branch
     bool pack_early = false;  // the subtree fronts all lie below the split level
     int fused_variant = 2;  // 0 = shared-memory LU (k_front_fused), 1 = register-resident (k_front_fused_w8) for f <= 64,
@@ -780,10 +778,6 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
         int nsch = lv.schur_ptr[l + 1] - lv.schur_ptr[l];
         if (nsch > 0) {
             if (s->schur_variant >= 1)
-                if (s->schur_ca && nsch >= s->schur_ca_min) // wide launches: cp.async operands, three CTAs per SM
-                    k_schur_dmma_ca<<<nsch, 256, smem_schur_dmma(), s->stream>>>(s->d_schur + lv.schur_ptr[l], s->d_nodes, s->d_fac, s->d_cb, s->d_lperm,
-                                                                                 s->d_upiv, s->d_amax, s->pivot_eps, s->d_counters);
-                else
                 k_schur_dmma<<<nsch, 256, smem_schur_dmma(), s->stream>>>(s->d_schur + lv.schur_ptr[l], s->d_nodes, s->d_fac, s->d_cb, s->d_lperm, s->d_upiv,
                                                                           s->d_amax, s->pivot_eps, s->d_counters);
             else
@@ -1069,8 +1063,6 @@ int32_t solver_b200_set_option(struct InterfaceB200* s, const char* key, double 
     else if (k == "use_front_warp") s->use_front_warp = value != 0.0;
     else if (k == "use_level_fork") s->use_level_fork = value != 0.0;
     else if (k == "inv_overlap") s->inv_overlap = value != 0.0;
-    else if (k == "schur_ca") s->schur_ca = value != 0.0;
-    else if (k == "schur_ca_min") s->schur_ca_min = (int)value;
     else if (k == "use_fused") s->use_fused = value != 0.0;
     else if (k == "use_top") s->use_top = value != 0.0;
     else if (k == "trace") s->want_trace = value != 0.0;
@@ -1497,8 +1489,6 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     CUDA_TRY(cudaFuncSetAttribute(k_panel_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_PW_SMEM), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_schur_fma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_schur_fma(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_schur_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024), B200_ERROR_NOT_AVAILABLE);
-    CUDA_TRY(cudaFuncSetAttribute(k_schur_dmma_ca, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024), B200_ERROR_NOT_AVAILABLE);
-    CUDA_TRY(cudaFuncSetAttribute(k_schur_dmma_ca, cudaFuncAttributePreferredSharedMemoryCarveout, 100), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_assemble_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, B200_ASM_SMEM_MAX), B200_ERROR_NOT_AVAILABLE);
     (void)W;
     if (s->n_top_items > 0) {
