@@ -162,7 +162,9 @@ int32_t solver_b200_get_stats(struct InterfaceB200 *solver, double *out, int32_t
  * 2 = DMMA + the tcgen05 int8 Ozaki kernel for fronts with at least "ozaki_min_u" update rows), "fuse_chain", "use_fused",
  * "fused_variant", "fused_maxf", "fused_w8_max", "use_front_warp" (1 = one warp per front for the large fused launches, 0 = k_front_fused), "use_level_fork" (1 = the independent
  * launches of a tree level run on parallel branches of the graph), "inv_overlap" (1 = the pivot-block inverses of the fronts below
- * the chain levels run on a low-priority branch underneath those levels),
+ * the chain levels run on a low-priority branch underneath those levels), "schur_front_nt" (fronts with at least this many rows of
+ * 64 x 64 Schur tiles get a launch of their own whose grid enumerates the tiles; smaller fronts share a launch over a tile list),
+ * "staged_copy" (1 = large pageable host buffers are staged through pinned memory by a few threads),
  * "use_leaf_reg", "asm_variant", "use_top", "top_max_nodes".  Unknown keys return
  * B200_ERROR_NOT_AVAILABLE. */
 int32_t solver_b200_set_option(struct InterfaceB200 *solver, const char *key, double value);

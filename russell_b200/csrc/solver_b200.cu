@@ -188,6 +188,11 @@ struct LevelLists {
     // schur_variant 2: fronts with u >= ozaki_min_u take the tcgen05 kernel (ozaki_tc.cuh)
     std::vector<int> oz_split_ptr, oz_item_ptr, oz_rows_max; // nlevels+1 / nlevels+1 / nlevels
     std::vector<int> diag_cnt; // per level: big fronts that need their own pivot-block launch (listed first in their class)
+    struct SchurFront { // a front whose Schur tiles are enumerated by the launch grid (k_schur_dmma_front)
+        int node, nt, parent, lookahead;
+    };
+    std::vector<SchurFront> schur_fronts;
+    std::vector<int> schur_front_ptr; // per level
     size_t oz_tile_bytes = 0, oz_scales = 0;                 // arena sizes (largest level)
 };
 
@@ -318,6 +323,7 @@ struct InterfaceB200 {
     cudaStream_t inv_side = nullptr;
     cudaEvent_t ev_inv0 = nullptr, ev_inv1 = nullptr;
     int inv_overlap = 1;      // option "inv_overlap" / B200_INV_OVERLAP
+    int schur_front_nt = 16;  // option "schur_front_nt": fronts with at least this many 64-row tile rows (u > 960) get a Schur launch of their own
     int inv_split_level = -1; // -1: no early branch
     bool pack_early = false;  // the subtree fronts all lie below the split level
     int fused_variant = 2;  // 0 = shared-memory LU (k_front_fused), 1 = register-resident (k_front_fused_w8) for f <= 64,
@@ -463,6 +469,8 @@ void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::ve
                       std::vector<int>& asm_ranges, std::vector<OzakiSplitItem>& oz_split, std::vector<OzakiItem>& oz_items) {
     const Plan& P = (*s->plan_sp);
     LevelLists& lv = s->lv;
+    lv.schur_fronts.clear();
+    lv.schur_front_ptr.assign(P.nlevels + 1, 0);
     lv.asm_ptr.assign(P.nlevels + 1, 0);
     lv.panel_ptr.assign(P.nlevels + 1, 0);
     lv.schur_ptr.assign(P.nlevels + 1, 0);
@@ -615,15 +623,19 @@ void build_work_lists(InterfaceB200* s, std::vector<AsmItem>& asm_items, std::ve
                     const int fuse_into = (par >= 0 && chain_fused(par)) ? par : -1;
                     const bool la = fuse_into >= 0 && s->fuse_diag && s->diag_variant == 4 && s->schur_variant >= 1;
                     if (la) diag_fused[par] = 1;
-                    for (int tj = 0; tj < nt; tj++)
-                        for (int ti = 0; ti < nt; ti++)
-                            schur_items.push_back({v, ti, tj, (la && ti == 0 && tj == 0) ? (fuse_into | B200_SCHUR_DIAG) : fuse_into});
+                    if (nt >= s->schur_front_nt && s->schur_variant >= 1) // a launch of its own, tiles from the grid
+                        lv.schur_fronts.push_back({v, nt, fuse_into, la ? 1 : 0});
+                    else
+                        for (int tj = 0; tj < nt; tj++)
+                            for (int ti = 0; ti < nt; ti++)
+                                schur_items.push_back({v, ti, tj, (la && ti == 0 && tj == 0) ? (fuse_into | B200_SCHUR_DIAG) : fuse_into});
                 }
             }
         }
         lv.asm_ptr[l + 1] = (int)asm_items.size();
         lv.panel_ptr[l + 1] = (int)panel_items.size();
         lv.schur_ptr[l + 1] = (int)schur_items.size();
+        lv.schur_front_ptr[l + 1] = (int)lv.schur_fronts.size();
         lv.oz_split_ptr[l + 1] = (int)oz_split.size(), lv.oz_item_ptr[l + 1] = (int)oz_items.size();
         lv.oz_tile_bytes = std::max(lv.oz_tile_bytes, lvl_tiles), lv.oz_scales = std::max(lv.oz_scales, lvl_scales);
     }
@@ -782,6 +794,12 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
                                                                           s->d_amax, s->pivot_eps, s->d_counters);
             else
                 k_schur_fma<<<nsch, 256, smem_schur_fma(W), s->stream>>>(s->d_schur + lv.schur_ptr[l], s->d_nodes, s->d_fac, s->d_cb);
+            cnt++;
+        }
+        for (int e = lv.schur_front_ptr[l]; e < lv.schur_front_ptr[l + 1]; e++) { // large fronts: one launch each, tiles from the grid
+            const LevelLists::SchurFront& sf = lv.schur_fronts[e];
+            k_schur_dmma_front<<<dim3(sf.nt, sf.nt), 256, smem_schur_dmma(), s->stream>>>(sf.node, sf.parent, sf.lookahead, s->d_nodes, s->d_fac, s->d_cb,
+                                                                                          s->d_lperm, s->d_upiv, s->d_amax, s->pivot_eps, s->d_counters);
             cnt++;
         }
         join();
@@ -1063,6 +1081,7 @@ int32_t solver_b200_set_option(struct InterfaceB200* s, const char* key, double 
     else if (k == "use_front_warp") s->use_front_warp = value != 0.0;
     else if (k == "use_level_fork") s->use_level_fork = value != 0.0;
     else if (k == "inv_overlap") s->inv_overlap = value != 0.0;
+    else if (k == "schur_front_nt") s->schur_front_nt = std::max(1, (int)value);
     else if (k == "use_fused") s->use_fused = value != 0.0;
     else if (k == "use_top") s->use_top = value != 0.0;
     else if (k == "trace") s->want_trace = value != 0.0;
@@ -1489,6 +1508,7 @@ int32_t solver_b200_initialize(struct InterfaceB200* s, int32_t ordering, int32_
     CUDA_TRY(cudaFuncSetAttribute(k_panel_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B200_PW_SMEM), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_schur_fma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_schur_fma(B200_MAXP)), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_schur_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024), B200_ERROR_NOT_AVAILABLE);
+    CUDA_TRY(cudaFuncSetAttribute(k_schur_dmma_front, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024), B200_ERROR_NOT_AVAILABLE);
     CUDA_TRY(cudaFuncSetAttribute(k_assemble_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, B200_ASM_SMEM_MAX), B200_ERROR_NOT_AVAILABLE);
     (void)W;
     if (s->n_top_items > 0) {

@@ -265,7 +265,8 @@ def test_factor_panels_match_host_walk_lower_and_saddle():
                                   {"diag_variant": 4, "use_fused": 0, "panel_width": 37}, {"diag_variant": 4, "use_fused": 0, "panel_width": 5},
                                   {"asm_variant": 0}, {"asm_variant": 0, "use_fused": 0, "panel_width": 13}, {"asm_variant": 1, "use_fused": 0, "panel_width": 13},
                                   {"nd_leaf": 96}, {"schur_variant": 2, "ozaki_min_u": 64}, {"schur_variant": 2, "ozaki_min_u": 100, "panel_width": 37},
-                                  {"schur_variant": 2, "ozaki_min_u": 1, "use_fused": 0, "panel_width": 20}])
+                                  {"schur_variant": 2, "ozaki_min_u": 1, "use_fused": 0, "panel_width": 20},
+                                  {"schur_front_nt": 2}, {"schur_front_nt": 1, "use_fused": 0, "panel_width": 37}, {"schur_front_nt": 1000}])
 def test_kernel_variants_match_host_walk(opts):
     # every alternative code path (shared-memory vs register-resident pivot-block LU, fused vs multi-kernel fronts,
     # persistent vs per-level sweeps) against the scalar walk, on a grid with fronts above the fused limit
