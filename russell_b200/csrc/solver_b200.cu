@@ -323,7 +323,9 @@ struct InterfaceB200 {
     cudaStream_t inv_side = nullptr;
     cudaEvent_t ev_inv0 = nullptr, ev_inv1 = nullptr;
     int inv_overlap = 1;      // option "inv_overlap" / B200_INV_OVERLAP
-    int schur_front_nt = 16;  // option "schur_front_nt": fronts with at least this many 64-row tile rows (u > 960) get a Schur launch of their own
+    int schur_front_nt = 64;  // option "schur_front_nt": fronts with at least this many rows of 64 x 64 tiles (u > 4032: 4096+ tiles, a full
+                              // GPU by themselves) get a Schur launch of their own.  (16 was measured at config 2: its top chain links then
+                              // leave the shared launch of their level, 5.70 -> 6.08 ms, profiles/r4p_schur_front.txt)
     int inv_split_level = -1; // -1: no early branch
     bool pack_early = false;  // the subtree fronts all lie below the split level
     int fused_variant = 2;  // 0 = shared-memory LU (k_front_fused), 1 = register-resident (k_front_fused_w8) for f <= 64,
