@@ -323,7 +323,6 @@ struct InterfaceB200 {
     cudaStream_t inv_side = nullptr;
     cudaEvent_t ev_inv0 = nullptr, ev_inv1 = nullptr;
     int inv_overlap = 1;      // option "inv_overlap" / B200_INV_OVERLAP
-    int schur_prefetch = 0;   // option "schur_prefetch": the Schur tiles request their C tile into L2 before the operand loads
     int schur_front_nt = 64;  // option "schur_front_nt": fronts with at least this many rows of 64 x 64 tiles (u > 4032: 4096+ tiles, a full
                               // GPU by themselves) get a Schur launch of their own.  (16 was measured at config 2: its top chain links then
                               // leave the shared launch of their level, 5.70 -> 6.08 ms, profiles/r4p_schur_front.txt)
@@ -794,7 +793,7 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
         if (nsch > 0) {
             if (s->schur_variant >= 1)
                 k_schur_dmma<<<nsch, 256, smem_schur_dmma(), s->stream>>>(s->d_schur + lv.schur_ptr[l], s->d_nodes, s->d_fac, s->d_cb, s->d_lperm, s->d_upiv,
-                                                                          s->d_amax, s->pivot_eps, s->d_counters, s->schur_prefetch);
+                                                                          s->d_amax, s->pivot_eps, s->d_counters);
             else
                 k_schur_fma<<<nsch, 256, smem_schur_fma(W), s->stream>>>(s->d_schur + lv.schur_ptr[l], s->d_nodes, s->d_fac, s->d_cb);
             cnt++;
@@ -802,7 +801,7 @@ int enqueue_levels(InterfaceB200* s, int* launches) {
         for (int e = lv.schur_front_ptr[l]; e < lv.schur_front_ptr[l + 1]; e++) { // large fronts: one launch each, tiles from the grid
             const LevelLists::SchurFront& sf = lv.schur_fronts[e];
             k_schur_dmma_front<<<dim3(sf.nt, sf.nt), 256, smem_schur_dmma(), s->stream>>>(sf.node, sf.parent, sf.lookahead, s->d_nodes, s->d_fac, s->d_cb,
-                                                                                          s->d_lperm, s->d_upiv, s->d_amax, s->pivot_eps, s->d_counters, s->schur_prefetch);
+                                                                                          s->d_lperm, s->d_upiv, s->d_amax, s->pivot_eps, s->d_counters);
             cnt++;
         }
         join();
@@ -1029,7 +1028,6 @@ struct InterfaceB200* solver_b200_new(void) {
     if ((e = getenv("B200_USE_LEAF_REG"))) s->use_leaf_reg = atoi(e);
     if ((e = getenv("B200_USE_LEVEL_FORK"))) s->use_level_fork = atoi(e);
     if ((e = getenv("B200_INV_OVERLAP"))) s->inv_overlap = atoi(e);
-    if ((e = getenv("B200_SCHUR_PREFETCH"))) s->schur_prefetch = atoi(e);
     if ((e = getenv("B200_STAGED_COPY"))) s->staged_copy = atoi(e);
     if ((e = getenv("B200_FUSED_W8_MAX"))) s->fused_w8_max = atoi(e);
     if ((e = getenv("B200_USE_LEAF_REG"))) s->use_leaf_reg = atoi(e);
@@ -1085,7 +1083,6 @@ int32_t solver_b200_set_option(struct InterfaceB200* s, const char* key, double 
     else if (k == "use_front_warp") s->use_front_warp = value != 0.0;
     else if (k == "use_level_fork") s->use_level_fork = value != 0.0;
     else if (k == "inv_overlap") s->inv_overlap = value != 0.0;
-    else if (k == "schur_prefetch") s->schur_prefetch = value != 0.0;
     else if (k == "schur_front_nt") s->schur_front_nt = std::max(1, (int)value);
     else if (k == "use_fused") s->use_fused = value != 0.0;
     else if (k == "use_top") s->use_top = value != 0.0;
