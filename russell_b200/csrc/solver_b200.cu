@@ -362,18 +362,55 @@ struct PlanCacheEntry {
 std::mutex g_plan_mu;
 std::vector<PlanCacheEntry> g_plan_cache; // most recent last, at most 3 entries
 
-void hash_pattern(int n, const int* rp, const int* ci, uint64_t& h1, uint64_t& h2) {
-    uint64_t a = 0x9e3779b97f4a7c15ull ^ (uint64_t)n, b = 0xc2b2ae3d27d4eb4full + (uint64_t)n;
-    auto mix = [&](uint64_t v) {
-        a = (a ^ v) * 0xff51afd7ed558ccdull, a ^= a >> 29;
-        b = (b + v) * 0xc4ceb9fe1a85ec53ull, b ^= b >> 31;
+// runs fn(chunk) for chunk = 0 .. nchunks-1 on a few threads (chunk boundaries are fixed by the caller, so results that are
+// combined in chunk order do not depend on the number of threads)
+template <class F>
+void for_chunks(int nchunks, F fn) {
+    unsigned nt = std::min<unsigned>(std::thread::hardware_concurrency(), 8u);
+    if (nt < 2 || nchunks < 4) {
+        for (int c = 0; c < nchunks; c++) fn(c);
+        return;
+    }
+    std::atomic<int> next{0};
+    auto work = [&]() {
+        for (int c = next++; c < nchunks; c = next++) fn(c);
     };
-    for (int i = 0; i <= n; i++) mix((uint32_t)rp[i]);
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; t++) th.emplace_back(work);
+    work();
+    for (auto& x : th) x.join();
+}
+
+// two independent 64-bit hashes of (n, row pointers, column indices): fixed chunks of 2^18 entries are hashed independently
+// (in parallel for large patterns) and their results chained in chunk order
+void hash_pattern(int n, const int* rp, const int* ci, uint64_t& h1, uint64_t& h2) {
+    struct H {
+        uint64_t a, b;
+        void mix(uint64_t v) {
+            a = (a ^ v) * 0xff51afd7ed558ccdull, a ^= a >> 29;
+            b = (b + v) * 0xc4ceb9fe1a85ec53ull, b ^= b >> 31;
+        }
+    };
+    const int CH = 1 << 18;
     const int nnz = rp[n];
-    int k = 0;
-    for (; k + 1 < nnz; k += 2) mix(((uint64_t)(uint32_t)ci[k] << 32) | (uint32_t)ci[k + 1]);
-    if (k < nnz) mix((uint32_t)ci[k]);
-    h1 = a, h2 = b;
+    const int c_rp = (int)(((long long)n + CH) / CH), c_ci = (int)(((long long)nnz + CH - 1) / CH);
+    std::vector<H> part((size_t)c_rp + c_ci);
+    for_chunks(c_rp + c_ci, [&](int c) {
+        H h{0x9e3779b97f4a7c15ull ^ (uint64_t)c, 0xc2b2ae3d27d4eb4full + (uint64_t)c};
+        if (c < c_rp) {
+            const int lo = c * CH, hi = (int)std::min<long long>((long long)n + 1, (long long)lo + CH);
+            for (int i = lo; i < hi; i++) h.mix((uint32_t)rp[i]);
+        } else {
+            const int lo = (c - c_rp) * CH, hi = (int)std::min<long long>(nnz, (long long)lo + CH);
+            int k = lo;
+            for (; k + 1 < hi; k += 2) h.mix(((uint64_t)(uint32_t)ci[k] << 32) | (uint32_t)ci[k + 1]);
+            if (k < hi) h.mix((uint32_t)ci[k]);
+        }
+        part[c] = h;
+    });
+    H tot{0x9e3779b97f4a7c15ull ^ (uint64_t)n, 0xc2b2ae3d27d4eb4full + (uint64_t)n};
+    for (const H& h : part) tot.mix(h.a), tot.mix(h.b);
+    h1 = tot.a, h2 = tot.b;
 }
 bool same_options(const AnalyzeOptions& x, const AnalyzeOptions& y) {
     return x.ordering == y.ordering && x.panel_width == y.panel_width && x.nd_leaf == y.nd_leaf && x.relax_small == y.relax_small &&
@@ -386,12 +423,17 @@ bool same_options(const AnalyzeOptions& x, const AnalyzeOptions& y) {
 bool values_need_matching(int matching, int n, const int* rp, const int* ci, const double* vals) {
     if (matching == 0) return false;
     if (matching == 1) return true;
-    for (int i = 0; i < n; i++) {
-        bool ok = false;
-        for (int k = rp[i]; k < rp[i + 1] && !ok; k++) ok = ci[k] == i && vals[k] != 0.0;
-        if (!ok) return true;
-    }
-    return false;
+    const int CH = 1 << 16;
+    std::atomic<int> weak{0};
+    for_chunks((n + CH - 1) / CH, [&](int c) {
+        const int lo = c * CH, hi = (int)std::min<long long>(n, (long long)lo + CH);
+        for (int i = lo; i < hi && !weak.load(std::memory_order_relaxed); i++) {
+            bool ok = false;
+            for (int k = rp[i]; k < rp[i + 1] && !ok; k++) ok = ci[k] == i && vals[k] != 0.0;
+            if (!ok) weak = 1;
+        }
+    });
+    return weak != 0;
 }
 
 // time spent in the allocations / copies of upload() by the calling thread (printed by initialize when verbose)
