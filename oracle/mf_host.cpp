@@ -358,5 +358,21 @@ void oracle_plan_nodes(void* h, int* p, int* u, int* level, int* parent) {
     Plan* P = (Plan*)h;
     for (int v = 0; v < P->nnodes; v++) p[v] = P->p[v], u[v] = P->u[v], level[v] = P->level[v], parent[v] = P->parent[v];
 }
+// FNV-1a over every array of the plan the device consumes: two runs of the analysis (serial / threaded) must agree bit for bit
+unsigned long long oracle_plan_hash(void* h) {
+    const Plan& P = *(Plan*)h;
+    unsigned long long x = 1469598103934665603ull;
+    auto fnv = [&x](const void* data, size_t bytes) {
+        const unsigned char* b = (const unsigned char*)data;
+        for (size_t i = 0; i < bytes; i++) x = (x ^ b[i]) * 1099511628211ull;
+    };
+#define HV(v) fnv((v).data(), (v).size() * sizeof((v)[0]))
+    HV(P.rowperm), HV(P.colperm), HV(P.c0), HV(P.p), HV(P.u), HV(P.parent), HV(P.level), HV(P.Loff), HV(P.Uoff), HV(P.Coff), HV(P.Doff);
+    HV(P.rows_ptr), HV(P.rows), HV(P.rel), HV(P.child_ptr), HV(P.child_idx), HV(P.level_ptr), HV(P.level_nodes), HV(P.in_sub);
+    HV(P.st_first), HV(P.st_root), HV(P.a_src), HV(P.a_dst), HV(P.a_scl), HV(P.full_ptr), HV(P.full_col), HV(P.full_src), HV(P.rscale), HV(P.cscale);
+#undef HV
+    fnv(&P.fac_size, sizeof(P.fac_size)), fnv(&P.cb_size, sizeof(P.cb_size)), fnv(&P.dinv_size, sizeof(P.dinv_size));
+    return x;
+}
 void oracle_plan_free(void* h) { delete (Plan*)h; }
 }

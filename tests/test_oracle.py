@@ -445,6 +445,42 @@ def test_threaded_nested_dissection_equals_serial():
     assert outs[0].startswith("0 ")
 
 
+def test_threaded_analysis_builds_the_same_plan_bit_for_bit():
+    # every array of the plan (permutations, front tree, row lists, relative indices, storage offsets incl. the contribution
+    # arena of the helper-thread allocator, scatter map) hashed in child processes: default threading, everything serial,
+    # every threaded stage forced (B200_PAR_FLOOR = 0)
+    import os
+    import subprocess
+    import sys
+
+    HERE = os.path.dirname(os.path.abspath(__file__))
+    ROOT = os.path.dirname(HERE)
+    code = ("import sys, ctypes; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import numpy as np, helpers\nfrom oracle import oracle\n"
+            "oracle.build()\n"
+            "lib = ctypes.CDLL(%r)\n"
+            "ip, dp = ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)\n"
+            "lib.oracle_plan_create.restype = ctypes.c_void_p\n"
+            "lib.oracle_plan_create.argtypes = [ctypes.c_int, ip, ip, dp] + [ctypes.c_int] * 5 + [ip]\n"
+            "lib.oracle_plan_hash.restype = ctypes.c_ulonglong\n"
+            "lib.oracle_plan_hash.argtypes = [ctypes.c_void_p]\n"
+            "out = []\n"
+            "for gen in (lambda: helpers.convection_diffusion_triplets(300), lambda: helpers.laplacian_3d_triplets(30), lambda: helpers.saddle_point_triplets(120)):\n"
+            "    n, ai, aj, ax = gen()\n"
+            "    bp, bj, bx = oracle.coo_to_csr(n, n, ai, aj, ax)\n"
+            "    nn = ctypes.c_int(0)\n"
+            "    h = lib.oracle_plan_create(n, bp.ctypes.data_as(ip), bj.ctypes.data_as(ip), bx.ctypes.data_as(dp), 0, 0, 2, 0, 0, ctypes.byref(nn))\n"
+            "    assert h\n"
+            "    out.append('%%d:%%016x' %% (nn.value, lib.oracle_plan_hash(h)))\n"
+            "print(' '.join(out))\n"
+            % (ROOT, HERE, os.path.join(ROOT, "oracle", "_build", "liboracle_mf.so")))
+    outs = []
+    for env_extra in ({}, {"B200_ND_SERIAL": "1"}, {"B200_PAR_FLOOR": "0"}):
+        env = dict(os.environ, **env_extra)
+        outs.append(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout.strip())
+    assert outs[0] == outs[1] == outs[2] and len(outs[0].split()) == 3, outs
+
+
 def test_host_walk_unstructured_graphs():
     # irregular graphs (k-nearest-neighbour meshes in 2D and 3D): the level-set separators are shrunk by the
     # minimum-vertex-cover refinement (ordering.cpp: shrink_separator_by_cover); the walk must still solve the system
